@@ -1,0 +1,163 @@
+"""SessionBatch — host handle over N independent game sessions resident in HBM.
+
+Batch-level mirror of the reference's per-room graph run (reference agent/game_agent_v2.py:1571-1587:
+InitialRouterNode -> BotBehaviorNode -> PhaseNode -> RefereeNode): `step()` is one such run for every
+non-terminal session.  Everything numeric happens in libgame_engine_b200.so; NumPy arrays here are only
+host buffers handed across the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .compiler import CompiledGame
+
+
+class Table:
+    """Owns a ge_table handle."""
+
+    def __init__(self, game: CompiledGame):
+        self.game = game
+        L = capi.lib()
+        self._h = ctypes.c_void_p()
+        self._blob = ctypes.create_string_buffer(game.blob, len(game.blob))
+        capi.check(L.ge_table_create(ctypes.cast(self._blob, ctypes.c_void_p), len(game.blob), ctypes.byref(self._h)))
+        self.record_size = int(L.ge_table_record_size(self._h))
+        assert self.record_size == game.record_size
+
+    def close(self) -> None:
+        if self._h:
+            capi.lib().ge_table_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SessionBatch:
+    def __init__(self, table: Table, n_sessions: int, first_session_id: int = 0, seed: int = 0, device: int = 0,
+                 kernel: str = "auto"):
+        self.table = table
+        self.n = int(n_sessions)
+        self.first_session_id = int(first_session_id)
+        self.seed = int(seed)
+        self.device = int(device)
+        L = capi.lib()
+        self._h = ctypes.c_void_p()
+        capi.check(L.ge_batch_create(table._h, device, self.n, self.first_session_id, self.seed, ctypes.byref(self._h)))
+        self.set_kernel(kernel)
+
+    # ---- control
+    def set_kernel(self, kernel: str) -> None:
+        capi.check(capi.lib().ge_batch_set_kernel(self._h, capi.KERNEL_NAMES[kernel]))
+
+    @property
+    def kernel(self) -> str:
+        k = capi.lib().ge_batch_get_kernel(self._h)
+        return {capi.KERNEL_COOP: "coop", capi.KERNEL_TPS: "tps"}[k]
+
+    def reset(self, first_session_id: Optional[int] = None, seed: Optional[int] = None) -> None:
+        if first_session_id is not None:
+            self.first_session_id = int(first_session_id)
+        if seed is not None:
+            self.seed = int(seed)
+        capi.check(capi.lib().ge_batch_reset(self._h, self.first_session_id, self.seed))
+
+    def step(self, n_steps: int = 1, stream: int = 0) -> None:
+        """n_steps single-step launches (asynchronous)."""
+        capi.check(capi.lib().ge_step(self._h, int(n_steps), ctypes.c_void_p(stream)))
+
+    def run_fused(self, n_steps: int, stream: int = 0) -> None:
+        capi.check(capi.lib().ge_run_fused(self._h, int(n_steps), ctypes.c_void_p(stream)))
+
+    def sync(self) -> None:
+        capi.check(capi.lib().ge_sync(self._h))
+
+    # ---- state
+    def export_state(self, first: int = 0, count: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        count = self.n - first if count is None else int(count)
+        S = self.table.record_size
+        if out is None:
+            out = np.empty((count, S), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == count * S
+        capi.check(capi.lib().ge_export_state(self._h, int(first), count, out.ctypes.data))
+        return out
+
+    def import_state(self, records: np.ndarray, first: int = 0) -> None:
+        rec = np.ascontiguousarray(records, dtype=np.uint8)
+        S = self.table.record_size
+        assert rec.size % S == 0
+        capi.check(capi.lib().ge_import_state(self._h, int(first), rec.size // S, rec.ctypes.data))
+
+    def run_host(self, records_in: Optional[np.ndarray], records_out: Optional[np.ndarray], n_steps: int,
+                 stats_out: Optional[np.ndarray] = None) -> None:
+        """End-to-end call with host buffers (H2D, n_steps steps, D2H); synchronous."""
+        pin = records_in.ctypes.data if records_in is not None else None
+        pout = records_out.ctypes.data if records_out is not None else None
+        pst = stats_out.ctypes.data if stats_out is not None else None
+        capi.check(capi.lib().ge_run_host(self._h, pin, pout, int(n_steps), pst))
+
+    # ---- statistics
+    def stats(self) -> np.ndarray:
+        out = np.zeros(capi.STATS_LEN, dtype=np.uint64)
+        capi.check(capi.lib().ge_stats(self._h, out.ctypes.data, capi.STATS_LEN))
+        return out
+
+    def stats_refresh(self, stream: int = 0) -> None:
+        capi.check(capi.lib().ge_stats_refresh(self._h, ctypes.c_void_p(stream)))
+
+    def stats_device_ptr(self) -> int:
+        return int(capi.lib().ge_stats_device_ptr(self._h) or 0)
+
+    def counted_steps(self) -> int:
+        v = ctypes.c_uint64()
+        capi.check(capi.lib().ge_counted_steps(self._h, ctypes.byref(v)))
+        return int(v.value)
+
+    def launch_count(self) -> int:
+        return int(capi.lib().ge_launch_count(self._h))
+
+    def state_device_ptr(self) -> int:
+        return int(capi.lib().ge_state_device_ptr(self._h) or 0)
+
+    def state_device_bytes(self) -> int:
+        return int(capi.lib().ge_state_device_bytes(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            capi.lib().ge_batch_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host memory from the library (cudaHostAlloc) exposed as a NumPy array."""
+
+    def __init__(self, nbytes: int):
+        self._p = ctypes.c_void_p()
+        capi.check(capi.lib().ge_host_alloc(ctypes.byref(self._p), int(nbytes)))
+        self.nbytes = int(nbytes)
+        self.array = np.ctypeslib.as_array(ctypes.cast(self._p, ctypes.POINTER(ctypes.c_uint8)), shape=(self.nbytes,))
+
+    def close(self) -> None:
+        if self._p:
+            self.array = None
+            capi.lib().ge_host_free(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,101 @@
+// ge_common.cuh — device-side building blocks shared by the two step-kernel mappings.
+//
+// Data layout in HBM ("session store"): sessions are grouped in tiles of 32.  A canonical record of
+// S bytes (SPEC.md section 5, S % 8 == 0) is split into N16 = S/16 columns of 16 bytes plus, when
+// S % 16 == 8, one trailing column of 8 bytes.  Column c of a tile is stored contiguously for the 32
+// sessions of the tile:   tile_base + c*512 + lane*16   (trailing column: tile_base + N16*512 + lane*8).
+// A warp that owns one tile therefore reads/writes every column with one fully coalesced 128-bit
+// (or 64-bit) access per lane: 512 contiguous bytes per instruction, no padding bytes moved.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/game_engine_b200.h"
+
+namespace ge {
+
+enum { FAM_WEREWOLF = 1, FAM_TTL = 2 };
+enum { KIND_UI = 0, KIND_TIMER = 1, KIND_ACTION = 2, KIND_TERMINAL = 3 };
+enum { ACT_NONE = 0, ACT_PICK_PLAYER = 1, ACT_PICK_OPTION = 2, ACT_MARK = 3 };
+enum { EX_NONE = 0, EX_VOTE_KILL = 1, EX_PROTECT = 2, EX_INVESTIGATE_RESOLVE = 3, EX_DAY_VOTE = 4,
+       EX_T_STATEMENTS = 16, EX_T_LIE = 17, EX_T_VOTES = 18 };
+enum { EN_NONE = 0, EN_ASSIGN_ROLES = 1, EN_NIGHT_RESET = 2,
+       EN_T_ROUND_START = 16, EN_T_REVEAL = 17, EN_T_SCORE = 18, EN_T_FINAL = 19 };
+enum { BR_ALWAYS = 0, BR_COUNT_EQ0 = 1, BR_COUNT_GE = 2, BR_PREV_IN = 3, BR_ALL_VAL_GE = 4, BR_TIE_PENDING = 5 };
+
+// stats word offsets (SPEC.md section 6)
+enum { ST_COUNTED = 0, ST_WINNER = 1, ST_LENGTH = 4, ST_VISITS = 260, ST_TAIL = 292 };
+
+// The compiled table travels to the kernels BY VALUE as a __grid_constant__ parameter: it lands in
+// the constant bank (uniform, cached) and there is no module-global symbol to race on between handles.
+struct DevTable {
+    ge_table_header_t h;
+    ge_phase_t phase[GE_MAX_PHASES];
+    ge_pred_t pred[GE_MAX_PREDS];
+    // per phase: which column groups a step that starts in this phase must READ besides column 0
+    // (bit0 = dynamic masks column, bit1 = role/team column, bit2 = per-player bytes); host-computed.
+    uint8_t need[GE_MAX_PHASES];
+};
+static_assert(sizeof(ge_phase_t) == 48 && sizeof(ge_pred_t) == 8 && sizeof(ge_table_header_t) == 32, "table ABI");
+static_assert(sizeof(DevTable) <= 4000, "table must fit the kernel parameter space");
+
+// ---- Philox4x32-10 (Random123 constants; SPEC.md section 3) -------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int j) {
+    return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
+}
+
+// index (from bit 0) of the k-th (0-based) set bit of m; BITS = number of low bits that can be set
+template <int BITS>
+__device__ __forceinline__ int kth_set_bit(uint32_t m, uint32_t k) {
+    int pos = 0;
+    if (BITS > 16) { const uint32_t c = __popc(m & 0xFFFFu); if (k >= c) { k -= c; pos += 16; m >>= 16; } }
+    if (BITS > 8)  { const uint32_t c = __popc(m & 0xFFu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; } }
+    if (BITS > 4)  { const uint32_t c = __popc(m & 0xFu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; } }
+    { const uint32_t c = __popc(m & 0x3u); if (k >= c) { k -= c; pos += 2; m >>= 2; } }
+    { const uint32_t c = m & 1u; if (k >= c) pos += 1; }
+    return pos;
+}
+
+__device__ __forceinline__ uint32_t all_mask(int P) { return P >= 32 ? 0xFFFFFFFFu : ((1u << P) - 1u); }
+
+// byte offset inside a tile of record byte `o` of session-lane `sl` (S = record bytes)
+template <int S>
+__device__ __host__ __forceinline__ constexpr uint32_t tile_off(uint32_t o, uint32_t sl) {
+    return (o / 16u < (uint32_t)(S / 16)) ? (o / 16u) * 512u + sl * 16u + (o % 16u)
+                                          : (uint32_t)(S / 16) * 512u + sl * 8u + (o - 16u * (uint32_t)(S / 16));
+}
+
+__device__ __forceinline__ uint4 ld128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ uint2 ld64(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ void st128(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ void st64(uint8_t* p, const uint2& v) { *reinterpret_cast<uint2*>(p) = v; }
+
+// block-level visit counters: warp-aggregated shared atomics, flushed once per block
+__device__ __forceinline__ void count_visit(uint32_t* s_visits, int new_phase, int lane) {
+    const unsigned m = __match_any_sync(0xFFFFFFFFu, new_phase);
+    if (new_phase >= 0 && lane == __ffs(m) - 1) atomicAdd(&s_visits[new_phase], (uint32_t)__popc(m));
+}
+__device__ __forceinline__ void flush_visits(const uint32_t* s_visits, unsigned long long* stats) {
+    // called by all threads after __syncthreads(); warp 0 writes
+    if (threadIdx.x < 32) {
+        const uint32_t v = s_visits[threadIdx.x];
+        if (v) atomicAdd(&stats[ST_VISITS + threadIdx.x], (unsigned long long)v);
+        uint32_t tot = v;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, d);
+        if (threadIdx.x == 0 && tot) atomicAdd(&stats[ST_COUNTED], (unsigned long long)tot);
+    }
+}
+
+}  // namespace ge

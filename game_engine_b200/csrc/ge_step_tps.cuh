@@ -1,0 +1,501 @@
+// ge_step_tps.cuh — "thread per session" mapping of the referee/phase step.
+//
+// One thread owns one session; a warp owns one 32-session tile, so every column of the session store
+// is one coalesced 128-bit access per lane.  All per-player state is 32-bit lane masks (bit p-1 =
+// player p); votes are tallied in BIT-SLICED counters (plane b holds bit b of every candidate's vote
+// count), so a plurality with lowest-id tie-break is a few AND/XORs instead of a per-candidate loop.
+// Loops over players are fully unrolled so the per-player bytes live in named registers (no local
+// memory).  The rules are SPEC.md; the restated reference code is BotBehaviorNode / PhaseNode /
+// RefereeNode (reference agent/game_agent_v2.py:468-617, 987-1241, 619-803).
+#pragma once
+#include "ge_common.cuh"
+
+namespace ge {
+
+enum { DIRTY_C0 = 1, DIRTY_C1 = 2, DIRTY_C2 = 4, DIRTY_PL = 8 };
+
+// =============================================================================== werewolf family
+template <int P8>
+struct WState {
+    uint32_t h0, h1;                                   // phase|prev<<8|step<<16 ; winner|kill<<8|protect<<16|revote<<24
+    uint32_t alive, can_vote;                          // column 0
+    uint32_t eligible, submitted, revealed, investigated;   // column 1
+    uint32_t wolf, secret, role_lo, role_hi;           // column 2
+    uint32_t tw[P8 / 4];                               // selected_target_id bytes
+};
+
+template <int P8>
+__device__ __forceinline__ uint32_t w_field(const WState<P8>& s, int f, uint32_t ALL) {
+    switch (f) {
+    case 0: return s.alive;      case 1: return s.can_vote;  case 2: return s.eligible;
+    case 3: return s.submitted;  case 4: return s.revealed;  case 5: return s.investigated;
+    case 6: return s.wolf;       case 7: return s.secret;
+    case 8: return ~(s.role_lo | s.role_hi) & ALL;
+    case 9: return s.role_lo & ~s.role_hi;
+    case 10: return ~s.role_lo & s.role_hi;
+    case 11: return s.role_lo & s.role_hi;
+    case 15: return ALL;
+    default: return 0u;
+    }
+}
+
+template <int P8>
+__device__ __forceinline__ uint32_t w_pred(const DevTable& T, const WState<P8>& s, int pi, uint32_t ALL) {
+    const ge_pred_t pr = T.pred[pi];
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
+        uint32_t m = ALL;
+        while (pos) { const int f = __ffs(pos) - 1; pos &= pos - 1; m &= w_field(s, f, ALL); }
+        while (neg) { const int f = __ffs(neg) - 1; neg &= neg - 1; m &= ~w_field(s, f, ALL); }
+        out |= m;
+    }
+    return out;
+}
+
+// bit-sliced vote counters
+template <int NPL>
+struct Tally {
+    uint32_t pl[NPL];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int b = 0; b < NPL; ++b) pl[b] = 0;
+    }
+    __device__ __forceinline__ void add(uint32_t onehot) {
+        uint32_t carry = onehot;
+#pragma unroll
+        for (int b = 0; b < NPL; ++b) { const uint32_t t = pl[b] & carry; pl[b] ^= carry; carry = t; }
+    }
+    // returns the mask of candidates that share the highest (non-zero) count
+    __device__ __forceinline__ uint32_t top() const {
+        uint32_t cand = 0;
+#pragma unroll
+        for (int b = 0; b < NPL; ++b) cand |= pl[b];
+#pragma unroll
+        for (int b = NPL - 1; b >= 0; --b) { const uint32_t t = cand & pl[b]; cand = t ? t : cand; }
+        return cand;
+    }
+};
+
+template <int P8>
+__device__ __forceinline__ void w_die(WState<P8>& s, int id) {
+    const uint32_t bit = ~(1u << (id - 1));
+    s.alive &= bit; s.can_vote &= bit; s.eligible &= bit;
+}
+
+// One step of one session.  Returns the phase index entered (for the visit counters) or -1 when the
+// session is terminal.  `dirty` collects which column groups changed.
+template <int P8>
+__device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t sid_lo, uint32_t sid_hi,
+                                      uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    constexpr int NPL = P8 <= 8 ? 4 : P8 <= 16 ? 5 : 6;
+    const int P = T.h.n_players;
+    const uint32_t ALL = all_mask(P);
+    const int X = s.h0 & 0xFF;
+    const uint32_t step0 = s.h0 >> 16;
+    const ge_phase_t& ph = T.phase[X];
+    if (ph.kind == KIND_TERMINAL) return -1;
+    dirty |= DIRTY_C0;
+    if (step0 == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
+
+    uint32_t winner = s.h1 & 0xFF, kill = (s.h1 >> 8) & 0xFF, protect = (s.h1 >> 16) & 0xFF, revote = s.h1 >> 24;
+    const uint32_t prev = (s.h0 >> 8) & 0xFF;
+
+    // ---- PhaseNode: ordered branch evaluation on the state before this step's effects
+    int taken = ph.n_branches - 1;
+    for (int b = 0; b < ph.n_branches; ++b) {
+        const ge_branch_t br = ph.br[b];
+        bool ok;
+        switch (br.op) {
+        case BR_ALWAYS: ok = true; break;
+        case BR_COUNT_EQ0: ok = w_pred(T, s, br.a, ALL) == 0; break;
+        case BR_COUNT_GE: ok = __popc(w_pred(T, s, br.a, ALL)) >= __popc(w_pred(T, s, (int)br.arg, ALL)); break;
+        case BR_PREV_IN: ok = (br.arg >> prev) & 1u; break;
+        case BR_TIE_PENDING: ok = (revote & 0x80u) != 0; break;
+        default: ok = false; break;
+        }
+        if (ok) { taken = b; break; }
+    }
+    const int Y = ph.br[taken].next;
+    const uint32_t tag = ph.br[taken].tag;
+
+    // ---- BotBehaviorNode: every actor draws its choice; votes go straight into the tally
+    if (ph.kind == KIND_ACTION) {
+        const uint32_t actors = w_pred(T, s, ph.actor_pred, ALL);
+        const uint32_t legal0 = ph.action_op == ACT_PICK_PLAYER ? w_pred(T, s, ph.action_arg, ALL) : 0u;
+        const bool excl = ph.action_flags & 1;
+        Tally<NPL> tally; tally.clear();
+        uint32_t chosen = 0, first_choice = 0; bool have_first = false;
+#pragma unroll
+        for (int b = 0; b < P8 / 4; ++b) {
+            const uint32_t ab = (actors >> (4 * b)) & 0xFu;
+            if (ab) {
+                const uint4 r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, k0, k1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((ab >> j) & 1u) {
+                        const int p = 4 * b + j;
+                        const uint32_t r = word_of(r4, j);
+                        uint32_t choice;
+                        if (ph.action_op == ACT_PICK_PLAYER) {
+                            const uint32_t legal = excl ? (legal0 & ~(1u << p)) : legal0;
+                            const uint32_t n = __popc(legal);
+                            const int idx = kth_set_bit<P8>(legal, __umulhi(r, n));
+                            choice = n ? (uint32_t)idx + 1u : 0u;
+                            if (n) { chosen |= 1u << idx; tally.add(1u << idx); }
+                        } else if (ph.action_op == ACT_PICK_OPTION) {
+                            choice = 1u + __umulhi(r, (uint32_t)ph.action_arg);
+                        } else {
+                            choice = 1u;
+                        }
+                        if (!have_first) { first_choice = choice; have_first = true; }
+                        s.tw[b] = (s.tw[b] & ~(0xFFu << (8 * j))) | (choice << (8 * j));
+                    }
+                }
+            }
+        }
+        dirty |= DIRTY_PL;
+        // ---- RefereeNode, effects of the phase just left
+        switch (ph.exit_op) {
+        case EX_VOTE_KILL: {
+            s.submitted |= actors; dirty |= DIRTY_C1;
+            const uint32_t top = tally.top();
+            kill = top ? (uint32_t)__ffs(top) : 0u;
+        } break;
+        case EX_PROTECT:
+            s.submitted |= actors; dirty |= DIRTY_C1;
+            protect = first_choice;
+            break;
+        case EX_INVESTIGATE_RESOLVE:
+            s.submitted |= actors; s.investigated |= chosen; dirty |= DIRTY_C1;
+            if (kill != 0 && kill != protect) w_die(s, (int)kill);
+            break;
+        case EX_DAY_VOTE: {
+            const uint32_t top = tally.top();
+            const uint32_t x = top ? (uint32_t)__ffs(top) : 0u;
+            const bool tied = __popc(top) > 1;
+            if (T.h.max_revotes > 0 && tied && (revote & 0x7Fu) < T.h.max_revotes) {
+                revote = ((revote & 0x7Fu) + 1u) | 0x80u;
+            } else {
+                revote &= 0x7Fu;
+                if (x) { w_die(s, (int)x); s.revealed |= 1u << (x - 1); dirty |= DIRTY_C1; }
+            }
+        } break;
+        default: break;
+        }
+    }
+
+    // ---- RefereeNode, effects of entering Y
+    const int en = T.phase[Y].entry_op;
+    if (en == EN_ASSIGN_ROLES) {
+        uint32_t key[P8];
+#pragma unroll
+        for (int b = 0; b < P8 / 4; ++b) {
+            if (4 * b < P) {
+                const uint4 r4 = philox4x32_10(sid_lo, sid_hi, step0, (1u << 16) | (uint32_t)b, k0, k1);
+                key[4 * b] = r4.x; key[4 * b + 1] = r4.y; key[4 * b + 2] = r4.z; key[4 * b + 3] = r4.w;
+            } else {
+                key[4 * b] = key[4 * b + 1] = key[4 * b + 2] = key[4 * b + 3] = 0;
+            }
+        }
+        // rank < W+2 is all that matters: pick the W+2 smallest (key, id) pairs in order
+        uint32_t rem = ALL, wolf = 0, lo = 0, hi = 0;
+        const int W = T.h.n_wolves;
+        for (int round = 0; round < W + 2; ++round) {
+            uint32_t best = 0; int bi = -1;
+#pragma unroll
+            for (int p = 0; p < P8; ++p) {
+                if (((rem >> p) & 1u) && (bi < 0 || key[p] < best)) { best = key[p]; bi = p; }
+            }
+            if (bi < 0) break;
+            rem &= ~(1u << bi);
+            const uint32_t bit = 1u << bi;
+            if (round < W) { wolf |= bit; lo |= bit; }            // role index 1
+            else if (round == W) { hi |= bit; }                    // role index 2 (Doctor)
+            else { lo |= bit; hi |= bit; }                         // role index 3 (Detective)
+        }
+        s.wolf = wolf; s.role_lo = lo; s.role_hi = hi;
+        s.secret = lo | hi; s.eligible = lo | hi;
+        dirty |= DIRTY_C1 | DIRTY_C2;
+    } else if (en == EN_NIGHT_RESET) {
+        s.submitted = 0;
+#pragma unroll
+        for (int b = 0; b < P8 / 4; ++b) s.tw[b] = 0;
+        kill = 0; protect = 0; revote = 0;
+        dirty |= DIRTY_C1 | DIRTY_PL;
+    }
+    if (tag) winner = tag;
+
+    s.h1 = winner | (kill << 8) | (protect << 16) | (revote << 24);
+    s.h0 = (uint32_t)Y | ((uint32_t)X << 8) | ((step0 + 1u) << 16);
+    return Y;
+}
+
+template <int P8>
+__global__ void __launch_bounds__(128)
+k_step_w_tps(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, uint64_t n_sessions, uint64_t n_tiles,
+             uint64_t first_sid, uint64_t seed, unsigned long long* __restrict__ stats, int n_steps) {
+    constexpr int S = 48 + P8;
+    constexpr int NT16 = P8 / 16;          // full 16-byte target columns
+    constexpr bool THALF = (P8 % 16) != 0; // trailing 8-byte column
+    __shared__ uint32_t s_visits[32];
+    if (threadIdx.x < 32) s_visits[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+
+    for (uint64_t tile = warp0; tile < n_tiles; tile += nwarps) {
+        uint8_t* base = tiles + tile * (uint64_t)(32 * S);
+        const uint64_t sess = tile * 32 + lane;
+        const bool in_range = sess < n_sessions;
+        WState<P8> s;
+        {
+            const uint4 c0 = ld128(base + lane * 16);
+            s.h0 = c0.x; s.h1 = c0.y; s.alive = c0.z; s.can_vote = c0.w;
+        }
+        bool live = in_range && T.phase[s.h0 & 0xFF].kind != KIND_TERMINAL;
+        if (live) {
+            const uint4 c1 = ld128(base + 512 + lane * 16);
+            const uint4 c2 = ld128(base + 1024 + lane * 16);
+            s.eligible = c1.x; s.submitted = c1.y; s.revealed = c1.z; s.investigated = c1.w;
+            s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
+#pragma unroll
+            for (int c = 0; c < NT16; ++c) {
+                const uint4 t = ld128(base + (3 + c) * 512 + lane * 16);
+                s.tw[4 * c] = t.x; s.tw[4 * c + 1] = t.y; s.tw[4 * c + 2] = t.z; s.tw[4 * c + 3] = t.w;
+            }
+            if (THALF) {
+                const uint2 t = ld64(base + (3 + NT16) * 512 + lane * 8);
+                s.tw[4 * NT16] = t.x; s.tw[4 * NT16 + 1] = t.y;
+            }
+        }
+        const uint64_t sid = first_sid + sess;
+        uint32_t dirty = 0;
+        for (int it = 0; it < n_steps; ++it) {
+            int np = -1;
+            if (live) {
+                np = w_step<P8>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                if (np < 0) live = false;
+            }
+            count_visit(s_visits, np, lane);
+        }
+        if (dirty & DIRTY_C0) st128(base + lane * 16, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
+        if (dirty & DIRTY_C1) st128(base + 512 + lane * 16, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
+        if (dirty & DIRTY_C2) st128(base + 1024 + lane * 16, make_uint4(s.wolf, s.secret, s.role_lo, s.role_hi));
+        if (dirty & DIRTY_PL) {
+#pragma unroll
+            for (int c = 0; c < NT16; ++c)
+                st128(base + (3 + c) * 512 + lane * 16, make_uint4(s.tw[4 * c], s.tw[4 * c + 1], s.tw[4 * c + 2], s.tw[4 * c + 3]));
+            if (THALF) st64(base + (3 + NT16) * 512 + lane * 8, make_uint2(s.tw[4 * NT16], s.tw[4 * NT16 + 1]));
+        }
+    }
+    __syncthreads();
+    flush_visits(s_visits, stats);
+}
+
+// =================================================================================== TTL family
+// Device record for player bucket PB: 8-byte header + PB player words (score|rounds<<8|vote<<16|flags<<24).
+template <int PB>
+struct TState {
+    uint32_t h0, h1;              // phase|prev<<8|step<<16 ; speaker|lie<<8|winner<<16
+    uint32_t pw[PB];
+};
+
+enum { TF_SPEAKER = 1, TF_STMTS = 2, TF_REVEALED = 4, TF_CANVOTE = 8, TF_VOTED = 16 };
+
+template <int PB>
+__device__ __forceinline__ int t_step(const DevTable& T, TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi,
+                                      uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    const int P = T.h.n_players;
+    const uint32_t ALL = all_mask(P);
+    const int X = s.h0 & 0xFF;
+    const uint32_t step0 = s.h0 >> 16;
+    const ge_phase_t& ph = T.phase[X];
+    if (ph.kind == KIND_TERMINAL) return -1;
+    dirty |= DIRTY_C0;
+    if (step0 == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
+
+    uint32_t speaker = s.h1 & 0xFF, lie = (s.h1 >> 8) & 0xFF, winner = (s.h1 >> 16) & 0xFF;
+    // lane masks from the per-player flag bytes
+    uint32_t m[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        const uint32_t fl = s.pw[p] >> 24;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) m[f] |= ((fl >> f) & 1u) << p;
+    }
+    auto field = [&](int f) -> uint32_t { return f == 15 ? ALL : f < 5 ? (f == 0 ? m[0] : f == 1 ? m[1] : f == 2 ? m[2] : f == 3 ? m[3] : m[4]) : 0u; };
+    auto pred = [&](int pi) -> uint32_t {
+        const ge_pred_t pr = T.pred[pi];
+        uint32_t out = 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0, mm = ALL;
+            while (pos) { const int f = __ffs(pos) - 1; pos &= pos - 1; mm &= field(f); }
+            while (neg) { const int f = __ffs(neg) - 1; neg &= neg - 1; mm &= ~field(f); }
+            out |= mm;
+        }
+        return out;
+    };
+
+    int taken = ph.n_branches - 1;
+    for (int b = 0; b < ph.n_branches; ++b) {
+        const ge_branch_t br = ph.br[b];
+        bool ok;
+        switch (br.op) {
+        case BR_ALWAYS: ok = true; break;
+        case BR_COUNT_EQ0: ok = pred(br.a) == 0; break;
+        case BR_COUNT_GE: ok = __popc(pred(br.a)) >= __popc(pred((int)br.arg)); break;
+        case BR_PREV_IN: ok = (br.arg >> ((s.h0 >> 8) & 0xFF)) & 1u; break;
+        case BR_ALL_VAL_GE: {
+            ok = true;
+#pragma unroll
+            for (int p = 0; p < PB; ++p)
+                if (p < P && ((s.pw[p] >> (8 * br.a)) & 0xFFu) < br.arg) ok = false;
+        } break;
+        default: ok = false; break;
+        }
+        if (ok) { taken = b; break; }
+    }
+    const int Y = ph.br[taken].next;
+    const uint32_t tag = ph.br[taken].tag;
+
+    if (ph.kind == KIND_ACTION) {
+        const uint32_t actors = pred(ph.actor_pred);
+        uint32_t first_choice = 0; bool have_first = false;
+#pragma unroll
+        for (int b = 0; b < (PB + 3) / 4; ++b) {
+            const uint32_t ab = (actors >> (4 * b)) & 0xFu;
+            if (ab) {
+                const uint4 r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, k0, k1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int p = 4 * b + j;
+                    if (p < PB && ((ab >> j) & 1u)) {
+                        const uint32_t r = word_of(r4, j);
+                        const uint32_t choice = ph.action_op == ACT_PICK_OPTION ? 1u + __umulhi(r, (uint32_t)ph.action_arg) : 1u;
+                        if (!have_first) { first_choice = choice; have_first = true; }
+                        if (ph.exit_op == EX_T_VOTES) s.pw[p] = (s.pw[p] & 0xFF00FFFFu) | (choice << 16);
+                    }
+                }
+            }
+        }
+        switch (ph.exit_op) {
+        case EX_T_STATEMENTS: m[1] |= actors; break;
+        case EX_T_LIE: if (have_first) lie = first_choice; break;
+        case EX_T_VOTES: m[4] |= actors; break;
+        default: break;
+        }
+    }
+
+    const int en = T.phase[Y].entry_op;
+    if (en == EN_T_ROUND_START) {
+        speaker = 0;
+#pragma unroll
+        for (int p = PB - 1; p >= 0; --p)
+            if (p < P && ((s.pw[p] >> 8) & 0xFFu) < T.h.rounds) speaker = p + 1;
+        lie = 0;
+        m[0] = speaker ? 1u << (speaker - 1) : 0u;
+        m[3] = ALL & ~m[0];
+        m[1] = 0; m[2] = 0; m[4] = 0;
+#pragma unroll
+        for (int p = 0; p < PB; ++p) s.pw[p] &= 0xFF00FFFFu;
+    } else if (en == EN_T_REVEAL) {
+        m[2] |= m[0];
+    } else if (en == EN_T_SCORE) {
+        const uint32_t voters = m[4] & m[3] & ~m[0];
+        uint32_t fooled = 0;
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            if ((voters >> p) & 1u) {
+                if (((s.pw[p] >> 16) & 0xFFu) == lie) s.pw[p] = (s.pw[p] & ~0xFFu) | ((s.pw[p] + 1u) & 0xFFu);
+                else fooled++;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            if ((uint32_t)(p + 1) == speaker) {
+                const uint32_t sc = ((s.pw[p] & 0xFFu) + fooled) & 0xFFu;
+                const uint32_t rd = (((s.pw[p] >> 8) & 0xFFu) + 1u) & 0xFFu;
+                s.pw[p] = (s.pw[p] & 0xFFFF0000u) | sc | (rd << 8);
+            }
+        }
+    } else if (en == EN_T_FINAL) {
+        uint32_t best = s.pw[0] & 0xFFu; winner = 1;
+#pragma unroll
+        for (int p = 1; p < PB; ++p)
+            if (p < P && (s.pw[p] & 0xFFu) > best) { best = s.pw[p] & 0xFFu; winner = p + 1; }
+    }
+    if (tag) winner = tag;
+
+    // write the flag bytes back
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        uint32_t fl = 0;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) fl |= ((m[f] >> p) & 1u) << f;
+        s.pw[p] = (s.pw[p] & 0x00FFFFFFu) | (fl << 24);
+    }
+    s.h1 = speaker | (lie << 8) | (winner << 16);
+    s.h0 = (uint32_t)Y | ((uint32_t)X << 8) | ((step0 + 1u) << 16);
+    return Y;
+}
+
+template <int PB>
+__global__ void __launch_bounds__(128)
+k_step_t_tps(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, uint64_t n_sessions, uint64_t n_tiles,
+             uint64_t first_sid, uint64_t seed, unsigned long long* __restrict__ stats, int n_steps) {
+    constexpr int S = 8 + 4 * PB;           // device record (PB even => S % 8 == 0)
+    constexpr int NW = S / 4;
+    constexpr int N16 = S / 16;
+    constexpr bool HALF = (S % 16) != 0;
+    __shared__ uint32_t s_visits[32];
+    if (threadIdx.x < 32) s_visits[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+
+    for (uint64_t tile = warp0; tile < n_tiles; tile += nwarps) {
+        uint8_t* base = tiles + tile * (uint64_t)(32 * S);
+        const uint64_t sess = tile * 32 + lane;
+        uint32_t w[NW];
+#pragma unroll
+        for (int c = 0; c < N16; ++c) {
+            const uint4 v = ld128(base + c * 512 + lane * 16);
+            w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+        }
+        if (HALF) { const uint2 v = ld64(base + N16 * 512 + lane * 8); w[4 * N16] = v.x; w[4 * N16 + 1] = v.y; }
+        TState<PB> s;
+        s.h0 = w[0]; s.h1 = w[1];
+#pragma unroll
+        for (int p = 0; p < PB; ++p) s.pw[p] = w[2 + p];
+        bool live = sess < n_sessions && T.phase[s.h0 & 0xFF].kind != KIND_TERMINAL;
+        const uint64_t sid = first_sid + sess;
+        uint32_t dirty = 0;
+        for (int it = 0; it < n_steps; ++it) {
+            int np = -1;
+            if (live) {
+                np = t_step<PB>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                if (np < 0) live = false;
+            }
+            count_visit(s_visits, np, lane);
+        }
+        if (dirty) {
+            w[0] = s.h0; w[1] = s.h1;
+#pragma unroll
+            for (int p = 0; p < PB; ++p) w[2 + p] = s.pw[p];
+#pragma unroll
+            for (int c = 0; c < N16; ++c) st128(base + c * 512 + lane * 16, make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+            if (HALF) st64(base + N16 * 512 + lane * 8, make_uint2(w[4 * N16], w[4 * N16 + 1]));
+        }
+    }
+    __syncthreads();
+    flush_visits(s_visits, stats);
+}
+
+}  // namespace ge

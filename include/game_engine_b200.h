@@ -1,0 +1,131 @@
+/*
+ * game_engine_b200.h — C ABI of the batched referee/phase-step simulator (B200, sm_100a).
+ *
+ * This is the drop-in boundary for the ONE data-parallel path of liruihan000/game_engine: the
+ * deterministic core of a graph run BotBehaviorNode -> PhaseNode -> RefereeNode.  Every entry point
+ * names the reference interface it replaces (paths under the reference repo).  Plain pointers and
+ * sizes only; bind with ctypes / cffi / cgo.
+ *
+ * All functions return 0 on success or a negative GE_ERR_* code; ge_last_error() gives the message
+ * of the last failure on the calling thread.  The library is re-entrant across handles; one handle
+ * must not be used from two threads at once.  There is no CPU fallback: without a CUDA device every
+ * compute call fails with GE_ERR_CUDA.
+ */
+#ifndef GAME_ENGINE_B200_H
+#define GAME_ENGINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GE_STATS_LEN 560          /* u64 words, layout in SPEC.md section 6 */
+#define GE_MAX_PHASES 32
+#define GE_MAX_PREDS 32
+
+#define GE_OK 0
+#define GE_ERR_ARG (-1)           /* bad argument / malformed table blob */
+#define GE_ERR_CUDA (-2)          /* CUDA runtime error (message has the cudaError string) */
+#define GE_ERR_UNSUPPORTED (-3)   /* table uses a family / player count the kernels do not cover */
+#define GE_ERR_NOMEM (-4)
+
+/* kernel mappings (ge_batch_set_kernel) */
+#define GE_KERNEL_AUTO 0
+#define GE_KERNEL_COOP 1          /* one lane per player, warp ballots / match_any (32/P sessions per warp) */
+#define GE_KERNEL_TPS 2           /* one thread per session, bit-sliced tallies */
+
+/* ---- binary transition table (produced by game_engine_b200/compiler.py) -------------------------
+ * Replaces: the per-step LLM reading of dsl['phases'] (reference agent/game_agent_v2.py:1022-1103,
+ * accessor agent/tools/utils.py:19-31, loader utils.py:557-581). */
+typedef struct {
+    uint8_t op, next, tag, a;
+    uint32_t arg;
+} ge_branch_t;
+
+typedef struct {
+    uint8_t id, kind, action_op, action_arg, action_flags, exit_op, entry_op, n_branches;
+    uint8_t actor_pred, pad[7];
+    ge_branch_t br[4];
+} ge_phase_t;
+
+typedef struct {
+    uint16_t pos0, neg0, pos1, neg1;
+} ge_pred_t;
+
+typedef struct {
+    char magic[4];                /* "GETB" */
+    uint16_t version;             /* 1 */
+    uint8_t family, n_phases, n_players, n_preds, n_wolves, rounds, max_revotes, reserved[3];
+    uint32_t init_masks;
+    uint32_t reserved2[3];
+} ge_table_header_t;
+
+typedef struct ge_table ge_table;
+typedef struct ge_batch ge_batch;
+
+/* Parse and validate a table blob.  Replaces load_dsl_by_gamename + yaml.safe_load per thread
+ * (reference agent/tools/utils.py:557-581). */
+int ge_table_create(const uint8_t *blob, size_t n, ge_table **out);
+void ge_table_destroy(ge_table *t);
+/* canonical packed record size S in bytes (SPEC.md section 5) */
+size_t ge_table_record_size(const ge_table *t);
+int ge_table_n_players(const ge_table *t);
+
+/* Allocate n_sessions sessions on `device` and initialise them from the DSL template.
+ * Session i has id first_session_id + i.  Replaces initialize_player_states_from_dsl
+ * (reference agent/tools/utils.py:584-653) and AgentState defaults (game_agent_v2.py:97-117). */
+int ge_batch_create(ge_table *t, int device, uint64_t n_sessions, uint64_t first_session_id, uint64_t seed,
+                    ge_batch **out);
+/* Re-initialise all sessions (new ids / seed), zero the statistics. */
+int ge_batch_reset(ge_batch *b, uint64_t first_session_id, uint64_t seed);
+void ge_batch_destroy(ge_batch *b);
+int ge_batch_set_kernel(ge_batch *b, int kernel);
+int ge_batch_get_kernel(const ge_batch *b);
+
+/* Apply n_steps session-phase-steps to every non-terminal session: n_steps launches of the step
+ * kernel on `cuda_stream` (NULL = the batch's own stream), each reading and writing the state once.
+ * Asynchronous.  Replaces one graph run BotBehaviorNode -> PhaseNode -> RefereeNode per step
+ * (reference agent/game_agent_v2.py:468-617, 987-1241, 619-803) including the tool applications
+ * _execute_update_player_actions / _execute_update_player_state (agent/tools/backend_tools.py:285-344,
+ * 204-225). */
+int ge_step(ge_batch *b, int n_steps, void *cuda_stream);
+/* Same semantics with the state kept in registers for up to n_steps steps (one launch). */
+int ge_run_fused(ge_batch *b, int n_steps, void *cuda_stream);
+int ge_sync(ge_batch *b);
+
+/* Canonical records (SPEC.md section 5), count * S bytes, sessions [first, first+count).
+ * Replaces reading / writing AgentState.player_states, current_phase_id, phase_history length
+ * (reference agent/game_agent_v2.py:97-117).  Synchronous. */
+int ge_export_state(ge_batch *b, uint64_t first, uint64_t count, void *host_buf);
+int ge_import_state(ge_batch *b, uint64_t first, uint64_t count, const void *host_buf);
+
+/* End-to-end call with HOST buffers: records_in (NULL = keep current device state) -> device,
+ * n_steps steps, records_out (NULL = skip) and stats (NULL = skip) back to the host.  Synchronous.
+ * Pinned buffers (ge_host_alloc) make the copies asynchronous DMA. */
+int ge_run_host(ge_batch *b, const void *records_in, void *records_out, int n_steps, uint64_t *host_stats);
+int ge_host_alloc(void **p, size_t bytes);
+void ge_host_free(void *p);
+
+/* Statistics (SPEC.md section 6).  ge_stats recomputes the final-state histograms, then copies
+ * GE_STATS_LEN words (n must be >= GE_STATS_LEN).  ge_stats_device_ptr returns the device buffer
+ * (valid after ge_stats_refresh) for an NCCL / torch.distributed all-reduce.  No reference analogue. */
+int ge_stats_refresh(ge_batch *b, void *cuda_stream);
+int ge_stats(ge_batch *b, uint64_t *host_hist, size_t n);
+void *ge_stats_device_ptr(ge_batch *b);
+int ge_counted_steps(ge_batch *b, uint64_t *out);
+
+/* device pointer / size of the tiled session store (for profiling and tests) */
+void *ge_state_device_ptr(ge_batch *b);
+size_t ge_state_device_bytes(const ge_batch *b);
+/* number of step-kernel launches issued by this batch since creation */
+uint64_t ge_launch_count(const ge_batch *b);
+
+const char *ge_last_error(void);
+const char *ge_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAME_ENGINE_B200_H */
