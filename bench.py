@@ -1,0 +1,449 @@
+#!/usr/bin/env python3
+"""bench.py — session-phase-steps/sec of the batched referee/phase step (contract in the task prompt).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU arm (oracle port, all host threads)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, NCCL
+
+Workload (BASELINE.json configs[1]): werewolf-(mafia).yaml, 8 players, 2^20 sessions per GPU, synthetic
+(Philox bots).  A "step" is ONE launch of the step kernel over ONE 2^20-session batch (every non-terminal
+session advances one phase; the state is read and written once).  To keep the inputs out of L2 the
+launches round-robin over a ring of batches whose footprint exceeds 2x L2, and to make the number
+independent of K the ring is a steady state: batch i starts i*G/R steps into its games and a batch that
+has been stepped G times is re-initialised with fresh session ids (the re-initialisation kernels are
+inside the timed region and counted in gpu_launches).  value = counted session-phase-steps (terminal
+sessions do not count) of all ranks / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "session_phase_steps_per_sec"
+UNIT = "session-phase-steps/s"
+FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# longest possible game in steps (SPEC.md): werewolf 11 + 9*(P-3) (one death per day down to 2 players), TTL 2 + 8*P
+
+
+def game_cap(family: int, players: int) -> int:
+    return 9 * players - 16 if family == 1 else 2 + 8 * players
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--game", default="werewolf-(mafia)")
+    ap.add_argument("--players", type=int, default=8)
+    ap.add_argument("--sessions", type=int, default=1 << 20, help="sessions per batch (per GPU)")
+    ap.add_argument("--ring", type=int, default=8, help="batches in the ring (footprint must exceed L2)")
+    ap.add_argument("--cap", type=int, default=0, help="steps before a batch is re-initialised (0 = by player count)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tps", "coop"])
+    ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--e2e-calls", type=int, default=6)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (pynvml; nvidia-smi fallback)."""
+
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop_evt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def run(self):
+        if self._nvml is None:
+            return
+        nv = self._nvml
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        if not s:       # fallback: one nvidia-smi sample (outside the timed region; said so in the record)
+            try:
+                import subprocess
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [int(x) for x in out.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 0, "note": "nvidia-smi after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------- helpers
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload_key: str):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload_key)
+    except Exception:
+        return None
+
+
+def build_oracle_native():
+    from oracle import oracle as _o
+    try:
+        _o.build(native=True)
+        return True
+    except Exception:
+        _o.build(native=False)
+        return False
+
+
+def cpu_oracle_rate(cg, n_sessions: int, cap: int, seed: int, threads: int, native: bool):
+    """Times Oracle B (the CPU port) on n_sessions full games; returns (steps, seconds)."""
+    from oracle.oracle import Oracle
+    o = Oracle(cg.blob, native=native)
+    rec = o.init(n_sessions)
+    st = o.new_stats()
+    t0 = time.perf_counter()
+    o.step(rec, 0, seed, cap, st, threads=threads)
+    return int(st[0]), time.perf_counter() - t0
+
+
+def cpu_baseline(cg, cap: int, seed: int, target_seconds: float):
+    native = build_oracle_native()
+    from oracle.oracle import Oracle
+    threads = Oracle(cg.blob, native=native).max_threads()
+    steps, dt = cpu_oracle_rate(cg, 1 << 13, cap, seed, threads, native)          # calibration
+    per_session = dt / (1 << 13)
+    n = int(max(1 << 13, min(1 << 22, target_seconds / max(per_session, 1e-9))))
+    steps, dt = cpu_oracle_rate(cg, n, cap, seed, threads, native)
+    return {
+        "value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": "%d sessions x %d steps (whole games) of the same workload, Oracle B (oracle/ge_oracle.c, gcc -O3%s, OpenMP), %.1f s"
+                  % (n, cap, " -march=native" if native else "", dt),
+    }
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from game_engine_b200 import compile_game
+    from oracle.oracle import Oracle
+    cg = compile_game(a.game, a.players)
+    cap = a.cap or game_cap(cg.family, a.players)
+    native = build_oracle_native()
+    o = Oracle(cg.blob, native=native)
+    threads = o.max_threads()
+    # size the per-step sample so that K+W steps take about a minute
+    steps, dt = cpu_oracle_rate(cg, 1 << 13, cap, a.seed, threads, native)
+    per_sess_step = dt / ((1 << 13) * cap)                 # seconds per session per pass (terminal passes are cheap)
+    n = int(max(1 << 10, min(a.sessions, 60.0 / max(per_sess_step * (a.steps + a.warmup), 1e-12))))
+    # same steady-state ring as the CUDA arm: R sub-batches staggered through their games
+    R = a.ring
+    n = max(R, n // R * R)
+    sub = n // R
+    recs = [o.init(sub) for _ in range(R)]
+    st = o.new_stats()
+    age, epoch = [0] * R, [0] * R
+    for i in range(R):
+        pre = (i * cap) // R
+        if pre:
+            o.step(recs[i], i * sub, a.seed, pre, None, threads=threads)
+        age[i] = pre
+
+    def one_step():
+        # one pass over the whole sample = one step of every sub-batch
+        for i in range(R):
+            if age[i] >= cap:
+                epoch[i] += 1
+                recs[i] = o.init(sub)
+                age[i] = 0
+            o.step(recs[i], (epoch[i] * R + i) * sub, a.seed, 1, st, threads=threads)
+            age[i] += 1
+
+    for _ in range(a.warmup):
+        one_step()
+    c0 = int(st[0])
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    counted = int(st[0]) - c0
+    value = counted / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "%s, %d players, sample of %d sessions per step (bounded sample of the 2^20-session batch), "
+                               "re-initialised every %d steps" % (a.game, a.players, n, cap),
+                   "note": "the reference repo has no CPU implementation of this path that can run without an LLM; this arm "
+                           "times the CPU port of the same rules (oracle/ge_oracle.c) on all host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d sessions per step, %d steps, Oracle B%s" % (n, a.steps, " -march=native" if native else "")},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------- our arm
+class _CudaArray:
+    """Minimal __cuda_array_interface__ view so torch can wrap the library's device statistics buffer."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from game_engine_b200 import compile_game
+    from game_engine_b200.batch import PinnedBuffer, SessionBatch, Table
+
+    cg = compile_game(a.game, a.players)
+    S = cg.record_size
+    cap = a.cap or game_cap(cg.family, a.players)
+    N, R = a.sessions, a.ring
+    tab = Table(cg)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sh = stream.cuda_stream
+
+    # session ids: unique across ranks, ring slots and epochs
+    def sid_base(epoch, slot):
+        return ((epoch * world + rank) * R + slot) * N
+
+    ring = [SessionBatch(tab, N, first_session_id=sid_base(0, i), seed=a.seed, device=local_rank, kernel=a.kernel) for i in range(R)]
+    for b in ring:
+        b.set_stream(sh)
+    age = [0] * R
+    epoch = [0] * R
+    for i, b in enumerate(ring):                     # stagger: batch i starts i*cap/R steps into its games
+        pre = (i * cap) // R
+        if pre:
+            b.step(pre)
+        age[i] = pre
+    k_global = 0
+    resets = 0
+
+    def one_step():
+        nonlocal k_global, resets
+        i = k_global % R
+        b = ring[i]
+        if age[i] >= cap:
+            epoch[i] += 1
+            b.reset(first_session_id=sid_base(epoch[i], i))
+            age[i] = 0
+            resets += 1
+        b.step(1)
+        age[i] += 1
+        k_global += 1
+
+    for _ in range(max(3, a.warmup)):
+        one_step()
+    torch.cuda.synchronize()
+    counted0 = sum(b.counted_steps() for b in ring)
+    launches0 = sum(b.launch_count() for b in ring)
+    agg = torch.zeros(560, dtype=torch.int64, device=dev)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(a.steps):
+        one_step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+
+    counted = sum(b.counted_steps() for b in ring) - counted0
+    launches = sum(b.launch_count() for b in ring) - launches0
+
+    # the job's only exchange step: statistics all-reduce (win rate + phase-length histogram) over NCCL
+    t_ar0 = time.perf_counter()
+    for b in ring:
+        b.stats_refresh()
+        agg += torch.as_tensor(_CudaArray(b.stats_device_ptr(), 560), device=dev)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+    allreduce_ms = (time.perf_counter() - t_ar0) * 1e3
+    stats = agg.cpu().numpy()
+
+    tm = torch.tensor([ms, float(counted), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = tm.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tm.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_max, counted_all, launches_all = float(tmax[0]), float(tsum[1]), int(tsum[2])
+    else:
+        ms_max, counted_all, launches_all = ms, float(counted), int(launches)
+    value = counted_all / (ms_max * 1e-3)
+
+    # ---- e2e: the public host-buffer call (H2D of the initial records, `cap` steps, D2H of the final
+    #      records + statistics), pinned host memory, wall clock around synchronous calls
+    e2e = None
+    if not a.no_e2e:
+        eb = SessionBatch(tab, N, first_session_id=sid_base(1 << 20, 0), seed=a.seed, device=local_rank, kernel=a.kernel)
+        pin_in, pin_out, pin_st = PinnedBuffer(N * S), PinnedBuffer(N * S), PinnedBuffer(560 * 8)
+        rin = pin_in.array.reshape(N, S)
+        rout = pin_out.array.reshape(N, S)
+        rst = pin_st.array.view(np.uint64)
+        eb.export_state(out=rin)                              # canonical initial records, produced by the library
+        eb.run_host(rin, rout, cap, rst)                      # warm-up call
+        eb.clear_stats()
+        eb.sync()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e_counted = 0
+        for c in range(a.e2e_calls):
+            eb.clear_stats()
+            eb.run_host(rin, rout, cap, rst)
+            e_counted += int(rst[0])
+        dt = time.perf_counter() - t0
+        # single-step variant: every session-phase-step round-trips through host memory
+        eb.clear_stats()
+        eb.sync()
+        t1 = time.perf_counter()
+        for c in range(4):
+            eb.run_host(rin if c == 0 else rout, rout, 1, rst)     # statistics are cumulative since clear_stats
+        s_counted = int(rst[0])
+        dt1 = time.perf_counter() - t1
+        ed = torch.tensor([dt, float(e_counted), dt1, float(s_counted)], dtype=torch.float64, device=dev)
+        if world > 1:
+            emax = ed.clone()
+            dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+            esum = ed.clone()
+            dist.all_reduce(esum, op=dist.ReduceOp.SUM)
+            dt, e_counted, dt1, s_counted = float(emax[0]), float(esum[1]), float(emax[2]), float(esum[3])
+        e2e = {
+            "value": e_counted / dt, "unit": UNIT,
+            "h2d_bytes_per_step": N * S, "d2h_bytes_per_step": N * S + 560 * 8,
+            "call": "SessionBatch.run_host / ge_run_host: pinned host records in -> %d steps -> records + stats out; "
+                    "bytes are per call (one call = %d steps for each of %d sessions)" % (cap, cap, N),
+            "calls": a.e2e_calls, "ms_per_call": dt / a.e2e_calls * 1e3,
+            "single_step_round_trip": {"value": s_counted / dt1, "unit": UNIT, "ms_per_call": dt1 / 4 * 1e3,
+                                       "note": "n_steps=1 per call: every step crosses PCIe twice"},
+        }
+        eb.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = hbm_peak()
+    B = 2 * S
+    achieved = counted_all / world * B / (ms_max * 1e-3) / 1e9          # per GPU
+    kern = ring[0].kernel
+    wl_key = "%s_p%d_%s" % (a.game, a.players, kern)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {
+            "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
+            "kernel": kern, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
+            "steps_before_reinit": cap, "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
+            "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(wl_key), "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": B, "kernel": "k_step_%s_%s" % ("w" if cg.family == 1 else "t", kern),
+                     "steps_per_launch": counted_all / world / a.steps},
+        "e2e": e2e,
+        "gpu_launches": launches_all,
+        "clocks": clocks,
+        "stats_allreduce_ms": allreduce_ms,
+        "win_rate": {"villagers": float(stats[2]) / max(1.0, float(stats[2] + stats[3])),
+                     "werewolves": float(stats[3]) / max(1.0, float(stats[2] + stats[3])),
+                     "sessions_finished": int(stats[2] + stats[3])} if cg.family == 1 else None,
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cg, cap, a.seed, a.cpu_seconds)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

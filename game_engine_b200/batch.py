@@ -54,6 +54,10 @@ class SessionBatch:
         self.set_kernel(kernel)
 
     # ---- control
+    def set_stream(self, stream: int) -> None:
+        """Bind to an external CUDA stream handle (e.g. torch.cuda.Stream().cuda_stream); 0 = own stream."""
+        capi.check(capi.lib().ge_batch_set_stream(self._h, ctypes.c_void_p(stream)))
+
     def set_kernel(self, kernel: str) -> None:
         capi.check(capi.lib().ge_batch_set_kernel(self._h, capi.KERNEL_NAMES[kernel]))
 
@@ -68,6 +72,9 @@ class SessionBatch:
         if seed is not None:
             self.seed = int(seed)
         capi.check(capi.lib().ge_batch_reset(self._h, self.first_session_id, self.seed))
+
+    def clear_stats(self) -> None:
+        capi.check(capi.lib().ge_batch_clear_stats(self._h))
 
     def step(self, n_steps: int = 1, stream: int = 0) -> None:
         """n_steps single-step launches (asynchronous)."""

@@ -26,7 +26,9 @@ SYMBOLS = [
     ("ge_table_n_players", _int, [_vp]),
     ("ge_batch_create", _int, [_vp, _int, _u64, _u64, _u64, ctypes.POINTER(_vp)]),
     ("ge_batch_reset", _int, [_vp, _u64, _u64]),
+    ("ge_batch_clear_stats", _int, [_vp]),
     ("ge_batch_destroy", None, [_vp]),
+    ("ge_batch_set_stream", _int, [_vp, _vp]),
     ("ge_batch_set_kernel", _int, [_vp, _int]),
     ("ge_batch_get_kernel", _int, [_vp]),
     ("ge_step", _int, [_vp, _int, _vp]),

@@ -37,7 +37,7 @@ struct ge_table {
     uint32_t init_words[40];     // initial device record
 };
 
-typedef void (*step_fn)(const DevTable, uint8_t*, uint64_t, uint64_t, uint64_t, uint64_t, unsigned long long*, int);
+typedef void (*step_fn)(const DevTable, const StepArgs);
 
 struct ge_batch {
     ge_table* tab;
@@ -45,10 +45,15 @@ struct ge_batch {
     uint64_t n, n_tiles, first_sid, seed;
     uint8_t* d_tiles;
     size_t tiles_bytes;
-    unsigned long long* d_stats;
+    unsigned long long* d_stats;      // accumulator: counted/visits (step kernels) + harvested histograms
+    unsigned long long* d_stats_out;  // snapshot returned by ge_stats / ge_stats_device_ptr
     uint8_t* d_stage;
     size_t stage_bytes;
-    cudaStream_t stream;
+    cudaStream_t stream;          // stream in use (own_stream unless ge_batch_set_stream bound another)
+    cudaStream_t own_stream;
+    uint32_t* d_presence;         // 3 rotating phase-presence words (StepArgs::presence)
+    uint32_t launch_idx;          // index of the next step launch
+    uint32_t next_override;       // presence override for the next launch (0 = read the device word)
     int kernel;
     step_fn fn[3];               // by kernel id (COOP, TPS)
     int grid[3];
@@ -170,7 +175,42 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             if (br.op == BR_ALL_VAL_GE && br.a > 2) return fail(GE_ERR_ARG, "value field out of range");
             if (br.op > BR_TIE_PENDING) return fail(GE_ERR_ARG, "unknown branch op");
         }
-        t->dev.need[i] = 7;
+    }
+    // Column groups a step that STARTS in phase i must read besides column 0 (bit0 = dynamic masks C1:
+    // fields 2..5; bit1 = role/team C2: fields 6..11; bit2 = per-player bytes).  A group is needed when a
+    // predicate reads one of its fields or an effect read-modify-writes it; effects that overwrite a
+    // whole group (ASSIGN_ROLES -> C2, NIGHT_RESET -> player bytes) need no read.
+    auto pred_need = [&](int pi) -> uint8_t {
+        if (pi < 0 || pi >= h.n_preds) return 0;
+        const ge_pred_t& p = t->dev.pred[pi];
+        uint8_t out = 0;
+        const uint16_t lits[4] = {p.pos0, p.neg0, p.pos1, p.neg1};
+        for (int c = 0; c < 2; ++c) {
+            if (lits[2 * c + 1] & 0x8000u) continue;          // clause marked empty (& ~ALL)
+            const uint16_t used = lits[2 * c] | lits[2 * c + 1];
+            if (used & 0x003Cu) out |= 1;
+            if (used & 0x0FC0u) out |= 2;
+        }
+        return out;
+    };
+    auto entry_need = [&](int en) -> uint8_t { return (en == EN_ASSIGN_ROLES || en == EN_NIGHT_RESET) ? 1 : 0; };
+    for (int i = 0; i < h.n_phases; ++i) {
+        const ge_phase_t& ph = t->dev.phase[i];
+        uint8_t need = 0;
+        if (h.family != FAM_WEREWOLF) { t->dev.need[i] = 7; continue; }
+        if (ph.kind == KIND_TERMINAL) { t->dev.need[i] = 0; continue; }
+        if (ph.kind == KIND_ACTION) {
+            need |= pred_need(ph.actor_pred);
+            if (ph.action_op == ACT_PICK_PLAYER) need |= pred_need(ph.action_arg);
+            if (ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE) need |= 1 | 4;
+        }
+        for (int b = 0; b < ph.n_branches; ++b) {
+            const ge_branch_t& br = ph.br[b];
+            if (br.op == BR_COUNT_EQ0 || br.op == BR_COUNT_GE) need |= pred_need(br.a);
+            if (br.op == BR_COUNT_GE) need |= pred_need((int)br.arg);
+            need |= entry_need(t->dev.phase[br.next].entry_op);
+        }
+        t->dev.need[i] = need;
     }
     if (t->dev.phase[0].id != 0) return fail(GE_ERR_ARG, "phase index 0 must be DSL phase 0");
     t->family = h.family;
@@ -245,15 +285,34 @@ static int glue_grid(const ge_batch* b, uint64_t items, int block) {
 }
 
 // ------------------------------------------------------------------------------------ batch
-extern "C" int ge_batch_reset(ge_batch* b, uint64_t first_session_id, uint64_t seed) {
-    if (!b) return fail(GE_ERR_ARG, "batch is NULL");
-    CU(cudaSetDevice(b->device));
+static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) {
     b->first_sid = first_session_id;
     b->seed = seed;
     InitRec rec;
     memcpy(rec.w, b->tab->init_words, sizeof rec.w);
     k_init<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, b->stream>>>(b->d_tiles, b->n_tiles, (uint32_t)b->tab->rec_dev, rec);
     CU(cudaGetLastError());
+    b->launches++;
+    CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
+    b->next_override = 1u;        // every session is in phase index 0
+    return GE_OK;
+}
+
+// Statistics are cumulative over the life of the handle: before the sessions are overwritten their
+// final-state histograms are folded into the accumulator ("harvest"), so win rates cover every session
+// the batch ever simulated.
+extern "C" int ge_batch_reset(ge_batch* b, uint64_t first_session_id, uint64_t seed) {
+    if (!b) return fail(GE_ERR_ARG, "batch is NULL");
+    CU(cudaSetDevice(b->device));
+    k_stats<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, b->d_tiles, (uint32_t)b->tab->rec_dev, b->n, b->d_stats);
+    CU(cudaGetLastError());
+    b->launches++;
+    return init_sessions(b, first_session_id, seed);
+}
+
+extern "C" int ge_batch_clear_stats(ge_batch* b) {
+    if (!b) return fail(GE_ERR_ARG, "batch is NULL");
+    CU(cudaSetDevice(b->device));
     CU(cudaMemsetAsync(b->d_stats, 0, GE_STATS_LEN * sizeof(unsigned long long), b->stream));
     return GE_OK;
 }
@@ -276,9 +335,12 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     b->sm_count = prop.multiProcessorCount;
     e = cudaMalloc(&b->d_tiles, b->tiles_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_stats, GE_STATS_LEN * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_stats_out, GE_STATS_LEN * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_presence, 3 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking);
+    b->stream = b->own_stream;
     if (e != cudaSuccess) {
-        cudaFree(b->d_tiles); cudaFree(b->d_stats); delete b;
+        cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_presence); delete b;
         return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_create: ") + cudaGetErrorString(e));
     }
     for (int k = GE_KERNEL_COOP; k <= GE_KERNEL_TPS; ++k) {
@@ -294,7 +356,8 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
         b->grid[k] = g < 1 ? 1 : (int)g;
     }
     b->kernel = GE_KERNEL_TPS;
-    const int rc = ge_batch_reset(b, first_session_id, seed);
+    int rc = ge_batch_clear_stats(b);
+    if (rc == GE_OK) rc = init_sessions(b, first_session_id, seed);
     if (rc != GE_OK) { ge_batch_destroy(b); return rc; }
     *out = b;
     return GE_OK;
@@ -303,9 +366,18 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
 extern "C" void ge_batch_destroy(ge_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
-    cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stage);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->own_stream) { cudaStreamSynchronize(b->own_stream); cudaStreamDestroy(b->own_stream); }
+    cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_stage); cudaFree(b->d_presence);
     delete b;
+}
+
+extern "C" int ge_batch_set_stream(ge_batch* b, void* cuda_stream) {
+    if (!b) return fail(GE_ERR_ARG, "batch is NULL");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    return GE_OK;
 }
 
 extern "C" int ge_batch_set_kernel(ge_batch* b, int kernel) {
@@ -317,8 +389,14 @@ extern "C" int ge_batch_get_kernel(const ge_batch* b) { return b ? b->kernel : G
 
 static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaStream_t st) {
     const step_fn fn = b->fn[b->kernel];
+    StepArgs a;
+    a.tiles = b->d_tiles; a.n_sessions = b->n; a.n_tiles = b->n_tiles; a.first_sid = b->first_sid; a.seed = b->seed;
+    a.stats = b->d_stats; a.presence = b->d_presence; a.n_steps = steps_per_launch;
     for (int i = 0; i < n_launches; ++i) {
-        fn<<<b->grid[b->kernel], 128, 0, st>>>(b->tab->dev, b->d_tiles, b->n, b->n_tiles, b->first_sid, b->seed, b->d_stats, steps_per_launch);
+        a.launch_idx = b->launch_idx++;
+        a.presence_override = b->next_override;
+        b->next_override = 0;
+        fn<<<b->grid[b->kernel], 128, 0, st>>>(b->tab->dev, a);
         b->launches++;
     }
     CU(cudaGetLastError());
@@ -360,6 +438,7 @@ static int export_async(ge_batch* b, uint64_t first, uint64_t count, void* host_
     if (rc) return rc;
     k_export<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage);
     CU(cudaGetLastError());
+    b->launches++;
     CU(cudaMemcpyAsync(host_buf, b->d_stage, count * S, cudaMemcpyDeviceToHost, b->stream));
     return GE_OK;
 }
@@ -371,6 +450,9 @@ static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void*
     CU(cudaMemcpyAsync(b->d_stage, host_buf, count * S, cudaMemcpyHostToDevice, b->stream));
     k_import<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage);
     CU(cudaGetLastError());
+    b->launches++;
+    CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
+    b->next_override = 0xFFFFFFFFu;   // imported sessions can be in any phase
     return GE_OK;
 }
 
@@ -404,10 +486,11 @@ extern "C" int ge_stats_refresh(ge_batch* b, void* cuda_stream) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     CU(cudaSetDevice(b->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
-    CU(cudaMemsetAsync(b->d_stats + ST_WINNER, 0, (ST_VISITS - ST_WINNER) * sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(b->d_stats + ST_TAIL, 0, 256 * sizeof(unsigned long long), st));
-    k_stats<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->tab->dev, b->d_tiles, (uint32_t)b->tab->rec_dev, b->n, b->d_stats);
+    // snapshot = accumulator + histograms of the sessions currently resident
+    CU(cudaMemcpyAsync(b->d_stats_out, b->d_stats, GE_STATS_LEN * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    k_stats<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->tab->dev, b->d_tiles, (uint32_t)b->tab->rec_dev, b->n, b->d_stats_out);
     CU(cudaGetLastError());
+    b->launches++;
     return GE_OK;
 }
 
@@ -415,12 +498,12 @@ extern "C" int ge_stats(ge_batch* b, uint64_t* host_hist, size_t n) {
     if (!b || !host_hist || n < GE_STATS_LEN) return fail(GE_ERR_ARG, "bad arguments to ge_stats");
     int rc = ge_stats_refresh(b, nullptr);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(host_hist, b->d_stats, GE_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(host_hist, b->d_stats_out, GE_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return GE_OK;
 }
 
-extern "C" void* ge_stats_device_ptr(ge_batch* b) { return b ? (void*)b->d_stats : nullptr; }
+extern "C" void* ge_stats_device_ptr(ge_batch* b) { return b ? (void*)b->d_stats_out : nullptr; }
 
 extern "C" int ge_counted_steps(ge_batch* b, uint64_t* out) {
     if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_counted_steps");
@@ -439,7 +522,7 @@ extern "C" int ge_run_host(ge_batch* b, const void* records_in, void* records_ou
     if (records_out && (rc = export_async(b, 0, b->n, records_out)) != GE_OK) return rc;
     if (host_stats) {
         if ((rc = ge_stats_refresh(b, nullptr)) != GE_OK) return rc;
-        CU(cudaMemcpyAsync(host_stats, b->d_stats, GE_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaMemcpyAsync(host_stats, b->d_stats_out, GE_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
     }
     CU(cudaStreamSynchronize(b->stream));
     return GE_OK;

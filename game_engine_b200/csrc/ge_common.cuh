@@ -38,6 +38,28 @@ struct DevTable {
 static_assert(sizeof(ge_phase_t) == 48 && sizeof(ge_pred_t) == 8 && sizeof(ge_table_header_t) == 32, "table ABI");
 static_assert(sizeof(DevTable) <= 4000, "table must fit the kernel parameter space");
 
+// Per-launch arguments of every step kernel.
+struct StepArgs {
+    uint8_t* tiles;
+    uint64_t n_sessions, n_tiles, first_sid, seed;
+    unsigned long long* stats;
+    // Phase-presence masks (3 rotating words): launch k READS word k%3 (bit i = some session was in
+    // phase index i after launch k-1), ORs the phases its sessions end in into word (k+1)%3 and clears
+    // word (k+2)%3 for launch k+1.  presence_override != 0 replaces the read (first launch after a
+    // reset or an import, when the device words are not valid).
+    uint32_t* presence;
+    uint32_t launch_idx, presence_override;
+    int n_steps;
+};
+
+__device__ __forceinline__ void publish_presence(const StepArgs& A, uint32_t block_present) {
+    // called by all threads after a __syncthreads() that orders the block's shared accumulation
+    if (threadIdx.x == 0) {
+        if (block_present) atomicOr(&A.presence[(A.launch_idx + 1) % 3], block_present);
+        if (blockIdx.x == 0) A.presence[(A.launch_idx + 2) % 3] = 0;
+    }
+}
+
 // ---- Philox4x32-10 (Random123 constants; SPEC.md section 3) -------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll

@@ -65,8 +65,11 @@ __device__ __forceinline__ uint32_t wc_pred(const DevTable& T, const WScalars& s
 // P8: record bucket (8/16/24/32); L lanes per session = 8, 16 or 32.
 template <int P8>
 __global__ void __launch_bounds__(128)
-k_step_w_coop(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, uint64_t n_sessions, uint64_t n_tiles,
-              uint64_t first_sid, uint64_t seed, unsigned long long* __restrict__ stats, int n_steps) {
+k_step_w_coop(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
+    uint8_t* __restrict__ tiles = A.tiles;
+    const uint64_t n_sessions = A.n_sessions, n_tiles = A.n_tiles, first_sid = A.first_sid, seed = A.seed;
+    unsigned long long* __restrict__ stats = A.stats;
+    const int n_steps = A.n_steps;
     constexpr int S = 48 + P8;
     constexpr int L = P8 <= 8 ? 8 : P8 <= 16 ? 16 : 32;
     constexpr int G = 32 / L;                  // sessions per warp
@@ -251,14 +254,18 @@ k_step_w_coop(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, u
     }
     __syncthreads();
     flush_visits(s_visits, stats);
+    publish_presence(A, 0xFFFFFFFFu);      // this kernel loads every column; make the next launch do the same
 }
 
 // =================================================================================== TTL family
 // PB: player bucket of the device record (4/8/16/32) = lanes per session.
 template <int PB>
 __global__ void __launch_bounds__(128)
-k_step_t_coop(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, uint64_t n_sessions, uint64_t n_tiles,
-              uint64_t first_sid, uint64_t seed, unsigned long long* __restrict__ stats, int n_steps) {
+k_step_t_coop(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
+    uint8_t* __restrict__ tiles = A.tiles;
+    const uint64_t n_sessions = A.n_sessions, n_tiles = A.n_tiles, first_sid = A.first_sid, seed = A.seed;
+    unsigned long long* __restrict__ stats = A.stats;
+    const int n_steps = A.n_steps;
     constexpr int S = 8 + 4 * PB;
     constexpr int L = PB;
     constexpr int G = 32 / L;
@@ -410,6 +417,7 @@ k_step_t_coop(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, u
     }
     __syncthreads();
     flush_visits(s_visits, stats);
+    publish_presence(A, 0xFFFFFFFFu);      // this kernel loads every column; make the next launch do the same
 }
 
 }  // namespace ge

@@ -84,6 +84,14 @@ __device__ __forceinline__ void w_die(WState<P8>& s, int id) {
     s.alive &= bit; s.can_vote &= bit; s.eligible &= bit;
 }
 
+template <int NW>
+__device__ __forceinline__ void set_byte(uint32_t (&w)[NW], int p, uint32_t v) {
+    const int wi = p >> 2, sh = (p & 3) * 8;
+#pragma unroll
+    for (int i = 0; i < NW; ++i)
+        if (i == wi) w[i] = (w[i] & ~(0xFFu << sh)) | (v << sh);
+}
+
 // One step of one session.  Returns the phase index entered (for the visit counters) or -1 when the
 // session is terminal.  `dirty` collects which column groups changed.
 template <int P8>
@@ -104,58 +112,60 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t
 
     // ---- PhaseNode: ordered branch evaluation on the state before this step's effects
     int taken = ph.n_branches - 1;
-    for (int b = 0; b < ph.n_branches; ++b) {
-        const ge_branch_t br = ph.br[b];
-        bool ok;
-        switch (br.op) {
-        case BR_ALWAYS: ok = true; break;
-        case BR_COUNT_EQ0: ok = w_pred(T, s, br.a, ALL) == 0; break;
-        case BR_COUNT_GE: ok = __popc(w_pred(T, s, br.a, ALL)) >= __popc(w_pred(T, s, (int)br.arg, ALL)); break;
-        case BR_PREV_IN: ok = (br.arg >> prev) & 1u; break;
-        case BR_TIE_PENDING: ok = (revote & 0x80u) != 0; break;
-        default: ok = false; break;
+    if (ph.n_branches > 1) {
+        for (int b = 0; b < ph.n_branches; ++b) {
+            const ge_branch_t br = ph.br[b];
+            bool ok;
+            switch (br.op) {
+            case BR_ALWAYS: ok = true; break;
+            case BR_COUNT_EQ0: ok = w_pred(T, s, br.a, ALL) == 0; break;
+            case BR_COUNT_GE: ok = __popc(w_pred(T, s, br.a, ALL)) >= __popc(w_pred(T, s, (int)br.arg, ALL)); break;
+            case BR_PREV_IN: ok = (br.arg >> prev) & 1u; break;
+            case BR_TIE_PENDING: ok = (revote & 0x80u) != 0; break;
+            default: ok = false; break;
+            }
+            if (ok) { taken = b; break; }
         }
-        if (ok) { taken = b; break; }
     }
     const int Y = ph.br[taken].next;
     const uint32_t tag = ph.br[taken].tag;
 
-    // ---- BotBehaviorNode: every actor draws its choice; votes go straight into the tally
+    // ---- BotBehaviorNode: actors are visited in rank order (the i-th actor of every session in the
+    // same warp iteration, so lanes stay converged); the Philox block is recomputed only when it changes.
     if (ph.kind == KIND_ACTION) {
         const uint32_t actors = w_pred(T, s, ph.actor_pred, ALL);
-        const uint32_t legal0 = ph.action_op == ACT_PICK_PLAYER ? w_pred(T, s, ph.action_arg, ALL) : 0u;
-        const bool excl = ph.action_flags & 1;
+        const int aop = ph.action_op;
+        const uint32_t legal0 = aop == ACT_PICK_PLAYER ? w_pred(T, s, ph.action_arg, ALL) : 0u;
+        const uint32_t excl = (ph.action_flags & 1) ? 0xFFFFFFFFu : 0u;
+        const bool record = ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE;
         Tally<NPL> tally; tally.clear();
-        uint32_t chosen = 0, first_choice = 0; bool have_first = false;
-#pragma unroll
-        for (int b = 0; b < P8 / 4; ++b) {
-            const uint32_t ab = (actors >> (4 * b)) & 0xFu;
-            if (ab) {
-                const uint4 r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, k0, k1);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if ((ab >> j) & 1u) {
-                        const int p = 4 * b + j;
-                        const uint32_t r = word_of(r4, j);
-                        uint32_t choice;
-                        if (ph.action_op == ACT_PICK_PLAYER) {
-                            const uint32_t legal = excl ? (legal0 & ~(1u << p)) : legal0;
-                            const uint32_t n = __popc(legal);
-                            const int idx = kth_set_bit<P8>(legal, __umulhi(r, n));
-                            choice = n ? (uint32_t)idx + 1u : 0u;
-                            if (n) { chosen |= 1u << idx; tally.add(1u << idx); }
-                        } else if (ph.action_op == ACT_PICK_OPTION) {
-                            choice = 1u + __umulhi(r, (uint32_t)ph.action_arg);
-                        } else {
-                            choice = 1u;
-                        }
-                        if (!have_first) { first_choice = choice; have_first = true; }
-                        s.tw[b] = (s.tw[b] & ~(0xFFu << (8 * j))) | (choice << (8 * j));
-                    }
-                }
+        uint32_t chosen = 0, first_choice = 0;
+        uint32_t rem = actors;
+        int cur_blk = -1;
+        uint4 r4 = make_uint4(0, 0, 0, 0);
+        while (rem) {
+            const int p = __ffs(rem) - 1;
+            const bool is_first = rem == actors;
+            rem &= rem - 1;
+            const int blk = p >> 2;
+            if (blk != cur_blk) { r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)blk, k0, k1); cur_blk = blk; }
+            const uint32_t r = word_of(r4, p & 3);
+            uint32_t choice;
+            if (aop == ACT_PICK_PLAYER) {
+                const uint32_t legal = legal0 & ~(excl & (1u << p));
+                const uint32_t n = __popc(legal);
+                const int idx = kth_set_bit<P8>(legal, __umulhi(r, n));
+                choice = n ? (uint32_t)idx + 1u : 0u;
+                if (n) { chosen |= 1u << idx; tally.add(1u << idx); }
+            } else if (aop == ACT_PICK_OPTION) {
+                choice = 1u + __umulhi(r, (uint32_t)ph.action_arg);
+            } else {
+                choice = 1u;
             }
+            if (is_first) first_choice = choice;
+            if (record) set_byte(s.tw, p, choice);
         }
-        dirty |= DIRTY_PL;
+        if (record) dirty |= DIRTY_PL;
         // ---- RefereeNode, effects of the phase just left
         switch (ph.exit_op) {
         case EX_VOTE_KILL: {
@@ -193,8 +203,8 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t
 #pragma unroll
         for (int b = 0; b < P8 / 4; ++b) {
             if (4 * b < P) {
-                const uint4 r4 = philox4x32_10(sid_lo, sid_hi, step0, (1u << 16) | (uint32_t)b, k0, k1);
-                key[4 * b] = r4.x; key[4 * b + 1] = r4.y; key[4 * b + 2] = r4.z; key[4 * b + 3] = r4.w;
+                const uint4 q4 = philox4x32_10(sid_lo, sid_hi, step0, (1u << 16) | (uint32_t)b, k0, k1);
+                key[4 * b] = q4.x; key[4 * b + 1] = q4.y; key[4 * b + 2] = q4.z; key[4 * b + 3] = q4.w;
             } else {
                 key[4 * b] = key[4 * b + 1] = key[4 * b + 2] = key[4 * b + 3] = 0;
             }
@@ -232,49 +242,60 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t
     return Y;
 }
 
+// Column groups a launch must load, from the phases present in the batch (see StepArgs::presence).
+__device__ __forceinline__ uint32_t need_of(const DevTable& T, uint32_t present) {
+    uint32_t need = 0;
+    while (present) { const int i = __ffs(present) - 1; present &= present - 1; need |= T.need[i]; }
+    return need;
+}
+
 template <int P8>
-__global__ void __launch_bounds__(128)
-k_step_w_tps(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, uint64_t n_sessions, uint64_t n_tiles,
-             uint64_t first_sid, uint64_t seed, unsigned long long* __restrict__ stats, int n_steps) {
+__global__ void __launch_bounds__(128, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
+k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
     constexpr int S = 48 + P8;
     constexpr int NT16 = P8 / 16;          // full 16-byte target columns
     constexpr bool THALF = (P8 % 16) != 0; // trailing 8-byte column
     __shared__ uint32_t s_visits[32];
+    __shared__ uint32_t s_present;
     if (threadIdx.x < 32) s_visits[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_present = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
+    // which column groups can any session of this batch need?  (bit0 C1, bit1 C2, bit2 player bytes)
+    const uint32_t present_in = A.presence_override ? A.presence_override : A.presence[A.launch_idx % 3];
+    const uint32_t need = A.n_steps > 1 ? 7u : need_of(T, present_in);
+    uint32_t present_out = 0;
 
-    for (uint64_t tile = warp0; tile < n_tiles; tile += nwarps) {
-        uint8_t* base = tiles + tile * (uint64_t)(32 * S);
+    for (uint64_t tile = warp0; tile < A.n_tiles; tile += nwarps) {
+        uint8_t* base = A.tiles + tile * (uint64_t)(32 * S);
         const uint64_t sess = tile * 32 + lane;
-        const bool in_range = sess < n_sessions;
         WState<P8> s;
-        {
-            const uint4 c0 = ld128(base + lane * 16);
-            s.h0 = c0.x; s.h1 = c0.y; s.alive = c0.z; s.can_vote = c0.w;
-        }
-        bool live = in_range && T.phase[s.h0 & 0xFF].kind != KIND_TERMINAL;
-        if (live) {
-            const uint4 c1 = ld128(base + 512 + lane * 16);
-            const uint4 c2 = ld128(base + 1024 + lane * 16);
-            s.eligible = c1.x; s.submitted = c1.y; s.revealed = c1.z; s.investigated = c1.w;
-            s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
+        // all loads are issued up front (no dependent second round trip)
+        const uint4 c0 = ld128(base + lane * 16);
+        uint4 c1 = make_uint4(0, 0, 0, 0), c2 = make_uint4(0, 0, 0, 0);
+        if (need & 1) c1 = ld128(base + 512 + lane * 16);
+        if (need & 2) c2 = ld128(base + 1024 + lane * 16);
 #pragma unroll
-            for (int c = 0; c < NT16; ++c) {
-                const uint4 t = ld128(base + (3 + c) * 512 + lane * 16);
-                s.tw[4 * c] = t.x; s.tw[4 * c + 1] = t.y; s.tw[4 * c + 2] = t.z; s.tw[4 * c + 3] = t.w;
-            }
-            if (THALF) {
-                const uint2 t = ld64(base + (3 + NT16) * 512 + lane * 8);
-                s.tw[4 * NT16] = t.x; s.tw[4 * NT16 + 1] = t.y;
-            }
+        for (int c = 0; c < NT16; ++c) {
+            uint4 t = make_uint4(0, 0, 0, 0);
+            if (need & 4) t = ld128(base + (3 + c) * 512 + lane * 16);
+            s.tw[4 * c] = t.x; s.tw[4 * c + 1] = t.y; s.tw[4 * c + 2] = t.z; s.tw[4 * c + 3] = t.w;
         }
-        const uint64_t sid = first_sid + sess;
+        if (THALF) {
+            uint2 t = make_uint2(0, 0);
+            if (need & 4) t = ld64(base + (3 + NT16) * 512 + lane * 8);
+            s.tw[4 * NT16] = t.x; s.tw[4 * NT16 + 1] = t.y;
+        }
+        s.h0 = c0.x; s.h1 = c0.y; s.alive = c0.z; s.can_vote = c0.w;
+        s.eligible = c1.x; s.submitted = c1.y; s.revealed = c1.z; s.investigated = c1.w;
+        s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
+        bool live = sess < A.n_sessions;
+        const uint64_t sid = A.first_sid + sess;
         uint32_t dirty = 0;
-        for (int it = 0; it < n_steps; ++it) {
+        for (int it = 0; it < A.n_steps; ++it) {
             int np = -1;
             if (live) {
                 np = w_step<P8>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
@@ -282,6 +303,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, ui
             }
             count_visit(s_visits, np, lane);
         }
+        if (sess < A.n_sessions) present_out |= 1u << (s.h0 & 31);
         if (dirty & DIRTY_C0) st128(base + lane * 16, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
         if (dirty & DIRTY_C1) st128(base + 512 + lane * 16, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
         if (dirty & DIRTY_C2) st128(base + 1024 + lane * 16, make_uint4(s.wolf, s.secret, s.role_lo, s.role_hi));
@@ -292,8 +314,11 @@ k_step_w_tps(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, ui
             if (THALF) st64(base + (3 + NT16) * 512 + lane * 8, make_uint2(s.tw[4 * NT16], s.tw[4 * NT16 + 1]));
         }
     }
+    present_out = __reduce_or_sync(0xFFFFFFFFu, present_out);
+    if (lane == 0 && present_out) atomicOr(&s_present, present_out);
     __syncthreads();
-    flush_visits(s_visits, stats);
+    flush_visits(s_visits, A.stats);
+    publish_presence(A, s_present);
 }
 
 // =================================================================================== TTL family
@@ -446,8 +471,11 @@ __device__ __forceinline__ int t_step(const DevTable& T, TState<PB>& s, uint32_t
 
 template <int PB>
 __global__ void __launch_bounds__(128)
-k_step_t_tps(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, uint64_t n_sessions, uint64_t n_tiles,
-             uint64_t first_sid, uint64_t seed, unsigned long long* __restrict__ stats, int n_steps) {
+k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
+    uint8_t* __restrict__ tiles = A.tiles;
+    const uint64_t n_sessions = A.n_sessions, n_tiles = A.n_tiles, first_sid = A.first_sid, seed = A.seed;
+    unsigned long long* __restrict__ stats = A.stats;
+    const int n_steps = A.n_steps;
     constexpr int S = 8 + 4 * PB;           // device record (PB even => S % 8 == 0)
     constexpr int NW = S / 4;
     constexpr int N16 = S / 16;
@@ -496,6 +524,7 @@ k_step_t_tps(const __grid_constant__ DevTable T, uint8_t* __restrict__ tiles, ui
     }
     __syncthreads();
     flush_visits(s_visits, stats);
+    publish_presence(A, 0xFFFFFFFFu);      // this kernel loads every column; make the next launch do the same
 }
 
 }  // namespace ge

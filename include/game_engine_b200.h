@@ -78,9 +78,15 @@ int ge_table_n_players(const ge_table *t);
  * (reference agent/tools/utils.py:584-653) and AgentState defaults (game_agent_v2.py:97-117). */
 int ge_batch_create(ge_table *t, int device, uint64_t n_sessions, uint64_t first_session_id, uint64_t seed,
                     ge_batch **out);
-/* Re-initialise all sessions (new ids / seed), zero the statistics. */
+/* Re-initialise all sessions with new ids / seed.  Statistics are cumulative over the life of the
+ * handle: the final-state histograms of the sessions being replaced are folded into the accumulator
+ * first, so win rates cover every session the batch ever simulated.  ge_batch_clear_stats zeroes it. */
 int ge_batch_reset(ge_batch *b, uint64_t first_session_id, uint64_t seed);
+int ge_batch_clear_stats(ge_batch *b);
 void ge_batch_destroy(ge_batch *b);
+/* Bind all work of this batch to an external CUDA stream (e.g. the caller's torch stream); NULL
+ * returns to the batch's own stream.  The stream is borrowed, not owned. */
+int ge_batch_set_stream(ge_batch *b, void *cuda_stream);
 int ge_batch_set_kernel(ge_batch *b, int kernel);
 int ge_batch_get_kernel(const ge_batch *b);
 
@@ -119,7 +125,7 @@ int ge_counted_steps(ge_batch *b, uint64_t *out);
 /* device pointer / size of the tiled session store (for profiling and tests) */
 void *ge_state_device_ptr(ge_batch *b);
 size_t ge_state_device_bytes(const ge_batch *b);
-/* number of step-kernel launches issued by this batch since creation */
+/* number of kernel launches (step + glue kernels) issued by this batch since creation */
 uint64_t ge_launch_count(const ge_batch *b);
 
 const char *ge_last_error(void);

@@ -181,9 +181,11 @@ static int pred_holds(const tab_t *t, const sess_t *s, int pred, int p) {
     for (int c = 0; c < 2; ++c) {
         uint16_t pos = rd16(q + 4 * c), neg = rd16(q + 4 * c + 2);
         int ok = 1;
-        for (int f = 0; f < 16; ++f) {
-            if (((pos >> f) & 1) && !field_of(t, s, f, p)) ok = 0;
-            if (((neg >> f) & 1) && field_of(t, s, f, p)) ok = 0;
+        for (int f = 0; f < 16 && ok; ++f) {
+            if (!(((pos | neg) >> f) & 1)) continue;
+            const int v = field_of(t, s, f, p);
+            if (((pos >> f) & 1) && !v) ok = 0;
+            if (((neg >> f) & 1) && v) ok = 0;
         }
         if (ok) return 1;
     }
@@ -228,7 +230,10 @@ static int step_session(const tab_t *t, sess_t *s, uint64_t seed, uint64_t sid, 
 
     /* --- bots act (BotBehaviorNode) --- */
     if (ph[1] == KIND_ACTION) {
+        uint8_t legal_ok[MAXP] = {0};      /* legal set on the state at the start of the step */
         for (int p = 0; p < P; ++p) actor[p] = (uint8_t)pred_holds(t, s, ph[8], p);
+        if (ph[2] == ACT_PICK_PLAYER)
+            for (int q = 0; q < P; ++q) legal_ok[q] = (uint8_t)pred_holds(t, s, ph[3], q);
         for (int p = 0; p < P; ++p) {
             if (!actor[p]) continue;
             if (first_actor < 0) first_actor = p;
@@ -237,7 +242,7 @@ static int step_session(const tab_t *t, sess_t *s, uint64_t seed, uint64_t sid, 
                 int legal[MAXP], n = 0;
                 for (int q = 0; q < P; ++q) {
                     if ((ph[4] & 1) && q == p) continue;
-                    if (pred_holds(t, s, ph[3], q)) legal[n++] = q;
+                    if (legal_ok[q]) legal[n++] = q;
                 }
                 choice[p] = n ? (uint8_t)(1 + legal[mulhi32(r, (uint32_t)n)]) : 0;
             } else if (ph[2] == ACT_PICK_OPTION) {

@@ -1,0 +1,124 @@
+"""DSL -> transition-table compiler: grammar, DNF predicates, table layout, reference-file equivalence."""
+import os
+import struct
+
+import pytest
+import yaml
+
+from conftest import REFERENCE, has_reference
+from game_engine_b200 import compile_game, DSLCompileError
+from game_engine_b200 import compiler as C
+from game_engine_b200 import table as T
+
+WEREWOLF, TTL = "werewolf-(mafia)", "two-truths-and-a-lie"
+
+
+def test_werewolf_table_matches_hand_written_expectation(games):
+    cg = games(WEREWOLF, 8)
+    t = cg.table
+    assert cg.phase_ids == list(range(17)) + [99]
+    assert cg.record_size == 56 and t.n_wolves == 2 and t.family == T.FAMILY_WEREWOLF
+    assert t.init_masks == 0b11                       # is_alive, can_vote start true (template)
+    kinds = [p.kind for p in t.phases]
+    U, M, A, X = T.KIND_UI, T.KIND_TIMER, T.KIND_ACTION, T.KIND_TERMINAL
+    assert kinds == [U, U, A, A, A, U, M, A, U, U, A, A, A, U, M, A, U, X]
+    assert [p.exit_op for p in t.phases] == [0, 0, 1, 2, 3, 0, 0, 4, 0, 0, 1, 2, 3, 0, 0, 4, 0, 0]
+    assert [p.entry_op for p in t.phases] == [0, 1, 2, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0]
+    # simple edges
+    nxt = {p.id: [cg.phase_ids[b.next] for b in p.branches] for p in t.phases}
+    assert nxt[0] == [1] and nxt[8] == [9] and nxt[13] == [9] and nxt[16] == [9] and nxt[99] == []
+    # the win-check phase: ordered branches, first match wins
+    br = t.phases[9].branches
+    assert [b.op for b in br] == [T.BR_COUNT_EQ0, T.BR_COUNT_GE, T.BR_PREV_IN, T.BR_PREV_IN]
+    assert nxt[9] == [99, 99, 10, 14] and [b.tag for b in br] == [1, 2, 0, 0]
+    assert br[2].arg == (1 << 8) | (1 << 16) and br[3].arg == 1 << 13
+    wolves_alive = (1 << 6 | 1 << 0, 0) + T.CLAUSE_EMPTY
+    villagers_alive = (1 << 0, 1 << 6) + T.CLAUSE_EMPTY
+    assert t.preds[br[0].a] == wolves_alive and t.preds[br[1].a] == wolves_alive and t.preds[br[1].arg] == villagers_alive
+    # actor predicates: role == 'Werewolf' and alive; can_vote and alive
+    assert t.preds[t.phases[2].actor_pred] == (1 << 9 | 1, 0) + T.CLAUSE_EMPTY
+    assert t.preds[t.phases[7].actor_pred] == (0b11, 0) + T.CLAUSE_EMPTY
+    assert t.phases[4].action_flags == T.ACTF_EXCLUDE_SELF and t.phases[3].action_flags == 0
+
+
+def test_ttl_table_matches_hand_written_expectation(games):
+    cg = games(TTL, 4)
+    t = cg.table
+    assert cg.phase_ids == list(range(9)) + [99] and cg.record_size == 24 and t.rounds == 1
+    assert t.init_masks == 1 << 3                      # can_vote
+    assert [p.kind for p in t.phases] == [0, 0, 2, 2, 1, 2, 0, 0, 0, 3]
+    assert [p.action_op for p in t.phases] == [0, 0, T.ACT_MARK, T.ACT_PICK_OPTION, 0, T.ACT_PICK_OPTION, 0, 0, 0, 0]
+    assert [p.entry_op for p in t.phases] == [0, 16, 0, 0, 0, 0, 17, 18, 0, 19]
+    b = t.phases[8].branches
+    assert [(x.op, cg.phase_ids[x.next]) for x in b] == [(T.BR_ALL_VAL_GE, 99), (T.BR_ALWAYS, 1)]
+    assert b[0].a == T.T_VAL_FIELDS["rounds_as_speaker"] and b[0].arg == 1
+    assert t.preds[t.phases[5].actor_pred] == (1 << 3, 1 << 0) + T.CLAUSE_EMPTY     # not speaker and can_vote
+
+
+def test_blob_layout_round_trip(games):
+    for cg in (games(WEREWOLF, 8), games(WEREWOLF, 32), games(TTL, 4)):
+        blob = cg.blob
+        assert blob[:4] == b"GETB" and struct.unpack_from("<H", blob, 4)[0] == 1
+        assert len(blob) == 32 + 48 * len(cg.table.phases) + 8 * len(cg.table.preds)
+        assert T.Table.unpack(blob).pack() == blob
+
+
+@pytest.mark.parametrize("P,W", [(4, 1), (7, 1), (8, 2), (16, 4), (32, 8)])
+def test_wolf_count_rule(P, W):
+    assert compile_game(WEREWOLF, P).table.n_wolves == W
+
+
+def test_record_sizes():
+    assert [T.record_size(T.FAMILY_WEREWOLF, p) for p in (8, 16, 32, 5)] == [56, 64, 80, 56]
+    assert [T.record_size(T.FAMILY_TTL, p) for p in (4, 3, 8, 32)] == [24, 24, 40, 136]
+
+
+def test_condition_grammar():
+    fm = C._FieldMap(T.FAMILY_WEREWOLF, ["Villager", "Werewolf", "Doctor", "Detective"], "werewolves", "villagers")
+    cp = lambda s: C.compile_predicate(s, fm)
+    assert cp("player.is_alive == true") == (1, 0) + T.CLAUSE_EMPTY
+    assert cp("player.is_alive == false") == (0, 1) + T.CLAUSE_EMPTY
+    assert cp("player.is_alive != true") == (0, 1) + T.CLAUSE_EMPTY
+    assert cp("player.team == 'villagers' and player.is_alive == true") == (1, 1 << 6) + T.CLAUSE_EMPTY
+    assert cp("player.role in ['Doctor', 'Detective'] and player.is_alive == true") == (1 << 10 | 1, 0, 1 << 11 | 1, 0)
+    assert cp("not (player.is_alive == true or player.can_vote == true)") == (0, 0b11) + T.CLAUSE_EMPTY
+    assert cp("(player.role == 'Doctor' or player.role == 'Detective') and player.is_alive") == (1 << 10 | 1, 0, 1 << 11 | 1, 0)
+    with pytest.raises(DSLCompileError):
+        cp("player.role == 'Seer'")
+    with pytest.raises(DSLCompileError):
+        cp("player.is_alive === true")
+    with pytest.raises(DSLCompileError):
+        cp("player.role in ['Doctor','Detective','Villager']")      # needs 3 clauses
+
+
+def test_audience_groups_compile(games):
+    aud = games(WEREWOLF, 8).audience_preds
+    assert set(aud) == {"werewolves", "villagers", "alive_players", "dead_players", "special_roles", "night_actors",
+                        "voters", "secret_holders"}
+    assert aud["dead_players"] == (0, 1) + T.CLAUSE_EMPTY
+
+
+def test_branch_keys_must_be_annotated_in_order():
+    dsl = C.load_dsl(WEREWOLF)
+    rules = C.load_rules(WEREWOLF)
+    rules["phases"][9]["branches"] = list(reversed(rules["phases"][9]["branches"]))
+    with pytest.raises(DSLCompileError):
+        compile_game(WEREWOLF, 8, dsl=dsl, rules=rules)
+
+
+def test_player_count_limits():
+    with pytest.raises(DSLCompileError):
+        compile_game(WEREWOLF, 3)            # min_players 4
+    with pytest.raises(DSLCompileError):
+        compile_game(TTL, 33)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not has_reference(), reason="needs /root/reference")
+@pytest.mark.parametrize("game,P", [(WEREWOLF, 8), (WEREWOLF, 32), (TTL, 4)])
+def test_reference_yaml_compiles_to_identical_table(game, P):
+    """The shipped condensed game files lose nothing the compiler consumes."""
+    with open(os.path.join(REFERENCE, "games", game + ".yaml"), encoding="utf-8") as f:
+        ref = yaml.safe_load(f)
+    a, b = compile_game(game, P, dsl=ref), compile_game(game, P)
+    assert a.blob == b.blob and a.phase_names == b.phase_names and a.template == b.template
