@@ -193,6 +193,7 @@ k_step_w_coop(const __grid_constant__ DevTable T, const __grid_constant__ StepAr
                     case EX_INVESTIGATE_RESOLVE:
                         s.submitted |= actors; s.investigated |= chosen; d1 = true;
                         if (kill != 0 && kill != protect) { const uint32_t bit = ~(1u << (kill - 1)); s.alive &= bit; s.can_vote &= bit; s.eligible &= bit; }
+                        kill = 0; protect = 0;
                         break;
                     case EX_DAY_VOTE:
                         if (T.h.max_revotes > 0 && tied && (revote & 0x7Fu) < T.h.max_revotes) {

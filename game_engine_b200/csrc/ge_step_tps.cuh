@@ -180,6 +180,7 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t
         case EX_INVESTIGATE_RESOLVE:
             s.submitted |= actors; s.investigated |= chosen; dirty |= DIRTY_C1;
             if (kill != 0 && kill != protect) w_die(s, (int)kill);
+            kill = 0; protect = 0;
             break;
         case EX_DAY_VOTE: {
             const uint32_t top = tally.top();

@@ -289,6 +289,7 @@ static int step_session(const tab_t *t, sess_t *s, uint64_t seed, uint64_t sid, 
         if (ph[5] == EX_INVESTIGATE_RESOLVE) {
             for (int p = 0; p < P; ++p) if (actor[p] && choice[p]) s->investigated[choice[p] - 1] = 1;
             if (s->kill_target && s->kill_target != s->protect_target) die(s, s->kill_target);
+            s->kill_target = 0; s->protect_target = 0;
         }
         break;
     case EX_DAY_VOTE: {

@@ -1,0 +1,41 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.json.gz: traces of the reference's real nodes (Oracle A) for the parity configs.
+
+Run in the build container (needs /root/reference):   python -m oracle.ref_harness.gen_golden
+Each fixture: {"game", "players", "seed", "sid", "trace": [state after 0, 1, 2, ... steps]} with wall-clock
+timestamps removed (oracle/ref_harness/driver.py:snapshot)."""
+import gzip
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_harness.driver import run_session  # noqa: E402
+
+CASES = [
+    # BASELINE.json configs[0]: two-truths-and-a-lie, 1 session, 4 seeded bots; seeds of SURVEY 8d config 1
+    ("two-truths-and-a-lie", 4, 0, 0), ("two-truths-and-a-lie", 4, 1, 0), ("two-truths-and-a-lie", 4, 0xC0FFEE, 0),
+    ("two-truths-and-a-lie", 3, 2, 1), ("two-truths-and-a-lie", 7, 5, 1 << 40),
+    ("werewolf-(mafia)", 8, 0, 0), ("werewolf-(mafia)", 8, 1, 1), ("werewolf-(mafia)", 8, 7, 123456789012),
+    ("werewolf-(mafia)", 8, 20261018, 4242), ("werewolf-(mafia)", 5, 3, 3), ("werewolf-(mafia)", 16, 4, 9),
+    ("werewolf-(mafia)", 32, 6, 31),
+]
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for game, P, seed, sid in CASES:
+        trace = run_session(game, P, seed, sid)
+        name = "%s_p%d_seed%d_sid%d.json.gz" % (game.replace("(", "").replace(")", ""), P, seed, sid)
+        blob = json.dumps({"game": game, "players": P, "seed": seed, "sid": sid, "trace": trace}, ensure_ascii=False,
+                          sort_keys=True, separators=(",", ":")).encode("utf-8")
+        with gzip.GzipFile(os.path.join(out_dir, name), "wb", mtime=0) as f:
+            f.write(blob)
+        print("%-60s %3d steps  %6d bytes" % (name, len(trace) - 1, os.path.getsize(os.path.join(out_dir, name))))
+
+
+if __name__ == "__main__":
+    main()
