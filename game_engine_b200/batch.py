@@ -73,6 +73,17 @@ class SessionBatch:
             self.seed = int(seed)
         capi.check(capi.lib().ge_batch_reset(self._h, self.first_session_id, self.seed))
 
+    def set_compaction(self, every_n_steps: int, min_dead_shift: int = 2) -> None:
+        """Active-prefix compaction: check every n steps, compact when >= 1/2^shift of the prefix is dead
+        (0 steps = off; default (8, 2))."""
+        capi.check(capi.lib().ge_batch_set_compaction(self._h, int(every_n_steps), int(min_dead_shift)))
+
+    def active(self) -> int:
+        """Length of the slot prefix that can still hold live sessions (synchronises)."""
+        v = ctypes.c_uint64()
+        capi.check(capi.lib().ge_batch_active(self._h, ctypes.byref(v)))
+        return int(v.value)
+
     def clear_stats(self) -> None:
         capi.check(capi.lib().ge_batch_clear_stats(self._h))
 

@@ -30,6 +30,8 @@ SYMBOLS = [
     ("ge_batch_destroy", None, [_vp]),
     ("ge_batch_set_stream", _int, [_vp, _vp]),
     ("ge_batch_set_kernel", _int, [_vp, _int]),
+    ("ge_batch_set_compaction", _int, [_vp, _int, _int]),
+    ("ge_batch_active", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_get_kernel", _int, [_vp]),
     ("ge_step", _int, [_vp, _int, _vp]),
     ("ge_run_fused", _int, [_vp, _int, _vp]),

@@ -51,6 +51,15 @@ struct ge_batch {
     size_t stage_bytes;
     cudaStream_t stream;          // stream in use (own_stream unless ge_batch_set_stream bound another)
     cudaStream_t own_stream;
+    // active-prefix compaction (see k_compact_*): slot -> original index, per-tile live masks, scratch
+    uint32_t* d_origin;
+    uint32_t* d_live_mask;
+    uint32_t* d_prefix;           // per-tile prefix inside a scan block
+    uint32_t* d_blk;              // per-scan-block prefix
+    int scan_blocks, dead_shift;
+    unsigned long long* d_cstate; // [0] n_active  [1] n_live  [2] pairs to swap  [3] live already in front  [4] old tiles
+    int compact_every, since_compact;
+    bool compacted;               // origin may differ from identity
     uint32_t* d_presence;         // 3 rotating phase-presence words (StepArgs::presence)
     uint32_t launch_idx;          // index of the next step launch
     uint32_t next_override;       // presence override for the next launch (0 = read the device word)
@@ -60,12 +69,17 @@ struct ge_batch {
     uint64_t launches;
 };
 
+static int restore_order(ge_batch* b);
+static int ensure_stage(ge_batch* b, size_t bytes);
+
 // ------------------------------------------------------------------------------------ glue kernels
 struct InitRec { uint32_t w[40]; };
 
 __device__ __forceinline__ uint32_t rt_tile_off(uint32_t o, uint32_t sl, uint32_t n16) {
     return (o / 16u < n16) ? (o / 16u) * 512u + sl * 16u + (o % 16u) : n16 * 512u + sl * 8u + (o - 16u * n16);
 }
+
+__global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
 
 __global__ void k_init(uint8_t* tiles, uint64_t n_tiles, uint32_t S, const __grid_constant__ InitRec rec) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,6 +158,149 @@ k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev
     }
 }
 
+// ------------------------------------------------------------------------------------ compaction
+// Active-prefix compaction.  All live sessions of a batch advance in lockstep, so finished games leave
+// holes that still cost issue slots.  Periodically the live sessions at the back are swapped, in place,
+// with terminal sessions at the front; step kernels then walk only slots [0, n_active).  Inputs are the
+// per-tile live masks and the live count the step kernel publishes — no pass over the records.  A swap
+// costs about one step of traffic, so it only runs when a quarter of the prefix is dead (dead_shift = 2).
+// Deterministic: ranks come from an exclusive scan, not from atomics.
+// cstate: [0] n_active [1] n_live [2] pairs [3] live already in front [4] tiles of the old prefix
+//         [5] live sessions after the last counted step (written by the step kernel) [6] scan ticket
+constexpr int CS_TILES = 1024;          // tiles per scan block
+
+__global__ void k_iota(uint32_t* origin, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) origin[i] = (uint32_t)i;
+}
+
+__global__ void k_cstate_reset(unsigned long long* cstate, unsigned long long n) {
+    if (threadIdx.x < 8) cstate[threadIdx.x] = threadIdx.x == 0 ? n : 0ull;
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += u; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += u; }
+        s_warp[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    return s_warp[warp] + incl - v;
+}
+
+// grid = ceil(max tiles / 1024) blocks of 1024 threads.  loc[t] = live sessions in tiles of the same block
+// before t, blk[b] = live sessions in blocks before b (filled in by the last block to finish).
+__global__ void __launch_bounds__(1024)
+k_compact_scan(const uint32_t* __restrict__ live_mask, uint32_t* loc, uint32_t* blk, unsigned long long* cstate, uint32_t dead_shift) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_last;
+    const uint64_t n_act = cstate[0];
+    const uint64_t live_now = cstate[5];
+    const uint64_t nt = (n_act + 31) >> 5;
+    const uint32_t nblk = (uint32_t)((nt + CS_TILES - 1) / CS_TILES);
+    // every block takes the same decision from the same two words (nobody writes them in this kernel)
+    if (live_now > n_act || ((n_act - live_now) << dead_shift) < n_act) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { cstate[1] = n_act; cstate[2] = 0; }
+        return;
+    }
+    if (blockIdx.x >= nblk) return;
+    const uint64_t t = (uint64_t)blockIdx.x * CS_TILES + threadIdx.x;
+    const uint32_t cnt = t < nt ? (uint32_t)__popc(live_mask[t]) : 0u;
+    const uint32_t excl = block_excl_scan_1024(cnt, s_warp, &s_total);
+    if (t < nt) loc[t] = excl;
+    if (threadIdx.x == 0) {
+        blk[blockIdx.x] = s_total;
+        __threadfence();
+        s_last = atomicAdd(&cstate[6], 1ull) == (unsigned long long)(nblk - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: exclusive scan of the block totals (nblk <= 1024), then the bounds of the swap
+    const uint32_t bt = threadIdx.x < nblk ? ((volatile uint32_t*)blk)[threadIdx.x] : 0u;
+    const uint32_t be = block_excl_scan_1024(bt, s_warp, &s_total);
+    if (threadIdx.x < nblk) blk[threadIdx.x] = be;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t n_live = s_total;
+        uint64_t pairs = 0, in_front = n_live;
+        if (n_live < n_act) {
+            const uint64_t tb = n_live >> 5;
+            const uint32_t lb = (uint32_t)(n_live & 31);
+            in_front = ((volatile uint32_t*)blk)[tb / CS_TILES] + ((volatile uint32_t*)loc)[tb] + __popc(live_mask[tb] & ((1u << lb) - 1u));
+            pairs = n_live - in_front;
+        }
+        cstate[0] = n_live; cstate[1] = n_live; cstate[2] = pairs; cstate[3] = in_front; cstate[4] = nt; cstate[6] = 0;
+    }
+}
+
+// Pair i swaps the i-th terminal session of the front region [0, n_live) with the i-th live session of the
+// back region [n_live, old prefix).  Both are located by binary search over the two-level prefix
+// P(t) = blk[t / 1024] + loc[t] (terminals before tile t = 32t - P(t)).  One thread per pair.
+__global__ void k_compact_swap(uint8_t* tiles, uint32_t S, uint32_t* origin, const uint32_t* __restrict__ live_mask,
+                               const uint32_t* __restrict__ loc, const uint32_t* __restrict__ blk, unsigned long long* cstate) {
+    const uint64_t n_live = cstate[1], pairs = cstate[2], in_front = cstate[3], nt = cstate[4];
+    if (blockIdx.x == 0 && threadIdx.x == 0) cstate[5] = 0;      // the next counted step starts from zero
+    if (pairs == 0) return;
+    const uint32_t n16 = S / 16;
+    const bool half = (S % 16) != 0;
+    const uint64_t tb = n_live >> 5;
+    const uint32_t lb = (uint32_t)(n_live & 31);
+    auto P = [&](uint64_t t) -> uint64_t { return (uint64_t)blk[t / CS_TILES] + loc[t]; };
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t lo = 0, hi = tb;                                // front: largest t in [0, tb] with 32t - P(t) <= i
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if (32 * mid - P(mid) <= i) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t valid_a = lo == tb ? ((1u << lb) - 1u) : 0xFFFFFFFFu;
+        const uint32_t a = (uint32_t)(32 * lo) + (uint32_t)kth_set_bit<32>(~live_mask[lo] & valid_a, (uint32_t)(i - (32 * lo - P(lo))));
+        const uint64_t r = in_front + i;                          // back: largest t in [tb, nt-1] with P(t) <= r
+        lo = tb; hi = nt - 1;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if (P(mid) <= r) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t b = (uint32_t)(32 * lo) + (uint32_t)kth_set_bit<32>(live_mask[lo], (uint32_t)(r - P(lo)));
+        uint8_t* ba = tiles + (uint64_t)(a >> 5) * (32ull * S);
+        uint8_t* bb = tiles + (uint64_t)(b >> 5) * (32ull * S);
+        for (uint32_t c = 0; c < n16; ++c) {
+            uint4* pa = reinterpret_cast<uint4*>(ba + c * 512u + (a & 31) * 16u);
+            uint4* pb = reinterpret_cast<uint4*>(bb + c * 512u + (b & 31) * 16u);
+            const uint4 t = *pa; *pa = *pb; *pb = t;
+        }
+        if (half) {
+            uint2* pa = reinterpret_cast<uint2*>(ba + n16 * 512u + (a & 31) * 8u);
+            uint2* pb = reinterpret_cast<uint2*>(bb + n16 * 512u + (b & 31) * 8u);
+            const uint2 t = *pa; *pa = *pb; *pb = t;
+        }
+        const uint32_t t = origin[a]; origin[a] = origin[b]; origin[b] = t;
+    }
+}
+
+// tiles -> canonical records in ORIGINAL session order when slots have been permuted by compaction
+__global__ void k_export_perm(const uint8_t* tiles, uint32_t S_dev, uint32_t S_canon, const uint32_t* __restrict__ origin,
+                              uint64_t n, uint64_t first, uint64_t count, uint8_t* out) {
+    const uint32_t n16 = S_dev / 16;
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = origin[slot];
+        if (o < first || o >= first + count) continue;
+        const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S_dev);
+        const uint32_t sl = (uint32_t)(slot & 31);
+        for (uint32_t k = 0; k < S_canon / 8; ++k)
+            *reinterpret_cast<uint2*>(out + (o - first) * S_canon + 8 * k) = *reinterpret_cast<const uint2*>(base + rt_tile_off(8 * k, sl, n16));
+    }
+}
+
 // ------------------------------------------------------------------------------------ table
 static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     if (!blob || n < sizeof(ge_table_header_t)) return fail(GE_ERR_ARG, "table blob too small");
@@ -197,9 +354,10 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     for (int i = 0; i < h.n_phases; ++i) {
         const ge_phase_t& ph = t->dev.phase[i];
         uint8_t need = 0;
-        if (h.family != FAM_WEREWOLF) { t->dev.need[i] = 7; continue; }
+        if (h.family != FAM_WEREWOLF) { t->dev.need[i] = 15; continue; }
         if (ph.kind == KIND_TERMINAL) { t->dev.need[i] = 0; continue; }
         if (ph.kind == KIND_ACTION) {
+            need |= 8;                                        // bots draw from the session's Philox stream (needs its id)
             need |= pred_need(ph.actor_pred);
             if (ph.action_op == ACT_PICK_PLAYER) need |= pred_need(ph.action_arg);
             if (ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE) need |= 1 | 4;
@@ -209,6 +367,7 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             if (br.op == BR_COUNT_EQ0 || br.op == BR_COUNT_GE) need |= pred_need(br.a);
             if (br.op == BR_COUNT_GE) need |= pred_need((int)br.arg);
             need |= entry_need(t->dev.phase[br.next].entry_op);
+            if (t->dev.phase[br.next].entry_op == EN_ASSIGN_ROLES) need |= 8;
         }
         t->dev.need[i] = need;
     }
@@ -295,6 +454,10 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
     b->launches++;
     CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
     b->next_override = 1u;        // every session is in phase index 0
+    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n);
+    CU(cudaGetLastError());
+    b->compacted = false;
+    b->since_compact = 0;
     return GE_OK;
 }
 
@@ -337,10 +500,23 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (e == cudaSuccess) e = cudaMalloc(&b->d_stats, GE_STATS_LEN * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_stats_out, GE_STATS_LEN * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_presence, 3 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_origin, b->n_tiles * 32 * sizeof(uint32_t));
+    // padded so that the scan kernel's 1024 x (multiple of 4) ranges never leave the allocation
+    const size_t mask_words = ((b->n_tiles + 4095) / 4096 + 1) * 4096;
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_live_mask, mask_words * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(b->d_live_mask, 0, mask_words * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_prefix, mask_words * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_cstate, 8 * sizeof(unsigned long long));
+    b->scan_blocks = (int)((b->n_tiles + CS_TILES - 1) / CS_TILES);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_blk, ((size_t)b->scan_blocks + 2) * sizeof(uint32_t));
+    b->dead_shift = 2;                                   // compact when >= 1/4 of the active prefix is dead
+    b->compact_every = b->scan_blocks <= 1024 ? 8 : 0;   // one finishing block scans the block totals
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking);
     b->stream = b->own_stream;
     if (e != cudaSuccess) {
-        cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_presence); delete b;
+        cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_presence);
+        cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate);
+        delete b;
         return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_create: ") + cudaGetErrorString(e));
     }
     for (int k = GE_KERNEL_COOP; k <= GE_KERNEL_TPS; ++k) {
@@ -369,6 +545,7 @@ extern "C" void ge_batch_destroy(ge_batch* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     if (b->own_stream) { cudaStreamSynchronize(b->own_stream); cudaStreamDestroy(b->own_stream); }
     cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_stage); cudaFree(b->d_presence);
+    cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate);
     delete b;
 }
 
@@ -382,22 +559,72 @@ extern "C" int ge_batch_set_stream(ge_batch* b, void* cuda_stream) {
 
 extern "C" int ge_batch_set_kernel(ge_batch* b, int kernel) {
     if (!b || kernel < GE_KERNEL_AUTO || kernel > GE_KERNEL_TPS) return fail(GE_ERR_ARG, "bad kernel id");
-    b->kernel = kernel == GE_KERNEL_AUTO ? GE_KERNEL_TPS : kernel;
+    kernel = kernel == GE_KERNEL_AUTO ? GE_KERNEL_TPS : kernel;
+    if (kernel == GE_KERNEL_COOP && b->kernel != GE_KERNEL_COOP) {
+        // the lane-per-player kernels walk every slot in session order: undo any compaction first
+        CU(cudaSetDevice(b->device));
+        const int rc = restore_order(b);
+        if (rc) return rc;
+    }
+    b->kernel = kernel;
+    return GE_OK;
+}
+
+extern "C" int ge_batch_set_compaction(ge_batch* b, int every_n_steps, int min_dead_shift) {
+    if (!b || every_n_steps < 0 || min_dead_shift < 0 || min_dead_shift > 16) return fail(GE_ERR_ARG, "bad arguments to ge_batch_set_compaction");
+    if (every_n_steps > 0 && b->scan_blocks > 1024) return fail(GE_ERR_UNSUPPORTED, "compaction supports batches up to 2^25 sessions");
+    b->compact_every = every_n_steps;
+    b->dead_shift = min_dead_shift;
+    return GE_OK;
+}
+
+extern "C" int ge_batch_active(ge_batch* b, uint64_t* out) {
+    if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_batch_active");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(out, b->d_cstate, sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
     return GE_OK;
 }
 extern "C" int ge_batch_get_kernel(const ge_batch* b) { return b ? b->kernel : GE_ERR_ARG; }
+
+// scan -> rank -> swap -> commit on the live masks of the step that just ran (all asynchronous, no host sync)
+static int enqueue_compaction(ge_batch* b, cudaStream_t st) {
+    if (!b->compacted) {
+        k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
+        b->compacted = true;
+        b->launches++;
+    }
+    k_compact_scan<<<b->scan_blocks, 1024, 0, st>>>(b->d_live_mask, b->d_prefix, b->d_blk, b->d_cstate, (uint32_t)b->dead_shift);
+    uint64_t sg = (b->n_tiles * 16 + 127) / 128;
+    if (sg > (uint64_t)b->sm_count * 8) sg = (uint64_t)b->sm_count * 8;
+    k_compact_swap<<<(int)(sg < 1 ? 1 : sg), 128, 0, st>>>(
+        b->d_tiles, (uint32_t)b->tab->rec_dev, b->d_origin, b->d_live_mask, b->d_prefix, b->d_blk, b->d_cstate);
+    CU(cudaGetLastError());
+    b->launches += 2;
+    b->since_compact = 0;
+    return GE_OK;
+}
 
 static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaStream_t st) {
     const step_fn fn = b->fn[b->kernel];
     StepArgs a;
     a.tiles = b->d_tiles; a.n_sessions = b->n; a.n_tiles = b->n_tiles; a.first_sid = b->first_sid; a.seed = b->seed;
     a.stats = b->d_stats; a.presence = b->d_presence; a.n_steps = steps_per_launch;
+    a.n_active = b->d_cstate; a.live_mask = b->d_live_mask; a.live_count = b->d_cstate + 5;
     for (int i = 0; i < n_launches; ++i) {
+        const bool compact_after = b->compact_every > 0 && b->kernel == GE_KERNEL_TPS && b->since_compact + 1 >= b->compact_every;
+        a.count_live = compact_after ? 1u : 0u;
         a.launch_idx = b->launch_idx++;
         a.presence_override = b->next_override;
         b->next_override = 0;
+        a.origin = b->compacted ? b->d_origin : nullptr;
         fn<<<b->grid[b->kernel], 128, 0, st>>>(b->tab->dev, a);
         b->launches++;
+        b->since_compact++;
+        if (compact_after) {
+            const int rc = enqueue_compaction(b, st);
+            if (rc != GE_OK) return rc;
+        }
     }
     CU(cudaGetLastError());
     return GE_OK;
@@ -436,16 +663,41 @@ static int export_async(ge_batch* b, uint64_t first, uint64_t count, void* host_
     const size_t S = b->tab->rec_canon;
     int rc = ensure_stage(b, count * S);
     if (rc) return rc;
-    k_export<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage);
+    if (b->compacted)
+        k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, b->d_origin, b->n, first, count, b->d_stage);
+    else
+        k_export<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage);
     CU(cudaGetLastError());
     b->launches++;
     CU(cudaMemcpyAsync(host_buf, b->d_stage, count * S, cudaMemcpyDeviceToHost, b->stream));
     return GE_OK;
 }
 
+// Undo the slot permutation of compaction: records go back to slot == session index, every slot active.
+static int restore_order(ge_batch* b) {
+    if (b->compacted) {
+        const size_t S = b->tab->rec_canon;
+        int rc = ensure_stage(b, b->n * S);
+        if (rc) return rc;
+        k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, b->d_origin, b->n, 0, b->n, b->d_stage);
+        k_import<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, 0, b->n, b->d_stage);
+        CU(cudaGetLastError());
+        b->launches += 2;
+        b->compacted = false;
+    }
+    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n);
+    CU(cudaGetLastError());
+    b->since_compact = 0;
+    CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
+    b->next_override = 0xFFFFFFFFu;
+    return GE_OK;
+}
+
 static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void* host_buf) {
     const size_t S = b->tab->rec_canon;
-    int rc = ensure_stage(b, count * S);
+    int rc = restore_order(b);         // imported sessions may be live anywhere
+    if (rc) return rc;
+    rc = ensure_stage(b, count * S);
     if (rc) return rc;
     CU(cudaMemcpyAsync(b->d_stage, host_buf, count * S, cudaMemcpyHostToDevice, b->stream));
     k_import<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage);

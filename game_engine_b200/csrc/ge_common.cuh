@@ -50,6 +50,14 @@ struct StepArgs {
     uint32_t* presence;
     uint32_t launch_idx, presence_override;
     int n_steps;
+    // Active-prefix compaction (ge_capi.cu): only slots [0, *n_active) can hold live sessions; `origin`
+    // maps a slot to the session's original index (NULL = identity; session id = first_sid + origin);
+    // the step kernel publishes which lanes of each tile are still live after the step in live_mask.
+    const unsigned long long* n_active;
+    const uint32_t* origin;
+    uint32_t* live_mask;
+    unsigned long long* live_count;   // when count_live != 0 the launch adds its number of live sessions here
+    uint32_t count_live;
 };
 
 __device__ __forceinline__ void publish_presence(const StepArgs& A, uint32_t block_present) {
@@ -102,6 +110,28 @@ __device__ __forceinline__ uint4 ld128(const uint8_t* p) { return *reinterpret_c
 __device__ __forceinline__ uint2 ld64(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
 __device__ __forceinline__ void st128(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 __device__ __forceinline__ void st64(uint8_t* p, const uint2& v) { *reinterpret_cast<uint2*>(p) = v; }
+
+// Warp-uniform visit accumulator.  Live sessions of a batch move in lockstep, so nearly every tile a warp
+// processes enters the same phase: the (phase, count) pair is kept in registers and only spilled to the
+// block's shared counters when the phase changes (and once at the end).
+struct VisitAcc {
+    int phase = -1;
+    uint32_t count = 0;
+    __device__ __forceinline__ void add(uint32_t* s_visits, int np, int lane) {
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, np >= 0);
+        while (todo) {                                   // one iteration per distinct phase in the tile (usually 1)
+            const int v = __shfl_sync(0xFFFFFFFFu, np, __ffs(todo) - 1);
+            const uint32_t same = __ballot_sync(0xFFFFFFFFu, np == v);
+            if (v != phase) { flush(s_visits, lane); phase = v; }
+            count += __popc(same);
+            todo &= ~same;
+        }
+    }
+    __device__ __forceinline__ void flush(uint32_t* s_visits, int lane) {
+        if (lane == 0 && count) atomicAdd(&s_visits[phase], count);
+        count = 0;
+    }
+};
 
 // block-level visit counters: warp-aggregated shared atomics, flushed once per block
 __device__ __forceinline__ void count_visit(uint32_t* s_visits, int new_phase, int lane) {

@@ -24,35 +24,39 @@ struct WState {
     uint32_t tw[P8 / 4];                               // selected_target_id bytes
 };
 
-template <int P8>
-__device__ __forceinline__ uint32_t w_field(const WState<P8>& s, int f, uint32_t ALL) {
-    switch (f) {
-    case 0: return s.alive;      case 1: return s.can_vote;  case 2: return s.eligible;
-    case 3: return s.submitted;  case 4: return s.revealed;  case 5: return s.investigated;
-    case 6: return s.wolf;       case 7: return s.secret;
-    case 8: return ~(s.role_lo | s.role_hi) & ALL;
-    case 9: return s.role_lo & ~s.role_hi;
-    case 10: return ~s.role_lo & s.role_hi;
-    case 11: return s.role_lo & s.role_hi;
-    case 15: return ALL;
-    default: return 0u;
-    }
-}
+constexpr int TPS_THREADS = 128;
 
-template <int P8>
-__device__ __forceinline__ uint32_t w_pred(const DevTable& T, const WState<P8>& s, int pi, uint32_t ALL) {
-    const ge_pred_t pr = T.pred[pi];
-    uint32_t out = 0;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
-        uint32_t m = ALL;
-        while (pos) { const int f = __ffs(pos) - 1; pos &= pos - 1; m &= w_field(s, f, ALL); }
-        while (neg) { const int f = __ffs(neg) - 1; neg &= neg - 1; m &= ~w_field(s, f, ALL); }
-        out |= m;
+// Per-thread table of the 12 predicate field masks (SPEC.md section 2) in shared memory, laid out
+// [field][thread] (conflict-free).  Predicates index it dynamically; this replaced a switch over the field
+// id that cost a quarter of an action step's instructions.
+struct FieldTable {
+    uint32_t (*f)[TPS_THREADS];
+    int tid;
+    template <int P8>
+    __device__ __forceinline__ void fill(const WState<P8>& s, uint32_t ALL) const {
+        f[0][tid] = s.alive;      f[1][tid] = s.can_vote;  f[2][tid] = s.eligible;  f[3][tid] = s.submitted;
+        f[4][tid] = s.revealed;   f[5][tid] = s.investigated;  f[6][tid] = s.wolf;  f[7][tid] = s.secret;
+        f[8][tid] = ~(s.role_lo | s.role_hi) & ALL;
+        f[9][tid] = s.role_lo & ~s.role_hi;
+        f[10][tid] = ~s.role_lo & s.role_hi;
+        f[11][tid] = s.role_lo & s.role_hi;
+        f[15][tid] = ALL;
     }
-    return out;
-}
+    __device__ __forceinline__ uint32_t pred(const DevTable& T, int pi, uint32_t ALL) const {
+        const ge_pred_t pr = T.pred[pi];
+        uint32_t out = 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
+            if (neg & 0x8000u) continue;                       // "& ~ALL": unused clause
+            uint32_t m = ALL;
+            while (pos) { const int k = __ffs(pos) - 1; pos &= pos - 1; m &= f[k][tid]; }
+            while (neg) { const int k = __ffs(neg) - 1; neg &= neg - 1; m &= ~f[k][tid]; }
+            out |= m;
+        }
+        return out;
+    }
+};
 
 // bit-sliced vote counters
 template <int NPL>
@@ -95,7 +99,7 @@ __device__ __forceinline__ void set_byte(uint32_t (&w)[NW], int p, uint32_t v) {
 // One step of one session.  Returns the phase index entered (for the visit counters) or -1 when the
 // session is terminal.  `dirty` collects which column groups changed.
 template <int P8>
-__device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t sid_lo, uint32_t sid_hi,
+__device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
                                       uint32_t k0, uint32_t k1, uint32_t& dirty) {
     constexpr int NPL = P8 <= 8 ? 4 : P8 <= 16 ? 5 : 6;
     const int P = T.h.n_players;
@@ -109,6 +113,8 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t
 
     uint32_t winner = s.h1 & 0xFF, kill = (s.h1 >> 8) & 0xFF, protect = (s.h1 >> 16) & 0xFF, revote = s.h1 >> 24;
     const uint32_t prev = (s.h0 >> 8) & 0xFF;
+    const bool acting = ph.kind == KIND_ACTION;
+    if (acting || ph.n_branches > 1) F.fill(s, ALL);
 
     // ---- PhaseNode: ordered branch evaluation on the state before this step's effects
     int taken = ph.n_branches - 1;
@@ -118,8 +124,8 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t
             bool ok;
             switch (br.op) {
             case BR_ALWAYS: ok = true; break;
-            case BR_COUNT_EQ0: ok = w_pred(T, s, br.a, ALL) == 0; break;
-            case BR_COUNT_GE: ok = __popc(w_pred(T, s, br.a, ALL)) >= __popc(w_pred(T, s, (int)br.arg, ALL)); break;
+            case BR_COUNT_EQ0: ok = F.pred(T, br.a, ALL) == 0; break;
+            case BR_COUNT_GE: ok = __popc(F.pred(T, br.a, ALL)) >= __popc(F.pred(T, (int)br.arg, ALL)); break;
             case BR_PREV_IN: ok = (br.arg >> prev) & 1u; break;
             case BR_TIE_PENDING: ok = (revote & 0x80u) != 0; break;
             default: ok = false; break;
@@ -132,10 +138,10 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t
 
     // ---- BotBehaviorNode: actors are visited in rank order (the i-th actor of every session in the
     // same warp iteration, so lanes stay converged); the Philox block is recomputed only when it changes.
-    if (ph.kind == KIND_ACTION) {
-        const uint32_t actors = w_pred(T, s, ph.actor_pred, ALL);
+    if (acting) {
+        const uint32_t actors = F.pred(T, ph.actor_pred, ALL);
         const int aop = ph.action_op;
-        const uint32_t legal0 = aop == ACT_PICK_PLAYER ? w_pred(T, s, ph.action_arg, ALL) : 0u;
+        const uint32_t legal0 = aop == ACT_PICK_PLAYER ? F.pred(T, ph.action_arg, ALL) : 0u;
         const uint32_t excl = (ph.action_flags & 1) ? 0xFFFFFFFFu : 0u;
         const bool record = ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE;
         Tally<NPL> tally; tally.clear();
@@ -243,6 +249,55 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, uint32_t
     return Y;
 }
 
+// A step of a session whose phase needs nothing but column 0 (UI / timer phases with no effects; the host
+// proves this per phase in DevTable::need).  c = {h0, h1, is_alive, can_vote}.  Same SPEC as w_step.
+__device__ __forceinline__ int w_step_light(const DevTable& T, uint4& c) {
+    const int X = c.x & 0xFF;
+    const uint32_t step0 = c.x >> 16;
+    const ge_phase_t& ph = T.phase[X];
+    if (ph.kind == KIND_TERMINAL) return -1;
+    if (step0 == 0) { c.x = (c.x & 0xFFFFu) | (1u << 16); return X; }
+    const uint32_t prev = (c.x >> 8) & 0xFF;
+    int taken = ph.n_branches - 1;
+    if (ph.n_branches > 1) {
+        const uint32_t ALL = all_mask(T.h.n_players);
+        auto lp = [&](int pi) -> uint32_t {                    // predicates of need==0 phases only read fields 0, 1, 15
+            const ge_pred_t pr = T.pred[pi];
+            uint32_t out = 0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t pos = k ? pr.pos1 : pr.pos0, neg = k ? pr.neg1 : pr.neg0;
+                if (neg & 0x8000u) continue;
+                uint32_t m = ALL;
+                if (pos & 1u) m &= c.z;
+                if (pos & 2u) m &= c.w;
+                if (neg & 1u) m &= ~c.z;
+                if (neg & 2u) m &= ~c.w;
+                out |= m;
+            }
+            return out;
+        };
+        for (int b = 0; b < ph.n_branches; ++b) {
+            const ge_branch_t br = ph.br[b];
+            bool ok;
+            switch (br.op) {
+            case BR_ALWAYS: ok = true; break;
+            case BR_COUNT_EQ0: ok = lp(br.a) == 0; break;
+            case BR_COUNT_GE: ok = __popc(lp(br.a)) >= __popc(lp((int)br.arg)); break;
+            case BR_PREV_IN: ok = (br.arg >> prev) & 1u; break;
+            case BR_TIE_PENDING: ok = ((c.y >> 24) & 0x80u) != 0; break;
+            default: ok = false; break;
+            }
+            if (ok) { taken = b; break; }
+        }
+    }
+    const int Y = ph.br[taken].next;
+    const uint32_t tag = ph.br[taken].tag;
+    if (tag) c.y = (c.y & ~0xFFu) | tag;
+    c.x = (uint32_t)Y | ((uint32_t)X << 8) | ((step0 + 1u) << 16);
+    return Y;
+}
+
 // Column groups a launch must load, from the phases present in the batch (see StepArgs::presence).
 __device__ __forceinline__ uint32_t need_of(const DevTable& T, uint32_t present) {
     uint32_t need = 0;
@@ -251,75 +306,118 @@ __device__ __forceinline__ uint32_t need_of(const DevTable& T, uint32_t present)
 }
 
 template <int P8>
-__global__ void __launch_bounds__(128, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
+__global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
 k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
     constexpr int S = 48 + P8;
     constexpr int NT16 = P8 / 16;          // full 16-byte target columns
     constexpr bool THALF = (P8 % 16) != 0; // trailing 8-byte column
     __shared__ uint32_t s_visits[32];
-    __shared__ uint32_t s_present;
+    __shared__ uint32_t s_present, s_live;
+    __shared__ uint32_t s_fields[16][TPS_THREADS];
     if (threadIdx.x < 32) s_visits[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_present = 0;
+    if (threadIdx.x == 0) { s_present = 0; s_live = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
-    // which column groups can any session of this batch need?  (bit0 C1, bit1 C2, bit2 player bytes)
+    // which column groups can any session of this batch need?  (bit0 C1, bit1 C2, bit2 player bytes, bit3 session id)
     const uint32_t present_in = A.presence_override ? A.presence_override : A.presence[A.launch_idx % 3];
-    const uint32_t need = A.n_steps > 1 ? 7u : need_of(T, present_in);
-    uint32_t present_out = 0;
+    const uint32_t need = A.n_steps > 1 ? 15u : need_of(T, present_in);
+    const uint64_t n_act = *A.n_active;                 // slots beyond it hold only terminal sessions
+    const uint32_t n_tiles_act = (uint32_t)((n_act + 31) >> 5);
+    const bool use_origin = A.origin != nullptr && (need & 8);
+    const FieldTable F{s_fields, (int)threadIdx.x};
+    uint32_t present_out = 0, live_cnt = 0;
+    VisitAcc visits;
 
-    for (uint64_t tile = warp0; tile < A.n_tiles; tile += nwarps) {
-        uint8_t* base = A.tiles + tile * (uint64_t)(32 * S);
-        const uint64_t sess = tile * 32 + lane;
-        WState<P8> s;
-        // all loads are issued up front (no dependent second round trip)
-        const uint4 c0 = ld128(base + lane * 16);
-        uint4 c1 = make_uint4(0, 0, 0, 0), c2 = make_uint4(0, 0, 0, 0);
-        if (need & 1) c1 = ld128(base + 512 + lane * 16);
-        if (need & 2) c2 = ld128(base + 1024 + lane * 16);
+    if (need == 0) {
+        // ---- light path: every present phase touches column 0 only.  Four tiles in flight per warp.
+        for (uint32_t tile = warp0; tile < n_tiles_act; tile += 4 * nwarps) {
+            uint4 c[4];
 #pragma unroll
-        for (int c = 0; c < NT16; ++c) {
-            uint4 t = make_uint4(0, 0, 0, 0);
-            if (need & 4) t = ld128(base + (3 + c) * 512 + lane * 16);
-            s.tw[4 * c] = t.x; s.tw[4 * c + 1] = t.y; s.tw[4 * c + 2] = t.z; s.tw[4 * c + 3] = t.w;
-        }
-        if (THALF) {
-            uint2 t = make_uint2(0, 0);
-            if (need & 4) t = ld64(base + (3 + NT16) * 512 + lane * 8);
-            s.tw[4 * NT16] = t.x; s.tw[4 * NT16 + 1] = t.y;
-        }
-        s.h0 = c0.x; s.h1 = c0.y; s.alive = c0.z; s.can_vote = c0.w;
-        s.eligible = c1.x; s.submitted = c1.y; s.revealed = c1.z; s.investigated = c1.w;
-        s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
-        bool live = sess < A.n_sessions;
-        const uint64_t sid = A.first_sid + sess;
-        uint32_t dirty = 0;
-        for (int it = 0; it < A.n_steps; ++it) {
-            int np = -1;
-            if (live) {
-                np = w_step<P8>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
-                if (np < 0) live = false;
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t t = tile + j * nwarps;
+                c[j] = t < n_tiles_act ? ld128(A.tiles + (uint64_t)t * (32 * S) + lane * 16) : make_uint4(0, 0, 0, 0);
             }
-            count_visit(s_visits, np, lane);
-        }
-        if (sess < A.n_sessions) present_out |= 1u << (s.h0 & 31);
-        if (dirty & DIRTY_C0) st128(base + lane * 16, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
-        if (dirty & DIRTY_C1) st128(base + 512 + lane * 16, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
-        if (dirty & DIRTY_C2) st128(base + 1024 + lane * 16, make_uint4(s.wolf, s.secret, s.role_lo, s.role_hi));
-        if (dirty & DIRTY_PL) {
 #pragma unroll
-            for (int c = 0; c < NT16; ++c)
-                st128(base + (3 + c) * 512 + lane * 16, make_uint4(s.tw[4 * c], s.tw[4 * c + 1], s.tw[4 * c + 2], s.tw[4 * c + 3]));
-            if (THALF) st64(base + (3 + NT16) * 512 + lane * 8, make_uint2(s.tw[4 * NT16], s.tw[4 * NT16 + 1]));
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t t = tile + j * nwarps;
+                if (t < n_tiles_act) {                        // warp-uniform
+                    const bool in_range = (uint64_t)t * 32 + lane < n_act;
+                    const int np = in_range ? w_step_light(T, c[j]) : -1;
+                    visits.add(s_visits, np, lane);
+                    if (np >= 0) st128(A.tiles + (uint64_t)t * (32 * S) + lane * 16, c[j]);
+                    if (in_range) present_out |= 1u << (c[j].x & 31);
+                    const uint32_t lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[c[j].x & 31].kind != KIND_TERMINAL);
+                    if (lane == 0) A.live_mask[t] = lm;
+                    live_cnt += __popc(lm);
+                }
+            }
+        }
+    } else {
+        for (uint32_t tile = warp0; tile < n_tiles_act; tile += nwarps) {
+            uint8_t* base = A.tiles + (uint64_t)tile * (32 * S);
+            const uint64_t sess = (uint64_t)tile * 32 + lane;
+            const bool in_range = sess < n_act;
+            uint64_t org = sess;
+            if (use_origin && in_range) org = A.origin[sess];
+            WState<P8> s;
+            // all loads are issued up front (no dependent second round trip)
+            const uint4 c0 = ld128(base + lane * 16);
+            uint4 c1 = make_uint4(0, 0, 0, 0), c2 = make_uint4(0, 0, 0, 0);
+            if (need & 1) c1 = ld128(base + 512 + lane * 16);
+            if (need & 2) c2 = ld128(base + 1024 + lane * 16);
+#pragma unroll
+            for (int c = 0; c < NT16; ++c) {
+                uint4 t = make_uint4(0, 0, 0, 0);
+                if (need & 4) t = ld128(base + (3 + c) * 512 + lane * 16);
+                s.tw[4 * c] = t.x; s.tw[4 * c + 1] = t.y; s.tw[4 * c + 2] = t.z; s.tw[4 * c + 3] = t.w;
+            }
+            if (THALF) {
+                uint2 t = make_uint2(0, 0);
+                if (need & 4) t = ld64(base + (3 + NT16) * 512 + lane * 8);
+                s.tw[4 * NT16] = t.x; s.tw[4 * NT16 + 1] = t.y;
+            }
+            s.h0 = c0.x; s.h1 = c0.y; s.alive = c0.z; s.can_vote = c0.w;
+            s.eligible = c1.x; s.submitted = c1.y; s.revealed = c1.z; s.investigated = c1.w;
+            s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
+            bool live = in_range;
+            const uint64_t sid = A.first_sid + org;
+            uint32_t dirty = 0;
+            for (int it = 0; it < A.n_steps; ++it) {
+                int np = -1;
+                if (live) {
+                    np = w_step<P8>(T, s, F, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                    if (np < 0) live = false;
+                }
+                visits.add(s_visits, np, lane);
+            }
+            if (in_range) present_out |= 1u << (s.h0 & 31);
+            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[s.h0 & 31].kind != KIND_TERMINAL);
+            if (lane == 0) A.live_mask[tile] = lm;
+            live_cnt += __popc(lm);
+            if (dirty & DIRTY_C0) st128(base + lane * 16, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
+            if (dirty & DIRTY_C1) st128(base + 512 + lane * 16, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
+            if (dirty & DIRTY_C2) st128(base + 1024 + lane * 16, make_uint4(s.wolf, s.secret, s.role_lo, s.role_hi));
+            if (dirty & DIRTY_PL) {
+#pragma unroll
+                for (int c = 0; c < NT16; ++c)
+                    st128(base + (3 + c) * 512 + lane * 16, make_uint4(s.tw[4 * c], s.tw[4 * c + 1], s.tw[4 * c + 2], s.tw[4 * c + 3]));
+                if (THALF) st64(base + (3 + NT16) * 512 + lane * 8, make_uint2(s.tw[4 * NT16], s.tw[4 * NT16 + 1]));
+            }
         }
     }
+    visits.flush(s_visits, lane);
     present_out = __reduce_or_sync(0xFFFFFFFFu, present_out);
-    if (lane == 0 && present_out) atomicOr(&s_present, present_out);
+    if (lane == 0) {
+        if (present_out) atomicOr(&s_present, present_out);
+        if (live_cnt) atomicAdd(&s_live, live_cnt);
+    }
     __syncthreads();
     flush_visits(s_visits, A.stats);
     publish_presence(A, s_present);
+    if (A.count_live && threadIdx.x == 0 && s_live) atomicAdd(A.live_count, (unsigned long long)s_live);
 }
 
 // =================================================================================== TTL family
@@ -489,9 +587,14 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 
-    for (uint64_t tile = warp0; tile < n_tiles; tile += nwarps) {
+    const uint64_t n_act = *A.n_active;
+    const uint64_t n_tiles_act = (n_act + 31) >> 5;
+    (void)n_tiles; (void)n_sessions;
+    for (uint64_t tile = warp0; tile < n_tiles_act; tile += nwarps) {
         uint8_t* base = tiles + tile * (uint64_t)(32 * S);
         const uint64_t sess = tile * 32 + lane;
+        uint64_t org = sess;
+        if (A.origin != nullptr && sess < n_act) org = A.origin[sess];
         uint32_t w[NW];
 #pragma unroll
         for (int c = 0; c < N16; ++c) {
@@ -503,8 +606,8 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
         s.h0 = w[0]; s.h1 = w[1];
 #pragma unroll
         for (int p = 0; p < PB; ++p) s.pw[p] = w[2 + p];
-        bool live = sess < n_sessions && T.phase[s.h0 & 0xFF].kind != KIND_TERMINAL;
-        const uint64_t sid = first_sid + sess;
+        bool live = sess < n_act && T.phase[s.h0 & 0xFF].kind != KIND_TERMINAL;
+        const uint64_t sid = first_sid + org;
         uint32_t dirty = 0;
         for (int it = 0; it < n_steps; ++it) {
             int np = -1;
@@ -513,6 +616,10 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
                 if (np < 0) live = false;
             }
             count_visit(s_visits, np, lane);
+        }
+        {
+            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, sess < n_act && T.phase[s.h0 & 31].kind != KIND_TERMINAL);
+            if (lane == 0) { A.live_mask[tile] = lm; if (A.count_live && lm) atomicAdd(A.live_count, (unsigned long long)__popc(lm)); }
         }
         if (dirty) {
             w[0] = s.h0; w[1] = s.h1;

@@ -88,6 +88,13 @@ void ge_batch_destroy(ge_batch *b);
  * returns to the batch's own stream.  The stream is borrowed, not owned. */
 int ge_batch_set_stream(ge_batch *b, void *cuda_stream);
 int ge_batch_set_kernel(ge_batch *b, int kernel);
+/* Active-prefix compaction (thread-per-session kernels): every `every_n_steps` launches a device-side check
+ * runs and, when at least 1/2^min_dead_shift of the active prefix holds finished games, the live sessions
+ * are swapped in front of them (on the device, no host sync) so later launches walk only the live prefix.
+ * Session ids, export order and statistics are unaffected.  every_n_steps = 0 turns it off; default (8, 2).
+ * ge_batch_active returns the current prefix length (synchronises). */
+int ge_batch_set_compaction(ge_batch *b, int every_n_steps, int min_dead_shift);
+int ge_batch_active(ge_batch *b, uint64_t *out);
 int ge_batch_get_kernel(const ge_batch *b);
 
 /* Apply n_steps session-phase-steps to every non-terminal session: n_steps launches of the step

@@ -400,6 +400,7 @@ int ge_cpu_step(const uint8_t *blob, size_t nb, uint8_t *records, uint64_t n_ses
 #pragma omp for schedule(static)
         for (int64_t i = 0; i < (int64_t)n_sessions; ++i) {
             sess_t s;
+            if (tab_phase(&t, records[(size_t)i * S])[1] == KIND_TERMINAL) continue;   /* frozen (SPEC D16) */
             unpack(&t, records + (size_t)i * S, &s);
             for (int k = 0; k < n_steps; ++k) my_counted += (uint64_t)step_session(&t, &s, seed, first_sid + (uint64_t)i, my_visits);
             pack(&t, &s, records + (size_t)i * S);
@@ -411,6 +412,7 @@ int ge_cpu_step(const uint8_t *blob, size_t nb, uint8_t *records, uint64_t n_ses
     (void)n_threads;
     for (uint64_t i = 0; i < n_sessions; ++i) {
         sess_t s;
+        if (tab_phase(&t, records[i * S])[1] == KIND_TERMINAL) continue;
         unpack(&t, records + i * S, &s);
         for (int k = 0; k < n_steps; ++k) counted += (uint64_t)step_session(&t, &s, seed, first_sid + i, visits);
         pack(&t, &s, records + i * S);

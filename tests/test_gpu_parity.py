@@ -133,3 +133,68 @@ def test_bad_import_is_rejected(games):
     rec[3, 0] = 200
     with pytest.raises(GameEngineError):
         b.import_state(rec)
+
+
+@pytest.mark.parametrize("game,P", [(WEREWOLF, 8), (WEREWOLF, 32), (TTL, 4)])
+def test_compaction_is_invisible(games, oracle_for, game, P):
+    """Active-prefix compaction permutes slots on the device; exports, statistics and ids must not notice."""
+    cg = games(game, P)
+    o = oracle_for(cg)
+    n, first, seed = 5000, 77, 31337
+    _, on = _batch(cg, n, first, seed, "tps")
+    _, every = _batch(cg, n, first, seed, "tps")
+    _, off = _batch(cg, n, first, seed, "tps")
+    on.set_compaction(4, 2)          # check every 4 steps, compact when >= 1/4 of the prefix is dead
+    every.set_compaction(1, 6)       # check every step, compact when >= 1/64 is dead
+    off.set_compaction(0)
+    rec = o.init(n)
+    ost = o.new_stats()
+    term = len(cg.phase_ids) - 1
+    prev_active = n
+    steps = 2 + 8 * P + 4 if game == TTL else 9 * P - 16 + 4
+    for k in range(steps):
+        for b in (on, every, off):
+            b.step(1)
+        o.step(rec, first, seed, 1, ost)
+        got = every.export_state()
+        assert np.array_equal(got, rec), "step %d (compaction every step)" % k
+        if k % 5 == 0 or k > steps - 6:
+            assert np.array_equal(on.export_state(), rec), "step %d (compaction every 4)" % k
+            assert np.array_equal(off.export_state(), rec), "step %d (no compaction)" % k
+        act = every.active()
+        live = int((rec[:, 0] != term).sum())
+        assert live <= act <= prev_active, (k, live, act, prev_active)
+        prev_active = act
+        assert off.active() == n
+    assert every.active() == 0          # every game is over: nothing left to walk
+    o.stats_final(rec, ost)
+    for b in (on, every, off):
+        np.testing.assert_array_equal(b.stats(), ost)
+    # partial export windows still address sessions by their original index
+    np.testing.assert_array_equal(every.export_state(1234, 321), rec[1234:1555])
+
+
+def test_import_after_compaction_restores_order(games, oracle_for):
+    cg = games(WEREWOLF, 8)
+    o = oracle_for(cg)
+    n, seed = 3000, 8
+    _, b = _batch(cg, n, 0, seed, "tps")
+    b.set_compaction(2, 4)
+    b.step(30)
+    assert b.active() < n
+    mid = b.export_state()
+    rec = o.init(n)
+    o.step(rec, 0, seed, 30)
+    np.testing.assert_array_equal(mid, rec)
+    b.import_state(mid[100:200], first=100)          # forces the slot order back to identity
+    assert b.active() == n
+    b.step(40)
+    o.step(rec, 0, seed, 40)
+    np.testing.assert_array_equal(b.export_state(), rec)
+    # switching to the lane-per-player kernel on a compacted batch must also work
+    _, c = _batch(cg, n, 0, seed, "tps")
+    c.set_compaction(1, 6)
+    c.step(25)
+    c.set_kernel("coop")
+    c.step(45)
+    np.testing.assert_array_equal(c.export_state(), rec)
