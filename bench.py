@@ -33,8 +33,9 @@ FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback when MEASURED_PE
 # longest possible game in steps (SPEC.md): werewolf 11 + 9*(P-3) (one death per day down to 2 players), TTL 2 + 8*P
 
 
-def game_cap(family: int, players: int) -> int:
-    return 9 * players - 16 if family == 1 else 2 + 8 * players
+def game_cap(family: int, players: int, max_revotes: int = 0) -> int:
+    # longest possible game: werewolf 11 + 9*(P-3) steps (+2 per re-vote, per day), TTL 2 + 8*P
+    return 9 * players - 16 + 2 * max_revotes * (players - 2) if family == 1 else 2 + 8 * players
 
 
 def parse_args():
@@ -177,7 +178,7 @@ def run_reference(a):
     from game_engine_b200 import compile_game
     from oracle.oracle import Oracle
     cg = compile_game(a.game, a.players)
-    cap = a.cap or game_cap(cg.family, a.players)
+    cap = a.cap or game_cap(cg.family, a.players, cg.table.max_revotes)
     native = build_oracle_native()
     o = Oracle(cg.blob, native=native)
     threads = o.max_threads()
@@ -262,7 +263,7 @@ def run_ours(a):
 
     cg = compile_game(a.game, a.players)
     S = cg.record_size
-    cap = a.cap or game_cap(cg.family, a.players)
+    cap = a.cap or game_cap(cg.family, a.players, cg.table.max_revotes)
     N, R = a.sessions, a.ring
     tab = Table(cg)
     stream = torch.cuda.Stream(device=dev)

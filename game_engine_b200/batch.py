@@ -64,7 +64,7 @@ class SessionBatch:
     @property
     def kernel(self) -> str:
         k = capi.lib().ge_batch_get_kernel(self._h)
-        return {capi.KERNEL_COOP: "coop", capi.KERNEL_TPS: "tps"}[k]
+        return {capi.KERNEL_COOP: "coop", capi.KERNEL_TPS: "tps", capi.KERNEL_TPS_GENERIC: "tps_generic"}[k]
 
     def reset(self, first_session_id: Optional[int] = None, seed: Optional[int] = None) -> None:
         if first_session_id is not None:

@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libgame_engine_b200.so")
 
 STATS_LEN = 560
 GE_OK, GE_ERR_ARG, GE_ERR_CUDA, GE_ERR_UNSUPPORTED, GE_ERR_NOMEM = 0, -1, -2, -3, -4
-KERNEL_AUTO, KERNEL_COOP, KERNEL_TPS = 0, 1, 2
-KERNEL_NAMES = {"auto": KERNEL_AUTO, "coop": KERNEL_COOP, "tps": KERNEL_TPS}
+KERNEL_AUTO, KERNEL_COOP, KERNEL_TPS, KERNEL_TPS_GENERIC = 0, 1, 2, 3
+KERNEL_NAMES = {"auto": KERNEL_AUTO, "coop": KERNEL_COOP, "tps": KERNEL_TPS, "tps_generic": KERNEL_TPS_GENERIC}
 
 # every symbol include/game_engine_b200.h declares: (name, restype, argtypes)
 _vp, _u64, _sz, _int = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int

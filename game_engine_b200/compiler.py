@@ -263,9 +263,11 @@ def n_wolves_for(rule: Any, n_players: int) -> int:
 
 
 def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: Optional[dict] = None,
-                 max_revotes: int = 0) -> CompiledGame:
+                 max_revotes: Optional[int] = None) -> CompiledGame:
     dsl = dsl if dsl is not None else load_dsl(game)
     rules = rules if rules is not None else load_rules(game)
+    if max_revotes is None:
+        max_revotes = int(rules.get("max_revotes", 0))
     decl = dsl["declaration"]
     fam = {"werewolf": T.FAMILY_WEREWOLF, "ttl": T.FAMILY_TTL}[rules["family"]]
     min_players = int(decl.get("min_players") or 2)

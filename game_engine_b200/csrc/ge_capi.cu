@@ -13,6 +13,7 @@
 #include "ge_common.cuh"
 #include "ge_step_tps.cuh"
 #include "ge_step_coop.cuh"
+#include "ge_spec_gen.cuh"
 
 using namespace ge;
 
@@ -35,6 +36,7 @@ struct ge_table {
     int family, P, bucket;       // bucket: werewolf P8 (8/16/24/32), TTL PB (4/8/16/32)
     size_t rec_canon, rec_dev;   // canonical / device record bytes
     uint32_t init_words[40];     // initial device record
+    void (*spec_fn)(const DevTable, const StepArgs);   // build-time specialised step kernel for this exact table, or NULL
 };
 
 typedef void (*step_fn)(const DevTable, const StepArgs);
@@ -64,8 +66,8 @@ struct ge_batch {
     uint32_t launch_idx;          // index of the next step launch
     uint32_t next_override;       // presence override for the next launch (0 = read the device word)
     int kernel;
-    step_fn fn[3];               // by kernel id (COOP, TPS)
-    int grid[3];
+    step_fn fn[4];               // by kernel id (COOP, TPS, TPS_GENERIC)
+    int grid[4];
     uint64_t launches;
 };
 
@@ -398,12 +400,21 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     return GE_OK;
 }
 
+// build-time specialised kernels (ge_spec_gen.cuh), matched by byte-identical table blobs
+struct SpecEntry { const unsigned char* blob; size_t len; step_fn fn; };
+#define GE_SPEC_ENTRY(S, FAM, BUCKET) {spec::S##_blob, sizeof(spec::S##_blob), (step_fn)k_step_w_tps<BUCKET, spec::S>},
+static const SpecEntry g_specs[] = { GE_SPEC_LIST(GE_SPEC_ENTRY) {nullptr, 0, nullptr} };
+
 extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
     if (!out) return fail(GE_ERR_ARG, "out is NULL");
     ge_table* t = new (std::nothrow) ge_table;
     if (!t) return fail(GE_ERR_NOMEM, "out of host memory");
     const int rc = validate_and_build(blob, n, t);
     if (rc != GE_OK) { delete t; return rc; }
+    t->spec_fn = nullptr;
+    const size_t used = sizeof(ge_table_header_t) + (size_t)t->dev.h.n_phases * sizeof(ge_phase_t) + (size_t)t->dev.h.n_preds * sizeof(ge_pred_t);
+    for (const SpecEntry* e = g_specs; e->blob; ++e)
+        if (e->len == used && memcmp(e->blob, blob, used) == 0) t->spec_fn = e->fn;
     *out = t;
     return GE_OK;
 }
@@ -519,13 +530,14 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
         delete b;
         return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_create: ") + cudaGetErrorString(e));
     }
-    for (int k = GE_KERNEL_COOP; k <= GE_KERNEL_TPS; ++k) {
-        b->fn[k] = pick_fn(t, k);
+    for (int k = GE_KERNEL_COOP; k <= GE_KERNEL_TPS_GENERIC; ++k) {
+        b->fn[k] = k == GE_KERNEL_TPS_GENERIC ? pick_fn(t, GE_KERNEL_TPS) : (k == GE_KERNEL_TPS && t->spec_fn) ? t->spec_fn : pick_fn(t, k);
         if (!b->fn[k]) { ge_batch_destroy(b); return fail(GE_ERR_UNSUPPORTED, "no kernel for this table"); }
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)b->fn[k], 128, 0);
         if (e != cudaSuccess || per_sm < 1) per_sm = 4;
         const uint64_t warps = k == GE_KERNEL_COOP ? b->n_tiles * (uint64_t)lanes_per_session(t) : b->n_tiles;
+        (void)0;
         uint64_t g = (warps + 3) / 4;
         const uint64_t cap = (uint64_t)b->sm_count * per_sm;      // persistent grid: whole multiples of the SM count
         if (g > cap) g = cap;
@@ -558,7 +570,7 @@ extern "C" int ge_batch_set_stream(ge_batch* b, void* cuda_stream) {
 }
 
 extern "C" int ge_batch_set_kernel(ge_batch* b, int kernel) {
-    if (!b || kernel < GE_KERNEL_AUTO || kernel > GE_KERNEL_TPS) return fail(GE_ERR_ARG, "bad kernel id");
+    if (!b || kernel < GE_KERNEL_AUTO || kernel > GE_KERNEL_TPS_GENERIC) return fail(GE_ERR_ARG, "bad kernel id");
     kernel = kernel == GE_KERNEL_AUTO ? GE_KERNEL_TPS : kernel;
     if (kernel == GE_KERNEL_COOP && b->kernel != GE_KERNEL_COOP) {
         // the lane-per-player kernels walk every slot in session order: undo any compaction first
@@ -612,7 +624,7 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
     a.stats = b->d_stats; a.presence = b->d_presence; a.n_steps = steps_per_launch;
     a.n_active = b->d_cstate; a.live_mask = b->d_live_mask; a.live_count = b->d_cstate + 5;
     for (int i = 0; i < n_launches; ++i) {
-        const bool compact_after = b->compact_every > 0 && b->kernel == GE_KERNEL_TPS && b->since_compact + 1 >= b->compact_every;
+        const bool compact_after = b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
         a.count_live = compact_after ? 1u : 0u;
         a.launch_idx = b->launch_idx++;
         a.presence_override = b->next_override;

@@ -8,6 +8,7 @@
 // memory).  The rules are SPEC.md; the restated reference code is BotBehaviorNode / PhaseNode /
 // RefereeNode (reference agent/game_agent_v2.py:468-617, 987-1241, 619-803).
 #pragma once
+#include <type_traits>
 #include "ge_common.cuh"
 
 namespace ge {
@@ -96,56 +97,195 @@ __device__ __forceinline__ void set_byte(uint32_t (&w)[NW], int p, uint32_t v) {
         if (i == wi) w[i] = (w[i] & ~(0xFFu << sh)) | (v << sh);
 }
 
-// One step of one session.  Returns the phase index entered (for the visit counters) or -1 when the
-// session is terminal.  `dirty` collects which column groups changed.
+// ---- table views -----------------------------------------------------------------------------------
+// The step body below is written once against a "view" of the phase it runs in.  RtView reads the
+// table passed at run time (any game).  CtView<Spec, X> reads a table generated at BUILD time from the
+// shipped game files (ge_spec_gen.cuh): every accessor is a constant expression, so for each phase the
+// compiler folds the op dispatch, the predicates and the branch list and drops the dead code — the
+// table is still the only statement of the game, it is just consumed by the compiler instead of by an
+// interpreter loop.
 template <int P8>
-__device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
-                                      uint32_t k0, uint32_t k1, uint32_t& dirty) {
-    constexpr int NPL = P8 <= 8 ? 4 : P8 <= 16 ? 5 : 6;
-    const int P = T.h.n_players;
-    const uint32_t ALL = all_mask(P);
-    const int X = s.h0 & 0xFF;
-    const uint32_t step0 = s.h0 >> 16;
-    const ge_phase_t& ph = T.phase[X];
-    if (ph.kind == KIND_TERMINAL) return -1;
-    dirty |= DIRTY_C0;
-    if (step0 == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
+__device__ __forceinline__ uint32_t w_field_of(const WState<P8>& s, int f, uint32_t ALL) {
+    switch (f) {
+    case 0: return s.alive;      case 1: return s.can_vote;  case 2: return s.eligible;
+    case 3: return s.submitted;  case 4: return s.revealed;  case 5: return s.investigated;
+    case 6: return s.wolf;       case 7: return s.secret;
+    case 8: return ~(s.role_lo | s.role_hi) & ALL;
+    case 9: return s.role_lo & ~s.role_hi;
+    case 10: return ~s.role_lo & s.role_hi;
+    case 11: return s.role_lo & s.role_hi;
+    case 15: return ALL;
+    default: return 0u;
+    }
+}
 
+struct RtView {
+    const DevTable& T;
+    const ge_phase_t& ph;
+    static constexpr bool is_const = false;
+    __device__ __forceinline__ RtView(const DevTable& t, int X) : T(t), ph(t.phase[X]) {}
+    __device__ __forceinline__ int kind() const { return ph.kind; }
+    __device__ __forceinline__ int action_op() const { return ph.action_op; }
+    __device__ __forceinline__ int action_arg() const { return ph.action_arg; }
+    __device__ __forceinline__ int action_flags() const { return ph.action_flags; }
+    __device__ __forceinline__ int exit_op() const { return ph.exit_op; }
+    __device__ __forceinline__ int actor_pred() const { return ph.actor_pred; }
+    __device__ __forceinline__ int n_branches() const { return ph.n_branches; }
+    __device__ __forceinline__ ge_branch_t branch(int b) const { return ph.br[b]; }
+    __device__ __forceinline__ int entry_op_after(int taken) const { return T.phase[ph.br[taken].next].entry_op; }
+    __device__ __forceinline__ int n_players() const { return T.h.n_players; }
+    __device__ __forceinline__ int n_wolves() const { return T.h.n_wolves; }
+    __device__ __forceinline__ int max_revotes() const { return T.h.max_revotes; }
+    __device__ __forceinline__ bool wants_fields() const { return ph.kind == KIND_ACTION || ph.n_branches > 1; }
+    template <int P8>
+    __device__ __forceinline__ uint32_t pred(const FieldTable& F, const WState<P8>&, int pi, uint32_t ALL) const { return F.pred(T, pi, ALL); }
+};
+
+template <class Spec, int X>
+struct CtView {
+    static constexpr bool is_const = true;
+    __device__ __forceinline__ static constexpr int kind() { return Spec::phase(X).kind; }
+    __device__ __forceinline__ static constexpr int action_op() { return Spec::phase(X).action_op; }
+    __device__ __forceinline__ static constexpr int action_arg() { return Spec::phase(X).action_arg; }
+    __device__ __forceinline__ static constexpr int action_flags() { return Spec::phase(X).action_flags; }
+    __device__ __forceinline__ static constexpr int exit_op() { return Spec::phase(X).exit_op; }
+    __device__ __forceinline__ static constexpr int actor_pred() { return Spec::phase(X).actor_pred; }
+    __device__ __forceinline__ static constexpr int n_branches() { return Spec::phase(X).n_branches; }
+    __device__ __forceinline__ static constexpr ge_branch_t branch(int b) { return Spec::phase(X).br[b]; }
+    __device__ __forceinline__ static int entry_op_after(int taken) {
+        int en = EN_NONE;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b < Spec::phase(X).n_branches && b == taken) en = Spec::phase(Spec::phase(X).br[b].next).entry_op;
+        return en;
+    }
+    __device__ __forceinline__ static constexpr int n_players() { return Spec::n_players; }
+    __device__ __forceinline__ static constexpr int n_wolves() { return Spec::n_wolves; }
+    __device__ __forceinline__ static constexpr int max_revotes() { return Spec::max_revotes; }
+    __device__ __forceinline__ static constexpr bool wants_fields() { return false; }       // predicates fold to register ops
+    template <int P8>
+    __device__ __forceinline__ static uint32_t pred(const FieldTable&, const WState<P8>& s, int pi, uint32_t ALL) {
+        const ge_pred_t pr = Spec::pred(pi);          // pi is a constant after inlining: the loops below fold
+        uint32_t out = 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
+            if (neg & 0x8000u) continue;
+            uint32_t m = ALL;
+#pragma unroll
+            for (int f = 0; f < 16; ++f) {
+                if ((pos >> f) & 1u) m &= w_field_of(s, f, ALL);
+                if ((neg >> f) & 1u) m &= ~w_field_of(s, f, ALL);
+            }
+            out |= m;
+        }
+        return out;
+    }
+};
+
+// One step of one session in phase X (already known not to be terminal and step0 != 0).  Returns the
+// phase index entered; `dirty` collects which column groups changed.
+template <int P8, class V>
+__device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
+                                           uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    constexpr int NPL = P8 <= 8 ? 4 : P8 <= 16 ? 5 : 6;
+    const int P = v.n_players();
+    const uint32_t ALL = all_mask(P);
+    const uint32_t step0 = s.h0 >> 16;
     uint32_t winner = s.h1 & 0xFF, kill = (s.h1 >> 8) & 0xFF, protect = (s.h1 >> 16) & 0xFF, revote = s.h1 >> 24;
     const uint32_t prev = (s.h0 >> 8) & 0xFF;
-    const bool acting = ph.kind == KIND_ACTION;
-    if (acting || ph.n_branches > 1) F.fill(s, ALL);
+    const bool acting = v.kind() == KIND_ACTION;
+    if (v.wants_fields()) F.fill(s, ALL);
 
     // ---- PhaseNode: ordered branch evaluation on the state before this step's effects
-    int taken = ph.n_branches - 1;
-    if (ph.n_branches > 1) {
-        for (int b = 0; b < ph.n_branches; ++b) {
-            const ge_branch_t br = ph.br[b];
-            bool ok;
-            switch (br.op) {
-            case BR_ALWAYS: ok = true; break;
-            case BR_COUNT_EQ0: ok = F.pred(T, br.a, ALL) == 0; break;
-            case BR_COUNT_GE: ok = __popc(F.pred(T, br.a, ALL)) >= __popc(F.pred(T, (int)br.arg, ALL)); break;
-            case BR_PREV_IN: ok = (br.arg >> prev) & 1u; break;
-            case BR_TIE_PENDING: ok = (revote & 0x80u) != 0; break;
-            default: ok = false; break;
+    const int nb = v.n_branches();
+    int taken = nb - 1;
+    if (nb > 1) {
+        bool done = false;
+#pragma unroll(V::is_const ? 4 : 1)
+        for (int b = 0; b < 4; ++b) {
+            if (b < nb && !done) {
+                const ge_branch_t br = v.branch(b);
+                bool ok;
+                switch (br.op) {
+                case BR_ALWAYS: ok = true; break;
+                case BR_COUNT_EQ0: ok = v.template pred<P8>(F, s, br.a, ALL) == 0; break;
+                case BR_COUNT_GE: ok = __popc(v.template pred<P8>(F, s, br.a, ALL)) >= __popc(v.template pred<P8>(F, s, (int)br.arg, ALL)); break;
+                case BR_PREV_IN: ok = (br.arg >> prev) & 1u; break;
+                case BR_TIE_PENDING: ok = (revote & 0x80u) != 0; break;
+                default: ok = false; break;
+                }
+                if (ok) { taken = b; done = true; }
             }
-            if (ok) { taken = b; break; }
         }
     }
-    const int Y = ph.br[taken].next;
-    const uint32_t tag = ph.br[taken].tag;
+    int Y = 0; uint32_t tag = 0;
+    if constexpr (V::is_const) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b < nb && b == taken) { Y = v.branch(b).next; tag = v.branch(b).tag; }
+    } else {
+        Y = v.branch(taken).next; tag = v.branch(taken).tag;
+    }
 
     // ---- BotBehaviorNode: actors are visited in rank order (the i-th actor of every session in the
     // same warp iteration, so lanes stay converged); the Philox block is recomputed only when it changes.
     if (acting) {
-        const uint32_t actors = F.pred(T, ph.actor_pred, ALL);
-        const int aop = ph.action_op;
-        const uint32_t legal0 = aop == ACT_PICK_PLAYER ? F.pred(T, ph.action_arg, ALL) : 0u;
-        const uint32_t excl = (ph.action_flags & 1) ? 0xFFFFFFFFu : 0u;
-        const bool record = ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE;
+        const uint32_t actors = v.template pred<P8>(F, s, v.actor_pred(), ALL);
+        const int aop = v.action_op();
+        const uint32_t legal0 = aop == ACT_PICK_PLAYER ? v.template pred<P8>(F, s, v.action_arg(), ALL) : 0u;
+        const uint32_t excl = (v.action_flags() & 1) ? 0xFFFFFFFFu : 0u;
+        const int exo = v.exit_op();
+        const bool record = exo >= EX_VOTE_KILL && exo <= EX_DAY_VOTE;
+        const bool tallying = exo == EX_VOTE_KILL || exo == EX_DAY_VOTE;
         Tally<NPL> tally; tally.clear();
         uint32_t chosen = 0, first_choice = 0;
+        uint32_t nib = 0;                       // P8 <= 8: nibble-packed vote counters (one candidate per nibble)
+        bool nib_used = false;
+        if (aop == ACT_PICK_PLAYER && (uint32_t)__popc(actors) * 3u > (uint32_t)P8) {
+            // ---- many actors (day vote): one statically unrolled pass over the players.  Philox words, target
+            // bytes and ranks are static; the pick is a lookup in a nibble LUT of the legal players' positions.
+            const uint32_t n0 = __popc(legal0);
+            uint64_t lut = 0;
+            if (P8 <= 16) {
+                int j = 0;
+#pragma unroll
+                for (int q = 0; q < P8; ++q)
+                    if ((legal0 >> q) & 1u) { lut |= (uint64_t)q << (4 * j); ++j; }
+            }
+            uint4 R[P8 / 4];
+#pragma unroll
+            for (int b = 0; b < P8 / 4; ++b)
+                R[b] = ((actors >> (4 * b)) & 0xFu) ? philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, k0, k1) : make_uint4(0, 0, 0, 0);
+            uint32_t rank = 0;
+            bool have_first = false;
+            nib_used = P8 <= 8;
+#pragma unroll
+            for (int p = 0; p < P8; ++p) {
+                const uint32_t self_in = (legal0 >> p) & 1u;
+                if ((actors >> p) & 1u) {
+                    const uint32_t r = word_of(R[p >> 2], p & 3);
+                    const uint32_t skip = excl & self_in;                 // 1 when this actor must skip itself
+                    const uint32_t n = n0 - skip;
+                    const uint32_t k = __umulhi(r, n);
+                    int idx;
+                    if (P8 <= 16) {
+                        const uint32_t j = k + ((skip && k >= rank) ? 1u : 0u);
+                        idx = (int)((lut >> (4 * j)) & 0xFu);
+                    } else {
+                        idx = kth_set_bit<P8>(legal0 & ~(skip << p), k);
+                    }
+                    const uint32_t choice = n ? (uint32_t)idx + 1u : 0u;
+                    if (n) {
+                        chosen |= 1u << idx;
+                        if (tallying) { if (P8 <= 8) nib += 1u << (4 * idx); else tally.add(1u << idx); }
+                    }
+                    if (!have_first) { first_choice = choice; have_first = true; }
+                    if (record) s.tw[p >> 2] = (s.tw[p >> 2] & ~(0xFFu << (8 * (p & 3)))) | (choice << (8 * (p & 3)));
+                }
+                rank += self_in;
+            }
+        } else {
         uint32_t rem = actors;
         int cur_blk = -1;
         uint4 r4 = make_uint4(0, 0, 0, 0);
@@ -162,23 +302,37 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const Fi
                 const uint32_t n = __popc(legal);
                 const int idx = kth_set_bit<P8>(legal, __umulhi(r, n));
                 choice = n ? (uint32_t)idx + 1u : 0u;
-                if (n) { chosen |= 1u << idx; tally.add(1u << idx); }
+                if (n) { chosen |= 1u << idx; if (tallying) tally.add(1u << idx); }
             } else if (aop == ACT_PICK_OPTION) {
-                choice = 1u + __umulhi(r, (uint32_t)ph.action_arg);
+                choice = 1u + __umulhi(r, (uint32_t)v.action_arg());
             } else {
                 choice = 1u;
             }
             if (is_first) first_choice = choice;
             if (record) set_byte(s.tw, p, choice);
         }
+        }
+        // plurality: candidates sharing the highest non-zero count (lowest id wins ties)
+        uint32_t top = 0;
+        if (tallying) {
+            if (nib_used) {
+                uint32_t best = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t c = (nib >> (4 * q)) & 0xFu;
+                    if (c > best) { best = c; top = 1u << q; } else if (c == best && c) top |= 1u << q;
+                }
+            } else {
+                top = tally.top();
+            }
+        }
         if (record) dirty |= DIRTY_PL;
         // ---- RefereeNode, effects of the phase just left
-        switch (ph.exit_op) {
-        case EX_VOTE_KILL: {
+        switch (exo) {
+        case EX_VOTE_KILL:
             s.submitted |= actors; dirty |= DIRTY_C1;
-            const uint32_t top = tally.top();
             kill = top ? (uint32_t)__ffs(top) : 0u;
-        } break;
+            break;
         case EX_PROTECT:
             s.submitted |= actors; dirty |= DIRTY_C1;
             protect = first_choice;
@@ -189,10 +343,9 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const Fi
             kill = 0; protect = 0;
             break;
         case EX_DAY_VOTE: {
-            const uint32_t top = tally.top();
             const uint32_t x = top ? (uint32_t)__ffs(top) : 0u;
             const bool tied = __popc(top) > 1;
-            if (T.h.max_revotes > 0 && tied && (revote & 0x7Fu) < T.h.max_revotes) {
+            if (v.max_revotes() > 0 && tied && (revote & 0x7Fu) < (uint32_t)v.max_revotes()) {
                 revote = ((revote & 0x7Fu) + 1u) | 0x80u;
             } else {
                 revote &= 0x7Fu;
@@ -204,7 +357,7 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const Fi
     }
 
     // ---- RefereeNode, effects of entering Y
-    const int en = T.phase[Y].entry_op;
+    const int en = v.entry_op_after(taken);
     if (en == EN_ASSIGN_ROLES) {
         uint32_t key[P8];
 #pragma unroll
@@ -218,7 +371,7 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const Fi
         }
         // rank < W+2 is all that matters: pick the W+2 smallest (key, id) pairs in order
         uint32_t rem = ALL, wolf = 0, lo = 0, hi = 0;
-        const int W = T.h.n_wolves;
+        const int W = v.n_wolves();
         for (int round = 0; round < W + 2; ++round) {
             uint32_t best = 0; int bi = -1;
 #pragma unroll
@@ -247,6 +400,38 @@ __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const Fi
     s.h1 = winner | (kill << 8) | (protect << 16) | (revote << 24);
     s.h0 = (uint32_t)Y | ((uint32_t)X << 8) | ((step0 + 1u) << 16);
     return Y;
+}
+
+// Generic entry: interpret the run-time table.  Returns the phase entered or -1 for a terminal session.
+template <int P8>
+__device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
+                                      uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    const int X = s.h0 & 0xFF;
+    if (T.phase[X].kind == KIND_TERMINAL) return -1;
+    dirty |= DIRTY_C0;
+    if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
+    return w_step_body<P8>(RtView(T, X), X, s, F, sid_lo, sid_hi, k0, k1, dirty);
+}
+
+// Specialised entry: a warp-uniform switch over the phases of a build-time table.
+template <int P8, class Spec, int X>
+__device__ __forceinline__ int w_step_spec_case(WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
+                                                uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
+    dirty |= DIRTY_C0;
+    if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
+    return w_step_body<P8>(CtView<Spec, X>{}, X, s, F, sid_lo, sid_hi, k0, k1, dirty);
+}
+
+template <int P8, class Spec, int X = 0>
+__device__ __forceinline__ int w_step_spec(WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
+                                           uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    if constexpr (X >= Spec::n_phases) {
+        return -1;
+    } else {
+        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X>(s, F, sid_lo, sid_hi, k0, k1, dirty);
+        return w_step_spec<P8, Spec, X + 1>(s, F, sid_lo, sid_hi, k0, k1, dirty);
+    }
 }
 
 // A step of a session whose phase needs nothing but column 0 (UI / timer phases with no effects; the host
@@ -305,7 +490,9 @@ __device__ __forceinline__ uint32_t need_of(const DevTable& T, uint32_t present)
     return need;
 }
 
-template <int P8>
+// Spec = void: interpret the run-time table T.  Spec = a generated ge::spec struct: the same table known at
+// build time (the host only selects this instantiation when the blobs are byte-identical).
+template <int P8, class Spec = void>
 __global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
 k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
     constexpr int S = 48 + P8;
@@ -388,7 +575,10 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
             for (int it = 0; it < A.n_steps; ++it) {
                 int np = -1;
                 if (live) {
-                    np = w_step<P8>(T, s, F, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                    if constexpr (std::is_void<Spec>::value)
+                        np = w_step<P8>(T, s, F, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                    else
+                        np = w_step_spec<P8, Spec>(s, F, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
                     if (np < 0) live = false;
                 }
                 visits.add(s_visits, np, lane);

@@ -34,7 +34,9 @@ extern "C" {
 /* kernel mappings (ge_batch_set_kernel) */
 #define GE_KERNEL_AUTO 0
 #define GE_KERNEL_COOP 1          /* one lane per player, warp ballots / match_any (32/P sessions per warp) */
-#define GE_KERNEL_TPS 2           /* one thread per session, bit-sliced tallies */
+#define GE_KERNEL_TPS 2           /* one thread per session, bit-sliced tallies; uses the build-time specialised
+                                     instantiation when the table is byte-identical to a shipped game's */
+#define GE_KERNEL_TPS_GENERIC 3   /* one thread per session, always the run-time table interpreter */
 
 /* ---- binary transition table (produced by game_engine_b200/compiler.py) -------------------------
  * Replaces: the per-step LLM reading of dsl['phases'] (reference agent/game_agent_v2.py:1022-1103,

@@ -122,3 +122,14 @@ def test_reference_yaml_compiles_to_identical_table(game, P):
         ref = yaml.safe_load(f)
     a, b = compile_game(game, P, dsl=ref), compile_game(game, P)
     assert a.blob == b.blob and a.phase_names == b.phase_names and a.template == b.template
+
+
+def test_revote_variant_compiles_with_tie_branches():
+    cg = compile_game("werewolf-revote", 32)
+    t = cg.table
+    assert t.max_revotes == 2 and cg.phase_ids[-3:] == [17, 18, 99]
+    for announce, revote in ((8, 17), (16, 18)):
+        br = t.phases[cg.index_of(announce)].branches
+        assert [(b.op, cg.phase_ids[b.next]) for b in br] == [(T.BR_TIE_PENDING, revote), (T.BR_ALWAYS, 9)]
+        rv = t.phases[cg.index_of(revote)]
+        assert rv.kind == T.KIND_ACTION and rv.exit_op == T.EX_DAY_VOTE and cg.phase_ids[rv.branches[0].next] == announce

@@ -7,10 +7,11 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-WEREWOLF, TTL = "werewolf-(mafia)", "two-truths-and-a-lie"
+WEREWOLF, TTL, REVOTE = "werewolf-(mafia)", "two-truths-and-a-lie", "werewolf-revote"
 CASES = [
     (TTL, 4), (TTL, 3), (TTL, 7), (TTL, 12), (TTL, 32),
     (WEREWOLF, 8), (WEREWOLF, 4), (WEREWOLF, 5), (WEREWOLF, 13), (WEREWOLF, 16), (WEREWOLF, 21), (WEREWOLF, 32),
+    (REVOTE, 8), (REVOTE, 32),          # extended game: tie -> re-vote phases (BASELINE config 4)
 ]
 
 
@@ -20,7 +21,7 @@ def _batch(cg, n, first, seed, kernel):
     return t, SessionBatch(t, n, first_session_id=first, seed=seed, kernel=kernel)
 
 
-@pytest.mark.parametrize("kernel", ["tps", "coop"])
+@pytest.mark.parametrize("kernel", ["tps", "tps_generic", "coop"])
 @pytest.mark.parametrize("game,P", CASES)
 def test_every_step_bit_exact(games, oracle_for, game, P, kernel):
     cg = games(game, P)
@@ -47,8 +48,8 @@ def test_every_step_bit_exact(games, oracle_for, game, P, kernel):
     assert b.counted_steps() == int(ost[0])
 
 
-@pytest.mark.parametrize("kernel", ["tps", "coop"])
-@pytest.mark.parametrize("game,P,n", [(WEREWOLF, 8, 1 << 16), (WEREWOLF, 32, 1 << 14), (TTL, 4, 1 << 16)])
+@pytest.mark.parametrize("kernel", ["tps", "tps_generic", "coop"])
+@pytest.mark.parametrize("game,P,n", [(WEREWOLF, 8, 1 << 16), (WEREWOLF, 32, 1 << 14), (TTL, 4, 1 << 16), (REVOTE, 32, 1 << 13)])
 def test_run_to_completion_matches(games, oracle_for, game, P, n, kernel):
     cg = games(game, P)
     o = oracle_for(cg)
@@ -56,7 +57,7 @@ def test_run_to_completion_matches(games, oracle_for, game, P, n, kernel):
     t, b = _batch(cg, n, first, seed, kernel)
     rec = o.init(n)
     ost = o.new_stats()
-    steps = 256
+    steps = 400 if game == REVOTE else 256
     b.step(steps)
     o.step(rec, first, seed, steps, ost)
     np.testing.assert_array_equal(b.export_state(), rec)

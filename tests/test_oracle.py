@@ -31,9 +31,10 @@ def _popc(a):
     return np.array([bin(int(x)).count("1") for x in a])
 
 
-@pytest.mark.parametrize("P", [4, 8, 13, 16, 32])
-def test_werewolf_properties(games, oracle_for, P):
-    cg = games(WEREWOLF, P)
+@pytest.mark.parametrize("game,P", [(WEREWOLF, 4), (WEREWOLF, 8), (WEREWOLF, 13), (WEREWOLF, 16), (WEREWOLF, 32),
+                                    ("werewolf-revote", 8), ("werewolf-revote", 16)])
+def test_werewolf_properties(games, oracle_for, game, P):
+    cg = games(game, P)
     o = oracle_for(cg)
     n, seed = 2000, 11
     rec = o.init(n)
@@ -41,7 +42,7 @@ def test_werewolf_properties(games, oracle_for, P):
     term = len(cg.phase_ids) - 1
     edges = {i: {b.next for b in ph.branches} for i, ph in enumerate(cg.table.phases)}
     prev_alive = _popc(_fields_w(rec)["alive"])
-    for k in range(300):
+    for k in range(420 if game != WEREWOLF else 300):
         before = rec.copy()
         o.step(rec, 0, seed, 1, st)
         f, fb = _fields_w(rec), _fields_w(before)
