@@ -49,7 +49,8 @@ def parse_args():
     ap.add_argument("--sessions", type=int, default=1 << 20, help="sessions per batch (per GPU)")
     ap.add_argument("--ring", type=int, default=8, help="batches in the ring (footprint must exceed L2)")
     ap.add_argument("--cap", type=int, default=0, help="steps before a batch is re-initialised (0 = by player count)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "tps", "coop"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tps", "tps_generic", "coop"])
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the ring's independent batches are spread over")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--e2e-calls", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -266,17 +267,20 @@ def run_ours(a):
     cap = a.cap or game_cap(cg.family, a.players, cg.table.max_revotes)
     N, R = a.sessions, a.ring
     tab = Table(cg)
-    stream = torch.cuda.Stream(device=dev)
+    # the ring's batches are independent sessions: batch i runs on stream i % NS so that one batch's launch
+    # ramp / tail and near-empty late-game launches overlap with another batch's work
+    NS = max(1, min(a.streams, R))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
+    stream = streams[0]
     torch.cuda.set_stream(stream)
-    sh = stream.cuda_stream
 
     # session ids: unique across ranks, ring slots and epochs
     def sid_base(epoch, slot):
         return ((epoch * world + rank) * R + slot) * N
 
     ring = [SessionBatch(tab, N, first_session_id=sid_base(0, i), seed=a.seed, device=local_rank, kernel=a.kernel) for i in range(R)]
-    for b in ring:
-        b.set_stream(sh)
+    for i, b in enumerate(ring):
+        b.set_stream(streams[i % NS].cuda_stream)
     age = [0] * R
     epoch = [0] * R
     for i, b in enumerate(ring):                     # stagger: batch i starts i*cap/R steps into its games
@@ -284,24 +288,40 @@ def run_ours(a):
         if pre:
             b.step(pre)
         age[i] = pre
+    from game_engine_b200.batch import step_many
     k_global = 0
     resets = 0
 
-    def one_step():
+    def run_steps(n):
+        """n launches, round-robin over the ring starting at slot k_global % R; a batch that has been stepped
+        `cap` times (the longest possible game) is first re-initialised with fresh session ids.  Whole rounds
+        that need no re-initialisation go to the library in one ge_step_many call (keeps Python out of the way)."""
         nonlocal k_global, resets
-        i = k_global % R
-        b = ring[i]
-        if age[i] >= cap:
-            epoch[i] += 1
-            b.reset(first_session_id=sid_base(epoch[i], i))
-            age[i] = 0
-            resets += 1
-        b.step(1)
-        age[i] += 1
-        k_global += 1
+        while n > 0:
+            i = k_global % R
+            if age[i] >= cap:
+                epoch[i] += 1
+                ring[i].reset(first_session_id=sid_base(epoch[i], i))
+                age[i] = 0
+                resets += 1
+            run = 0                                   # launches until some batch hits the cap, walking from slot i
+            while run < n and age[(i + run) % R] + (run // R) < cap:
+                run += 1
+            run = max(run, 1)
+            head = min(run, (R - i) % R)              # finish the current round first
+            for j in range(head):
+                ring[(i + j) % R].step(1)
+            full, tail = divmod(run - head, R)
+            if full:
+                step_many(ring, full)
+            for j in range(tail):
+                ring[j].step(1)
+            for j in range(run):
+                age[(i + j) % R] += 1
+            k_global += run
+            n -= run
 
-    for _ in range(max(3, a.warmup)):
-        one_step()
+    run_steps(max(3, a.warmup))
     torch.cuda.synchronize()
     counted0 = sum(b.counted_steps() for b in ring)
     launches0 = sum(b.launch_count() for b in ring)
@@ -313,9 +333,16 @@ def run_ours(a):
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(a.steps):
-        one_step()
+    ev0.record(stream)                                       # every stream is idle here (device synchronised above)
+    for st in streams[1:]:
+        st.wait_event(ev0)
+    t_enq0 = time.perf_counter()
+    run_steps(a.steps)
+    enqueue_ms = (time.perf_counter() - t_enq0) * 1e3        # host time to enqueue K steps
+    for st in streams[1:]:                                   # join: ev1 fires when the work of ALL streams is done
+        e = torch.cuda.Event()
+        e.record(st)
+        stream.wait_event(e)
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -330,6 +357,7 @@ def run_ours(a):
     # the job's only exchange step: statistics all-reduce (win rate + phase-length histogram) over NCCL
     t_ar0 = time.perf_counter()
     for b in ring:
+        b.set_stream(stream.cuda_stream)
         b.stats_refresh()
         agg += torch.as_tensor(_CudaArray(b.stats_device_ptr(), 560), device=dev)
     if world > 1:
@@ -414,7 +442,7 @@ def run_ours(a):
         "dtype": "u32", "data": "synthetic",
         "config": {
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
-            "kernel": kern, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
+            "kernel": kern, "streams": NS, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
             "steps_before_reinit": cap, "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
             "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,
         },
@@ -426,6 +454,7 @@ def run_ours(a):
         "gpu_launches": launches_all,
         "clocks": clocks,
         "stats_allreduce_ms": allreduce_ms,
+        "host_enqueue_ms": enqueue_ms,
         "win_rate": {"villagers": float(stats[2]) / max(1.0, float(stats[2] + stats[3])),
                      "werewolves": float(stats[3]) / max(1.0, float(stats[2] + stats[3])),
                      "sessions_finished": int(stats[2] + stats[3])} if cg.family == 1 else None,

@@ -84,6 +84,12 @@ class SessionBatch:
         capi.check(capi.lib().ge_batch_active(self._h, ctypes.byref(v)))
         return int(v.value)
 
+    def active_hint(self) -> int:
+        """Non-blocking upper bound of active() (refreshed after each compaction); 0 = every game is over."""
+        v = ctypes.c_uint64()
+        capi.check(capi.lib().ge_batch_active_hint(self._h, ctypes.byref(v)))
+        return int(v.value)
+
     def clear_stats(self) -> None:
         capi.check(capi.lib().ge_batch_clear_stats(self._h))
 
@@ -157,6 +163,12 @@ class SessionBatch:
             self.close()
         except Exception:
             pass
+
+
+def step_many(batches, n_rounds: int = 1) -> None:
+    """n_rounds round-robin passes: one step of every batch in order (one C call; see ge_step_many)."""
+    arr = (ctypes.c_void_p * len(batches))(*[b._h for b in batches])
+    capi.check(capi.lib().ge_step_many(arr, len(batches), int(n_rounds)))
 
 
 class PinnedBuffer:

@@ -32,8 +32,10 @@ SYMBOLS = [
     ("ge_batch_set_kernel", _int, [_vp, _int]),
     ("ge_batch_set_compaction", _int, [_vp, _int, _int]),
     ("ge_batch_active", _int, [_vp, ctypes.POINTER(_u64)]),
+    ("ge_batch_active_hint", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_get_kernel", _int, [_vp]),
     ("ge_step", _int, [_vp, _int, _vp]),
+    ("ge_step_many", _int, [ctypes.POINTER(_vp), _int, _int]),
     ("ge_run_fused", _int, [_vp, _int, _vp]),
     ("ge_sync", _int, [_vp]),
     ("ge_export_state", _int, [_vp, _u64, _u64, _vp]),

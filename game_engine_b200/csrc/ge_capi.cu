@@ -61,6 +61,8 @@ struct ge_batch {
     int scan_blocks, dead_shift;
     unsigned long long* d_cstate; // [0] n_active  [1] n_live  [2] pairs to swap  [3] live already in front  [4] old tiles
     int compact_every, since_compact;
+    unsigned long long* h_hint;   // pinned {n_active, epoch}: refreshed by an async copy after every compaction
+    unsigned long long epoch;     // bumped by every (re)initialisation; stale hints are ignored
     bool compacted;               // origin may differ from identity
     uint32_t* d_presence;         // 3 rotating phase-presence words (StepArgs::presence)
     uint32_t launch_idx;          // index of the next step launch
@@ -175,8 +177,8 @@ __global__ void k_iota(uint32_t* origin, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) origin[i] = (uint32_t)i;
 }
 
-__global__ void k_cstate_reset(unsigned long long* cstate, unsigned long long n) {
-    if (threadIdx.x < 8) cstate[threadIdx.x] = threadIdx.x == 0 ? n : 0ull;
+__global__ void k_cstate_reset(unsigned long long* cstate, unsigned long long n, unsigned long long epoch) {
+    if (threadIdx.x < 8) cstate[threadIdx.x] = threadIdx.x == 0 ? n : threadIdx.x == 7 ? epoch : 0ull;   // [7] = epoch tag
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t* total) {
@@ -465,7 +467,8 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
     b->launches++;
     CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
     b->next_override = 1u;        // every session is in phase index 0
-    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n);
+    b->epoch++;
+    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch);
     CU(cudaGetLastError());
     b->compacted = false;
     b->since_compact = 0;
@@ -518,6 +521,8 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (e == cudaSuccess) e = cudaMemset(b->d_live_mask, 0, mask_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_prefix, mask_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cstate, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc(&b->h_hint, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) { b->h_hint[0] = n_sessions; b->h_hint[1] = 0; }
     b->scan_blocks = (int)((b->n_tiles + CS_TILES - 1) / CS_TILES);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_blk, ((size_t)b->scan_blocks + 2) * sizeof(uint32_t));
     b->dead_shift = 2;                                   // compact when >= 1/4 of the active prefix is dead
@@ -526,7 +531,7 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     b->stream = b->own_stream;
     if (e != cudaSuccess) {
         cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_presence);
-        cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate);
+        cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
         delete b;
         return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_create: ") + cudaGetErrorString(e));
     }
@@ -557,7 +562,7 @@ extern "C" void ge_batch_destroy(ge_batch* b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     if (b->own_stream) { cudaStreamSynchronize(b->own_stream); cudaStreamDestroy(b->own_stream); }
     cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_stage); cudaFree(b->d_presence);
-    cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate);
+    cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
     delete b;
 }
 
@@ -590,6 +595,15 @@ extern "C" int ge_batch_set_compaction(ge_batch* b, int every_n_steps, int min_d
     return GE_OK;
 }
 
+extern "C" int ge_batch_active_hint(ge_batch* b, uint64_t* out) {
+    if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_batch_active_hint");
+    // the pair is written by two ordered copies; a hint from an older epoch (before the last reset) is ignored
+    const unsigned long long ep = ((volatile unsigned long long*)b->h_hint)[1];
+    const unsigned long long v = ((volatile unsigned long long*)b->h_hint)[0];
+    *out = (ep == b->epoch && ((volatile unsigned long long*)b->h_hint)[1] == ep) ? v : b->n;
+    return GE_OK;
+}
+
 extern "C" int ge_batch_active(ge_batch* b, uint64_t* out) {
     if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_batch_active");
     CU(cudaSetDevice(b->device));
@@ -614,6 +628,9 @@ static int enqueue_compaction(ge_batch* b, cudaStream_t st) {
     CU(cudaGetLastError());
     b->launches += 2;
     b->since_compact = 0;
+    // non-blocking progress hint for the host: {n_active, epoch} (cstate[0], cstate[7] are not adjacent: two copies)
+    CU(cudaMemcpyAsync(&b->h_hint[0], b->d_cstate, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&b->h_hint[1], b->d_cstate + 7, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     return GE_OK;
 }
 
@@ -646,6 +663,21 @@ extern "C" int ge_step(ge_batch* b, int n_steps, void* cuda_stream) {
     if (!b || n_steps < 0) return fail(GE_ERR_ARG, "bad arguments to ge_step");
     CU(cudaSetDevice(b->device));
     return launch_steps(b, n_steps, 1, cuda_stream ? (cudaStream_t)cuda_stream : b->stream);
+}
+
+extern "C" int ge_step_many(ge_batch** batches, int n_batches, int n_rounds) {
+    if (!batches || n_batches < 0 || n_rounds < 0) return fail(GE_ERR_ARG, "bad arguments to ge_step_many");
+    for (int i = 0; i < n_batches; ++i)
+        if (!batches[i]) return fail(GE_ERR_ARG, "NULL batch in ge_step_many");
+    int cur_dev = -1;
+    for (int r = 0; r < n_rounds; ++r)
+        for (int i = 0; i < n_batches; ++i) {
+            ge_batch* b = batches[i];
+            if (b->device != cur_dev) { CU(cudaSetDevice(b->device)); cur_dev = b->device; }
+            const int rc = launch_steps(b, 1, 1, b->stream);
+            if (rc != GE_OK) return rc;
+        }
+    return GE_OK;
 }
 
 extern "C" int ge_run_fused(ge_batch* b, int n_steps, void* cuda_stream) {
@@ -697,7 +729,8 @@ static int restore_order(ge_batch* b) {
         b->launches += 2;
         b->compacted = false;
     }
-    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n);
+    b->epoch++;
+    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch);
     CU(cudaGetLastError());
     b->since_compact = 0;
     CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));

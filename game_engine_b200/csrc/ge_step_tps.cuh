@@ -520,6 +520,18 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
 
     if (need == 0) {
         // ---- light path: every present phase touches column 0 only.  Four tiles in flight per warp.
+        // Sessions move in lockstep, so usually ONE non-terminal phase x0 is present: its single successor is
+        // resolved once here and the common lane only rewrites the header word.
+        uint32_t nonterm = 0;
+        for (int i = 0; i < T.h.n_phases; ++i)
+            if (T.phase[i].kind != KIND_TERMINAL) nonterm |= 1u << i;
+        const uint32_t live_present = present_in & nonterm;
+        int x0 = -1; uint32_t y0 = 0, tag0 = 0;
+        if (__popc(live_present) == 1) {
+            const int x = __ffs(live_present) - 1;
+            if (T.phase[x].n_branches == 1 && T.phase[x].br[0].op == BR_ALWAYS) { x0 = x; y0 = T.phase[x].br[0].next; tag0 = T.phase[x].br[0].tag; }
+        }
+        const bool y0_live = x0 >= 0 && T.phase[y0].kind != KIND_TERMINAL;
         for (uint32_t tile = warp0; tile < n_tiles_act; tile += 4 * nwarps) {
             uint4 c[4];
 #pragma unroll
@@ -532,11 +544,31 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
                 const uint32_t t = tile + j * nwarps;
                 if (t < n_tiles_act) {                        // warp-uniform
                     const bool in_range = (uint64_t)t * 32 + lane < n_act;
-                    const int np = in_range ? w_step_light(T, c[j]) : -1;
-                    visits.add(s_visits, np, lane);
+                    const bool fast = in_range && (int)(c[j].x & 0xFF) == x0 && (c[j].x >> 16) != 0;
+                    int np = -1;
+                    if (fast) {
+                        c[j].x = y0 | ((uint32_t)x0 << 8) | ((c[j].x & 0xFFFF0000u) + 0x10000u);
+                        if (tag0) c[j].y = (c[j].y & ~0xFFu) | tag0;
+                        np = (int)y0;
+                    } else if (in_range) {
+                        np = w_step_light(T, c[j]);
+                    }
+                    const uint32_t stepped = __ballot_sync(0xFFFFFFFFu, np >= 0);
                     if (np >= 0) st128(A.tiles + (uint64_t)t * (32 * S) + lane * 16, c[j]);
-                    if (in_range) present_out |= 1u << (c[j].x & 31);
-                    const uint32_t lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[c[j].x & 31].kind != KIND_TERMINAL);
+                    uint32_t lm;
+                    if (__ballot_sync(0xFFFFFFFFu, fast) == stepped) {          // warp-uniform: every stepped lane took the fast route
+                        if (stepped) {
+                            if ((int)y0 != visits.phase) { visits.flush(s_visits, lane); visits.phase = (int)y0; }
+                            visits.count += __popc(stepped);
+                            present_out |= 1u << y0;
+                        }
+                        lm = y0_live ? stepped : 0u;
+                        if (stepped != 0xFFFFFFFFu && in_range && np < 0) present_out |= 1u << (c[j].x & 31);
+                    } else {
+                        visits.add(s_visits, np, lane);
+                        if (in_range) present_out |= 1u << (c[j].x & 31);
+                        lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[c[j].x & 31].kind != KIND_TERMINAL);
+                    }
                     if (lane == 0) A.live_mask[t] = lm;
                     live_cnt += __popc(lm);
                 }

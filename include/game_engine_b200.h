@@ -97,6 +97,10 @@ int ge_batch_set_kernel(ge_batch *b, int kernel);
  * ge_batch_active returns the current prefix length (synchronises). */
 int ge_batch_set_compaction(ge_batch *b, int every_n_steps, int min_dead_shift);
 int ge_batch_active(ge_batch *b, uint64_t *out);
+/* Non-blocking variant: the value an asynchronous copy brought to the host after the most recent completed
+ * compaction of the current epoch (an upper bound that only decreases; n_sessions until the first one).
+ * 0 means every game of the batch is over — the cue to re-initialise it without waiting for a step cap. */
+int ge_batch_active_hint(ge_batch *b, uint64_t *out);
 int ge_batch_get_kernel(const ge_batch *b);
 
 /* Apply n_steps session-phase-steps to every non-terminal session: n_steps launches of the step
@@ -106,6 +110,10 @@ int ge_batch_get_kernel(const ge_batch *b);
  * _execute_update_player_actions / _execute_update_player_state (agent/tools/backend_tools.py:285-344,
  * 204-225). */
 int ge_step(ge_batch *b, int n_steps, void *cuda_stream);
+/* Round-robin over several batches: n_rounds times, one ge_step(b, 1) for every batch in order, each on
+ * its own (bound) stream.  One call instead of n_rounds * n_batches keeps the host out of the way when the
+ * launches are short. */
+int ge_step_many(ge_batch **batches, int n_batches, int n_rounds);
 /* Same semantics with the state kept in registers for up to n_steps steps (one launch). */
 int ge_run_fused(ge_batch *b, int n_steps, void *cuda_stream);
 int ge_sync(ge_batch *b);
