@@ -127,6 +127,18 @@ class SessionBatch:
         pst = stats_out.ctypes.data if stats_out is not None else None
         capi.check(capi.lib().ge_run_host(self._h, pin, pout, int(n_steps), pst))
 
+    def set_host_fused(self, on: bool) -> None:
+        """Host-buffer calls apply their n_steps in one fused launch (state in registers) when on."""
+        capi.check(capi.lib().ge_batch_set_host_fused(self._h, 1 if on else 0))
+
+    def run_host_async(self, records_in: Optional[np.ndarray], records_out: Optional[np.ndarray], n_steps: int,
+                       stats_out: Optional[np.ndarray] = None) -> None:
+        """run_host without the final synchronisation (pinned buffers; call sync() before reading them)."""
+        pin = records_in.ctypes.data if records_in is not None else None
+        pout = records_out.ctypes.data if records_out is not None else None
+        pst = stats_out.ctypes.data if stats_out is not None else None
+        capi.check(capi.lib().ge_run_host_async(self._h, pin, pout, int(n_steps), pst))
+
     # ---- statistics
     def stats(self) -> np.ndarray:
         out = np.zeros(capi.STATS_LEN, dtype=np.uint64)

@@ -41,6 +41,8 @@ SYMBOLS = [
     ("ge_export_state", _int, [_vp, _u64, _u64, _vp]),
     ("ge_import_state", _int, [_vp, _u64, _u64, _vp]),
     ("ge_run_host", _int, [_vp, _vp, _vp, _int, _vp]),
+    ("ge_run_host_async", _int, [_vp, _vp, _vp, _int, _vp]),
+    ("ge_batch_set_host_fused", _int, [_vp, _int]),
     ("ge_host_alloc", _int, [ctypes.POINTER(_vp), _sz]),
     ("ge_host_free", None, [_vp]),
     ("ge_stats_refresh", _int, [_vp, _vp]),

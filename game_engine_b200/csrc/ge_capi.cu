@@ -61,6 +61,7 @@ struct ge_batch {
     int scan_blocks, dead_shift;
     unsigned long long* d_cstate; // [0] n_active  [1] n_live  [2] pairs to swap  [3] live already in front  [4] old tiles
     int compact_every, since_compact;
+    bool host_fused;              // ge_run_host[_async]: apply n_steps in one fused launch
     unsigned long long* h_hint;   // pinned {n_active, epoch}: refreshed by an async copy after every compaction
     unsigned long long epoch;     // bumped by every (re)initialisation; stale hints are ignored
     bool compacted;               // origin may differ from identity
@@ -595,6 +596,12 @@ extern "C" int ge_batch_set_compaction(ge_batch* b, int every_n_steps, int min_d
     return GE_OK;
 }
 
+extern "C" int ge_batch_set_host_fused(ge_batch* b, int on) {
+    if (!b) return fail(GE_ERR_ARG, "batch is NULL");
+    b->host_fused = on != 0;
+    return GE_OK;
+}
+
 extern "C" int ge_batch_active_hint(ge_batch* b, uint64_t* out) {
     if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_batch_active_hint");
     // the pair is written by two ordered copies; a hint from an older epoch (before the last reset) is ignored
@@ -810,12 +817,30 @@ extern "C" int ge_counted_steps(ge_batch* b, uint64_t* out) {
     return GE_OK;
 }
 
+extern "C" int ge_run_host_async(ge_batch* b, const void* records_in, void* records_out, int n_steps, uint64_t* host_stats) {
+    if (!b || n_steps < 0) return fail(GE_ERR_ARG, "bad arguments to ge_run_host_async");
+    CU(cudaSetDevice(b->device));
+    int rc;
+    if (records_in && (rc = import_async(b, 0, b->n, records_in)) != GE_OK) return rc;
+    if (b->host_fused && n_steps > 1) rc = launch_steps(b, 1, n_steps, b->stream);
+    else rc = launch_steps(b, n_steps, 1, b->stream);
+    if (rc != GE_OK) return rc;
+    if (records_out && (rc = export_async(b, 0, b->n, records_out)) != GE_OK) return rc;
+    if (host_stats) {
+        if ((rc = ge_stats_refresh(b, nullptr)) != GE_OK) return rc;
+        CU(cudaMemcpyAsync(host_stats, b->d_stats_out, GE_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
+    }
+    return GE_OK;
+}
+
 extern "C" int ge_run_host(ge_batch* b, const void* records_in, void* records_out, int n_steps, uint64_t* host_stats) {
     if (!b || n_steps < 0) return fail(GE_ERR_ARG, "bad arguments to ge_run_host");
     CU(cudaSetDevice(b->device));
     int rc;
     if (records_in && (rc = import_async(b, 0, b->n, records_in)) != GE_OK) return rc;
-    if ((rc = launch_steps(b, n_steps, 1, b->stream)) != GE_OK) return rc;
+    if (b->host_fused && n_steps > 1) rc = launch_steps(b, 1, n_steps, b->stream);
+    else rc = launch_steps(b, n_steps, 1, b->stream);
+    if (rc != GE_OK) return rc;
     if (records_out && (rc = export_async(b, 0, b->n, records_out)) != GE_OK) return rc;
     if (host_stats) {
         if ((rc = ge_stats_refresh(b, nullptr)) != GE_OK) return rc;

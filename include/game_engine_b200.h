@@ -128,6 +128,12 @@ int ge_import_state(ge_batch *b, uint64_t first, uint64_t count, const void *hos
  * n_steps steps, records_out (NULL = skip) and stats (NULL = skip) back to the host.  Synchronous.
  * Pinned buffers (ge_host_alloc) make the copies asynchronous DMA. */
 int ge_run_host(ge_batch *b, const void *records_in, void *records_out, int n_steps, uint64_t *host_stats);
+/* The same work enqueued on the batch's stream without the final synchronisation (host buffers must be pinned
+ * and stay valid until ge_sync).  Several batches driven this way overlap H2D, compute and D2H. */
+int ge_run_host_async(ge_batch *b, const void *records_in, void *records_out, int n_steps, uint64_t *host_stats);
+/* on != 0: the host-buffer calls apply their n_steps in ONE fused launch (state in registers across the steps,
+ * as ge_run_fused) instead of n_steps launches — the right mode for run-to-completion calls on small batches. */
+int ge_batch_set_host_fused(ge_batch *b, int on);
 int ge_host_alloc(void **p, size_t bytes);
 void ge_host_free(void *p);
 

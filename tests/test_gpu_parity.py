@@ -199,3 +199,31 @@ def test_import_after_compaction_restores_order(games, oracle_for):
     c.set_kernel("coop")
     c.step(45)
     np.testing.assert_array_equal(c.export_state(), rec)
+
+
+def test_run_host_async_pipeline(games, oracle_for):
+    """Several sub-batches driven with run_host_async overlap copies and compute; results equal one oracle run."""
+    from game_engine_b200.batch import PinnedBuffer, SessionBatch, Table
+    cg = games(WEREWOLF, 8)
+    o = oracle_for(cg)
+    n, nsub, seed = 8192, 4, 13
+    sub = n // nsub
+    S = cg.record_size
+    tab = Table(cg)
+    subs = [SessionBatch(tab, sub, first_session_id=j * sub, seed=seed) for j in range(nsub)]
+    pin_in, pin_out, pin_st = PinnedBuffer(n * S), PinnedBuffer(n * S), PinnedBuffer(nsub * 560 * 8)
+    rin = pin_in.array.reshape(nsub, sub, S)
+    rout = pin_out.array.reshape(nsub, sub, S)
+    rst = pin_st.array.view(np.uint64).reshape(nsub, 560)
+    rec = o.init(n)
+    rin[:] = rec.reshape(nsub, sub, S)
+    for j, sb in enumerate(subs):
+        sb.set_host_fused(j % 2 == 0)            # fused and launch-per-step sub-batches must agree
+        sb.run_host_async(rin[j], rout[j], 56, rst[j])
+    for sb in subs:
+        sb.sync()
+    ost = o.new_stats()
+    o.step(rec, 0, seed, 56, ost)
+    o.stats_final(rec, ost)
+    np.testing.assert_array_equal(rout.reshape(n, S), rec)
+    np.testing.assert_array_equal(rst.sum(axis=0), ost)
