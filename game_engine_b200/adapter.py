@@ -76,7 +76,9 @@ class Record:
             if f < 8:
                 return base[f]
             if 8 <= f < 12:
-                return sum(1 << p for p in range(P) if self.role[p] == f - 8)
+                return sum(1 << p for p in range(P) if self.role[p] == f - 8) if self.secret else 0
+            if f == T.W_ROLES_ASSIGNED:
+                return ALL if self.secret else 0
             return 0
         if f < 5:
             return sum(1 << p for p in range(P) if (self.flags[p] >> f) & 1)

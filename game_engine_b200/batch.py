@@ -139,6 +139,23 @@ class SessionBatch:
         pst = stats_out.ctypes.data if stats_out is not None else None
         capi.check(capi.lib().ge_run_host_async(self._h, pin, pout, int(n_steps), pst))
 
+    def eval_preds(self, preds, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Lane masks [count, len(preds)] of DNF predicates (tuples (pos0, neg0, pos1, neg1)), e.g. the compiled
+        audience groups of a game (CompiledGame.audience_preds)."""
+        count = self.n - first if count is None else int(count)
+        arr = np.ascontiguousarray(np.array(list(preds), dtype=np.uint16).reshape(-1, 4))
+        out = np.zeros((count, arr.shape[0]), dtype=np.uint32)
+        capi.check(capi.lib().ge_eval_preds(self._h, arr.ctypes.data, arr.shape[0], int(first), count, out.ctypes.data))
+        return out
+
+    def audience_masks(self, first: int = 0, count: Optional[int] = None) -> dict:
+        """{group name: uint32[count]} for every audience group of the game's declaration."""
+        aud = self.table.game.audience_preds
+        if not aud:
+            return {}
+        m = self.eval_preds(list(aud.values()), first, count)
+        return {name: m[:, j].copy() for j, name in enumerate(aud)}
+
     # ---- statistics
     def stats(self) -> np.ndarray:
         out = np.zeros(capi.STATS_LEN, dtype=np.uint64)

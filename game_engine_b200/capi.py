@@ -45,6 +45,7 @@ SYMBOLS = [
     ("ge_batch_set_host_fused", _int, [_vp, _int]),
     ("ge_host_alloc", _int, [ctypes.POINTER(_vp), _sz]),
     ("ge_host_free", None, [_vp]),
+    ("ge_eval_preds", _int, [_vp, _vp, _int, _u64, _u64, _vp]),
     ("ge_stats_refresh", _int, [_vp, _vp]),
     ("ge_stats", _int, [_vp, _vp, _sz]),
     ("ge_stats_device_ptr", _vp, [_vp]),

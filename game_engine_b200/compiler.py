@@ -150,8 +150,10 @@ class _FieldMap:
             if name == "team":
                 if val == self.wolf_team:
                     return [self._lit(T.W_FIELDS["team_is_wolf"], not neg)]
-                if val == self.village_team:
-                    return [self._lit(T.W_FIELDS["team_is_wolf"], neg)]
+                if val == self.village_team:      # a villager is an ASSIGNED non-wolf (team is '' before role assignment)
+                    if not neg:
+                        return [(1 << T.W_ROLES_ASSIGNED, 1 << T.W_FIELDS["team_is_wolf"])]
+                    return [(0, 1 << T.W_ROLES_ASSIGNED), (1 << T.W_FIELDS["team_is_wolf"], 0)]
                 raise DSLCompileError("unknown team %r" % (val,))
             fields = T.W_FIELDS
         else:

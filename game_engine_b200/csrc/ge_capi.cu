@@ -306,6 +306,60 @@ __global__ void k_export_perm(const uint8_t* tiles, uint32_t S_dev, uint32_t S_c
     }
 }
 
+// ------------------------------------------------------------------------------------ audience masks
+// Evaluates up to 32 DNF predicates (same encoding as the table's) for every session of a window: the lane
+// masks of the DSL's audience_groups (reference games/werewolf-(mafia).yaml:138-165; consumed by the UI tools'
+// audience_ids, src/lib/canvas/types.ts:14-17).  Output row = session (original order), column = predicate.
+struct PredList { ge_pred_t p[32]; int n; };
+
+__global__ void k_eval_preds(const __grid_constant__ DevTable T, const __grid_constant__ PredList PL, const uint8_t* tiles,
+                             uint32_t S_dev, const uint32_t* __restrict__ origin, uint64_t n, uint64_t first, uint64_t count,
+                             uint32_t* out) {
+    const uint32_t n16 = S_dev / 16;
+    const int P = T.h.n_players;
+    const uint32_t ALL = P >= 32 ? 0xFFFFFFFFu : ((1u << P) - 1u);
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = origin ? origin[slot] : slot;
+        if (o < first || o >= first + count) continue;
+        const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S_dev);
+        const uint32_t sl = (uint32_t)(slot & 31);
+        uint32_t F[16];
+#pragma unroll
+        for (int f = 0; f < 16; ++f) F[f] = 0;
+        F[15] = ALL;
+        if (T.h.family == FAM_WEREWOLF) {
+            const uint4 c0 = *reinterpret_cast<const uint4*>(base + sl * 16);
+            const uint4 c1 = *reinterpret_cast<const uint4*>(base + 512 + sl * 16);
+            const uint4 c2 = *reinterpret_cast<const uint4*>(base + 1024 + sl * 16);
+            F[0] = c0.z; F[1] = c0.w; F[2] = c1.x; F[3] = c1.y; F[4] = c1.z; F[5] = c1.w; F[6] = c2.x; F[7] = c2.y;
+            F[8] = c2.y ? ~(c2.z | c2.w) & ALL : 0u; F[9] = c2.z & ~c2.w; F[10] = ~c2.z & c2.w; F[11] = c2.z & c2.w;
+            F[12] = c2.y ? ALL : 0u;
+        } else {
+            for (int p = 0; p < P; ++p) {
+                const uint32_t fl = *reinterpret_cast<const uint32_t*>(base + rt_tile_off(8 + 4 * p, sl, n16)) >> 24;
+#pragma unroll
+                for (int f = 0; f < 5; ++f) F[f] |= ((fl >> f) & 1u) << p;
+            }
+        }
+        for (int j = 0; j < PL.n; ++j) {
+            const ge_pred_t pr = PL.p[j];
+            uint32_t res = 0;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
+                uint32_t m = ALL;
+#pragma unroll
+                for (int f = 0; f < 16; ++f) {
+                    if ((pos >> f) & 1u) m &= F[f];
+                    if ((neg >> f) & 1u) m &= ~F[f];
+                }
+                res |= m;
+            }
+            out[(o - first) * PL.n + j] = res;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ table
 static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     if (!blob || n < sizeof(ge_table_header_t)) return fail(GE_ERR_ARG, "table blob too small");
@@ -351,7 +405,7 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             if (lits[2 * c + 1] & 0x8000u) continue;          // clause marked empty (& ~ALL)
             const uint16_t used = lits[2 * c] | lits[2 * c + 1];
             if (used & 0x003Cu) out |= 1;
-            if (used & 0x0FC0u) out |= 2;
+            if (used & 0x1FC0u) out |= 2;
         }
         return out;
     };
@@ -377,6 +431,9 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
         t->dev.need[i] = need;
     }
     if (t->dev.phase[0].id != 0) return fail(GE_ERR_ARG, "phase index 0 must be DSL phase 0");
+    t->dev.nonterm = 0;
+    for (int i = 0; i < h.n_phases; ++i)
+        if (t->dev.phase[i].kind != KIND_TERMINAL) t->dev.nonterm |= 1u << i;
     t->family = h.family;
     t->P = h.n_players;
     memset(t->init_words, 0, sizeof t->init_words);
@@ -782,6 +839,27 @@ extern "C" int ge_import_state(ge_batch* b, uint64_t first, uint64_t count, cons
     CU(cudaSetDevice(b->device));
     int rc = import_async(b, first, count, host_buf);
     if (rc) return rc;
+    CU(cudaStreamSynchronize(b->stream));
+    return GE_OK;
+}
+
+extern "C" int ge_eval_preds(ge_batch* b, const ge_pred_t* preds, int n_preds, uint64_t first, uint64_t count, uint32_t* host_masks) {
+    if (!b || !preds || !host_masks || n_preds < 1 || n_preds > 32 || first + count > b->n) return fail(GE_ERR_ARG, "bad arguments to ge_eval_preds");
+    if (count == 0) return GE_OK;
+    CU(cudaSetDevice(b->device));
+    const size_t bytes = count * (size_t)n_preds * sizeof(uint32_t);
+    int rc = ensure_stage(b, bytes);
+    if (rc) return rc;
+    PredList pl;
+    memset(&pl, 0, sizeof pl);
+    memcpy(pl.p, preds, (size_t)n_preds * sizeof(ge_pred_t));
+    pl.n = n_preds;
+    k_eval_preds<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, pl, b->d_tiles, (uint32_t)b->tab->rec_dev,
+                                                               b->compacted ? b->d_origin : nullptr, b->n, first, count,
+                                                               reinterpret_cast<uint32_t*>(b->d_stage));
+    CU(cudaGetLastError());
+    b->launches++;
+    CU(cudaMemcpyAsync(host_masks, b->d_stage, bytes, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     return GE_OK;
 }

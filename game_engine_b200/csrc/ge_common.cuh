@@ -34,6 +34,7 @@ struct DevTable {
     // per phase: which column groups a step that starts in this phase must READ besides column 0
     // (bit0 = dynamic masks column, bit1 = role/team column, bit2 = per-player bytes); host-computed.
     uint8_t need[GE_MAX_PHASES];
+    uint32_t nonterm;          // bit i: phase index i is not terminal (host-computed)
 };
 static_assert(sizeof(ge_phase_t) == 48 && sizeof(ge_pred_t) == 8 && sizeof(ge_table_header_t) == 32, "table ABI");
 static_assert(sizeof(DevTable) <= 4000, "table must fit the kernel parameter space");

@@ -41,7 +41,8 @@ __device__ __forceinline__ uint32_t wc_field(const WScalars& s, int f, uint32_t 
     case 0: return s.alive;      case 1: return s.can_vote;  case 2: return s.eligible;
     case 3: return s.submitted;  case 4: return s.revealed;  case 5: return s.investigated;
     case 6: return s.wolf;       case 7: return s.secret;
-    case 8: return ~(s.role_lo | s.role_hi) & ALL;
+    case 8: return s.secret ? ~(s.role_lo | s.role_hi) & ALL : 0u;      // role 0 only once roles are assigned
+    case 12: return s.secret ? ALL : 0u;
     case 9: return s.role_lo & ~s.role_hi;
     case 10: return ~s.role_lo & s.role_hi;
     case 11: return s.role_lo & s.role_hi;

@@ -37,7 +37,8 @@ struct FieldTable {
     __device__ __forceinline__ void fill(const WState<P8>& s, uint32_t ALL) const {
         f[0][tid] = s.alive;      f[1][tid] = s.can_vote;  f[2][tid] = s.eligible;  f[3][tid] = s.submitted;
         f[4][tid] = s.revealed;   f[5][tid] = s.investigated;  f[6][tid] = s.wolf;  f[7][tid] = s.secret;
-        f[8][tid] = ~(s.role_lo | s.role_hi) & ALL;
+        f[8][tid] = s.secret ? ~(s.role_lo | s.role_hi) & ALL : 0u;
+        f[12][tid] = s.secret ? ALL : 0u;
         f[9][tid] = s.role_lo & ~s.role_hi;
         f[10][tid] = ~s.role_lo & s.role_hi;
         f[11][tid] = s.role_lo & s.role_hi;
@@ -110,7 +111,8 @@ __device__ __forceinline__ uint32_t w_field_of(const WState<P8>& s, int f, uint3
     case 0: return s.alive;      case 1: return s.can_vote;  case 2: return s.eligible;
     case 3: return s.submitted;  case 4: return s.revealed;  case 5: return s.investigated;
     case 6: return s.wolf;       case 7: return s.secret;
-    case 8: return ~(s.role_lo | s.role_hi) & ALL;
+    case 8: return s.secret ? ~(s.role_lo | s.role_hi) & ALL : 0u;      // role 0 only once roles are assigned
+    case 12: return s.secret ? ALL : 0u;
     case 9: return s.role_lo & ~s.role_hi;
     case 10: return ~s.role_lo & s.role_hi;
     case 11: return s.role_lo & s.role_hi;
@@ -522,10 +524,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
         // ---- light path: every present phase touches column 0 only.  Four tiles in flight per warp.
         // Sessions move in lockstep, so usually ONE non-terminal phase x0 is present: its single successor is
         // resolved once here and the common lane only rewrites the header word.
-        uint32_t nonterm = 0;
-        for (int i = 0; i < T.h.n_phases; ++i)
-            if (T.phase[i].kind != KIND_TERMINAL) nonterm |= 1u << i;
-        const uint32_t live_present = present_in & nonterm;
+        const uint32_t live_present = present_in & T.nonterm;
         int x0 = -1; uint32_t y0 = 0, tag0 = 0;
         if (__popc(live_present) == 1) {
             const int x = __ffs(live_present) - 1;

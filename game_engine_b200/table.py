@@ -66,6 +66,7 @@ W_FIELDS = {
     "is_alive": 0, "can_vote": 1, "night_action_eligible": 2, "night_action_submitted": 3,
     "role_revealed": 4, "investigated": 5, "team_is_wolf": 6, "has_secret_role": 7,
 }
+W_ROLES_ASSIGNED = 12      # derived: all players once the session has any secret role (roles are assigned), else nobody
 W_ROLE_BASE = 8
 T_FIELDS = {"is_speaker": 0, "statements_submitted": 1, "lie_revealed": 2, "can_vote": 3, "has_voted": 4}
 # per-player value fields usable by ALL_VAL_GE

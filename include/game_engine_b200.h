@@ -137,6 +137,13 @@ int ge_batch_set_host_fused(ge_batch *b, int on);
 int ge_host_alloc(void **p, size_t bytes);
 void ge_host_free(void *p);
 
+/* Audience masks: evaluates n_preds (<= 32) DNF predicates over the mask fields of SPEC.md section 2 for the
+ * sessions [first, first+count); host_masks[i * n_preds + j] = lane mask (bit p-1 = player p) of predicate j in
+ * session first+i.  Replaces the LLM reading declaration.audience_groups[*].selection_criteria
+ * (reference games/werewolf-(mafia).yaml:138-165) when ActionExecutor fills the UI tools' audience_ids
+ * (agent/game_agent_v2.py:1243-1568, src/lib/canvas/types.ts:14-17).  Synchronous. */
+int ge_eval_preds(ge_batch *b, const ge_pred_t *preds, int n_preds, uint64_t first, uint64_t count, uint32_t *host_masks);
+
 /* Statistics (SPEC.md section 6).  ge_stats recomputes the final-state histograms, then copies
  * GE_STATS_LEN words (n must be >= GE_STATS_LEN).  ge_stats_device_ptr returns the device buffer
  * (valid after ge_stats_refresh) for an NCCL / torch.distributed all-reduce.  No reference analogue. */

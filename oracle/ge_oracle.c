@@ -165,7 +165,16 @@ static int field_of(const tab_t *t, const sess_t *s, int f, int p) {
         case 0: return s->alive[p];     case 1: return s->can_vote[p];  case 2: return s->eligible[p];
         case 3: return s->submitted[p]; case 4: return s->revealed[p];  case 5: return s->investigated[p];
         case 6: return s->wolf[p];      case 7: return s->secret[p];
-        case 8: case 9: case 10: case 11: return s->role[p] == f - 8;
+        case 8: case 9: case 10: case 11: {          /* a role only counts once roles are assigned */
+            int assigned = 0;
+            for (int q = 0; q < t->P; ++q) assigned |= s->secret[q];
+            return assigned && s->role[p] == f - 8;
+        }
+        case 12: {
+            int assigned = 0;
+            for (int q = 0; q < t->P; ++q) assigned |= s->secret[q];
+            return assigned;
+        }
         default: return 0;
         }
     }
@@ -468,6 +477,37 @@ int ge_cpu_peek_choices(const uint8_t *blob, size_t nb, const uint8_t *record, u
             choices[p] = n ? (uint8_t)(1 + legal[mulhi32(r, (uint32_t)n)]) : 0;
         } else if (ph[2] == ACT_PICK_OPTION) choices[p] = (uint8_t)(1 + mulhi32(r, ph[3]));
         else if (ph[2] == ACT_MARK) choices[p] = 1;
+    }
+    return 0;
+}
+
+/* audience masks: out[i * n_preds + j] = lane mask of predicate j (8 bytes each: pos0, neg0, pos1, neg1 as u16) */
+int ge_cpu_eval_preds(const uint8_t *blob, size_t nb, const uint8_t *records, uint64_t n_sessions, const uint8_t *preds,
+                      int n_preds, uint32_t *out) {
+    tab_t t;
+    if (tab_open(&t, blob, nb)) return -1;
+    const size_t S = rec_size(&t);
+    for (uint64_t i = 0; i < n_sessions; ++i) {
+        sess_t s;
+        unpack(&t, records + i * S, &s);
+        for (int j = 0; j < n_preds; ++j) {
+            const uint8_t *q = preds + 8 * j;
+            uint32_t m = 0;
+            for (int p = 0; p < t.P; ++p) {
+                int any = 0;
+                for (int c = 0; c < 2; ++c) {
+                    uint16_t pos = rd16(q + 4 * c), neg = rd16(q + 4 * c + 2);
+                    int ok = 1;
+                    for (int f = 0; f < 16; ++f) {
+                        if (((pos >> f) & 1) && !field_of(&t, &s, f, p)) ok = 0;
+                        if (((neg >> f) & 1) && field_of(&t, &s, f, p)) ok = 0;
+                    }
+                    any |= ok;
+                }
+                if (any) m |= 1u << p;
+            }
+            out[i * (uint64_t)n_preds + j] = m;
+        }
     }
     return 0;
 }

@@ -38,6 +38,7 @@ class Oracle:
         L.ge_cpu_stats_final.argtypes = [u8p, sz, u8p, u64, u8p]
         L.ge_cpu_peek_choices.argtypes = [u8p, sz, u8p, u64, u64, u8p]
         L.ge_cpu_philox.argtypes = [u8p, u8p, u8p]
+        L.ge_cpu_eval_preds.argtypes = [u8p, sz, u8p, u64, u8p, ctypes.c_int, u8p]
         self.blob = bytes(blob)
         self._blob_buf = ctypes.create_string_buffer(self.blob, len(self.blob))
         self._bp = ctypes.cast(self._blob_buf, ctypes.c_void_p)
@@ -69,6 +70,12 @@ class Oracle:
         out = np.zeros(self.n_players, dtype=np.uint8)
         r = np.ascontiguousarray(record, dtype=np.uint8)
         self.lib.ge_cpu_peek_choices(self._bp, len(self.blob), r.ctypes.data, sid, seed, out.ctypes.data)
+        return out
+
+    def eval_preds(self, rec: np.ndarray, preds) -> np.ndarray:
+        arr = np.ascontiguousarray(np.array(list(preds), dtype=np.uint16).reshape(-1, 4))
+        out = np.zeros((rec.shape[0], arr.shape[0]), dtype=np.uint32)
+        self.lib.ge_cpu_eval_preds(self._bp, len(self.blob), rec.ctypes.data, rec.shape[0], arr.ctypes.data, arr.shape[0], out.ctypes.data)
         return out
 
     def philox(self, key, ctr):

@@ -33,7 +33,7 @@ def test_werewolf_table_matches_hand_written_expectation(games):
     assert nxt[9] == [99, 99, 10, 14] and [b.tag for b in br] == [1, 2, 0, 0]
     assert br[2].arg == (1 << 8) | (1 << 16) and br[3].arg == 1 << 13
     wolves_alive = (1 << 6 | 1 << 0, 0) + T.CLAUSE_EMPTY
-    villagers_alive = (1 << 0, 1 << 6) + T.CLAUSE_EMPTY
+    villagers_alive = (1 << 0 | 1 << 12, 1 << 6) + T.CLAUSE_EMPTY          # assigned (12), not wolf (6), alive (0)
     assert t.preds[br[0].a] == wolves_alive and t.preds[br[1].a] == wolves_alive and t.preds[br[1].arg] == villagers_alive
     # actor predicates: role == 'Werewolf' and alive; can_vote and alive
     assert t.preds[t.phases[2].actor_pred] == (1 << 9 | 1, 0) + T.CLAUSE_EMPTY
@@ -79,7 +79,8 @@ def test_condition_grammar():
     assert cp("player.is_alive == true") == (1, 0) + T.CLAUSE_EMPTY
     assert cp("player.is_alive == false") == (0, 1) + T.CLAUSE_EMPTY
     assert cp("player.is_alive != true") == (0, 1) + T.CLAUSE_EMPTY
-    assert cp("player.team == 'villagers' and player.is_alive == true") == (1, 1 << 6) + T.CLAUSE_EMPTY
+    assert cp("player.team == 'villagers' and player.is_alive == true") == (1 | 1 << 12, 1 << 6) + T.CLAUSE_EMPTY
+    assert cp("player.team != 'villagers'") == (0, 1 << 12, 1 << 6, 0)        # unassigned, or a wolf
     assert cp("player.role in ['Doctor', 'Detective'] and player.is_alive == true") == (1 << 10 | 1, 0, 1 << 11 | 1, 0)
     assert cp("not (player.is_alive == true or player.can_vote == true)") == (0, 0b11) + T.CLAUSE_EMPTY
     assert cp("(player.role == 'Doctor' or player.role == 'Detective') and player.is_alive") == (1 << 10 | 1, 0, 1 << 11 | 1, 0)

@@ -227,3 +227,21 @@ def test_run_host_async_pipeline(games, oracle_for):
     o.stats_final(rec, ost)
     np.testing.assert_array_equal(rout.reshape(n, S), rec)
     np.testing.assert_array_equal(rst.sum(axis=0), ost)
+
+
+@pytest.mark.parametrize("game,P", [(WEREWOLF, 8), (WEREWOLF, 32)])
+def test_audience_masks_on_gpu(games, oracle_for, game, P):
+    cg = games(game, P)
+    o = oracle_for(cg)
+    n, seed = 3000, 4
+    _, b = _batch(cg, n, 0, seed, "tps")
+    b.set_compaction(2, 4)                    # masks must be reported in original session order after compaction too
+    rec = o.init(n)
+    for steps in (3, 9, 14, 20):
+        b.step(steps)
+        o.step(rec, 0, seed, steps)
+        want = o.eval_preds(rec, list(cg.audience_preds.values()))
+        got = b.eval_preds(list(cg.audience_preds.values()))
+        np.testing.assert_array_equal(got, want)
+        am = b.audience_masks(100, 50)
+        np.testing.assert_array_equal(am["werewolves"], want[100:150, list(cg.audience_preds).index("werewolves")])

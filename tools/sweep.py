@@ -24,6 +24,7 @@ def run(game, P, n, kernel, cap, ring, stream):
         b.set_stream(stream.cuda_stream)
         b.step(3)
         b.reset()
+        b.clear_stats()
     torch.cuda.synchronize()
     c0 = sum(b.counted_steps() for b in bs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
