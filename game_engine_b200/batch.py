@@ -78,6 +78,11 @@ class SessionBatch:
         (0 steps = off; default (8, 2))."""
         capi.check(capi.lib().ge_batch_set_compaction(self._h, int(every_n_steps), int(min_dead_shift)))
 
+    def set_regroup(self, every_n_steps: int, min_mixed_shift: int = 3) -> None:
+        """Phase regrouping: check every n steps, counting-sort the active prefix by phase when >= 1/2^shift of
+        the tiles are mixed (0 steps = off; on by default for tables with a tie -> re-vote loop)."""
+        capi.check(capi.lib().ge_batch_set_regroup(self._h, int(every_n_steps), int(min_mixed_shift)))
+
     def active(self) -> int:
         """Length of the slot prefix that can still hold live sessions (synchronises)."""
         v = ctypes.c_uint64()

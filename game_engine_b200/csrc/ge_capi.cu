@@ -65,6 +65,11 @@ struct ge_batch {
     unsigned long long* h_hint;   // pinned {n_active, epoch}: refreshed by an async copy after every compaction
     unsigned long long epoch;     // bumped by every (re)initialisation; stale hints are ignored
     bool compacted;               // origin may differ from identity
+    // phase regrouping (see k_regroup_*): counting sort of the active prefix by phase, through a scratch store
+    uint32_t* d_rg;               // RG_WORDS control words (histogram, trigger, bases, cursors)
+    uint8_t* d_rg_tiles;          // scratch session store (same size as d_tiles)
+    uint32_t* d_rg_origin;
+    int regroup_every, rg_mixed_shift;
     uint32_t* d_presence;         // 3 rotating phase-presence words (StepArgs::presence)
     uint32_t launch_idx;          // index of the next step launch
     uint32_t next_override;       // presence override for the next launch (0 = read the device word)
@@ -75,6 +80,7 @@ struct ge_batch {
 };
 
 static int restore_order(ge_batch* b);
+extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixed_shift);
 static int ensure_stage(ge_batch* b, size_t bytes);
 
 // ------------------------------------------------------------------------------------ glue kernels
@@ -303,6 +309,109 @@ __global__ void k_export_perm(const uint8_t* tiles, uint32_t S_dev, uint32_t S_c
         const uint32_t sl = (uint32_t)(slot & 31);
         for (uint32_t k = 0; k < S_canon / 8; ++k)
             *reinterpret_cast<uint2*>(out + (o - first) * S_canon + 8 * k) = *reinterpret_cast<const uint2*>(base + rt_tile_off(8 * k, sl, n16));
+    }
+}
+
+// ------------------------------------------------------------------------------------ phase regrouping
+// Sessions of one batch normally advance in lockstep, so a warp's 32 sessions are in the same phase and the
+// warp-uniform phase switch of the step kernel costs one body.  Tables with loops of data-dependent length
+// (the tie -> re-vote loop of werewolf-revote) de-synchronise them: every warp then runs every phase body
+// present in its tile, i.e. each launch pays for the most expensive phase.  Regrouping is a counting sort of
+// the active prefix by phase index (terminal sessions last, which also makes it a compaction): afterwards at
+// most one tile per phase is mixed.  It is decided and done on the device (no host synchronisation):
+//   step kernel (counted launch): rg[0..31] += sessions that entered phase i, rg[32] += mixed tiles
+//   k_regroup_plan: trigger when >= 1/2^mixed_shift of the tiles are mixed or >= 1/2^dead_shift of the prefix
+//                   is dead; exclusive scan of the live phases' counts -> first slot of every phase
+//   k_regroup_scatter: blocks of 1024 slots; ranks inside a block from warp match + shared counters, the
+//                   block's range inside each phase from one global atomic per phase; record -> scratch
+//   k_regroup_copyback: scratch -> session store (the prefix only)
+// Slot order inside a phase is not deterministic, and does not have to be: session ids come from the origin
+// map, exports are in original order and the statistics are sums.
+enum { RG_HIST = 0, RG_MIXED = 32, RG_OLD = 33, RG_BASE = 64, RG_CURSOR = 100, RG_WORDS = 160, RG_TERM = 32 };
+
+__global__ void k_regroup_plan(unsigned long long* cstate, uint32_t* rg, uint32_t nonterm, uint32_t mixed_shift, uint32_t dead_shift) {
+    const int lane = threadIdx.x;                      // one warp
+    const uint64_t n_act = cstate[0];
+    const uint32_t cnt = ((nonterm >> lane) & 1u) ? rg[RG_HIST + lane] : 0u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += u; }
+    const uint64_t n_live = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint64_t mixed = rg[RG_MIXED];
+    const uint64_t tiles = (n_act + 31) >> 5;
+    const bool trig = n_act > 0 && n_live <= n_act &&
+                      (((mixed << mixed_shift) >= tiles && mixed > 0) || (((n_act - n_live) << dead_shift) >= n_act && n_live < n_act));
+    __syncwarp();
+    rg[RG_BASE + lane] = incl - cnt;
+    rg[RG_CURSOR + lane] = 0;
+    rg[RG_HIST + lane] = 0;
+    if (lane == 0) {
+        rg[RG_BASE + RG_TERM] = (uint32_t)n_live;
+        rg[RG_CURSOR + RG_TERM] = 0;
+        rg[RG_MIXED] = 0;
+        rg[RG_OLD] = trig ? (uint32_t)n_act : 0u;
+        if (trig) cstate[0] = n_live;
+        cstate[5] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_regroup_scatter(const uint8_t* __restrict__ tiles, uint32_t S, const uint32_t* __restrict__ origin, uint32_t* rg, uint32_t nonterm,
+                  uint8_t* __restrict__ out_tiles, uint32_t* __restrict__ out_origin) {
+    __shared__ uint32_t s_cnt[RG_TERM + 1], s_base[RG_TERM + 1];
+    const uint32_t old = rg[RG_OLD];
+    if (old == 0) return;
+    const uint32_t n16 = S / 16;
+    const bool half = (S % 16) != 0;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t c0 = blockIdx.x * 1024u; c0 < old; c0 += gridDim.x * 1024u) {
+        if (threadIdx.x <= RG_TERM) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t slot = c0 + threadIdx.x;
+        const bool valid = slot < old;
+        const uint8_t* src = tiles + (uint64_t)(slot >> 5) * (32ull * S);
+        int key = -1;
+        if (valid) {
+            const uint32_t ph = *reinterpret_cast<const uint32_t*>(src + (slot & 31) * 16u) & 31u;
+            key = ((nonterm >> ph) & 1u) ? (int)ph : RG_TERM;
+        }
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, key);
+        const int leader = __ffs(same) - 1;
+        uint32_t wbase = 0;
+        if (valid && lane == leader) wbase = atomicAdd(&s_cnt[key], (uint32_t)__popc(same));
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, leader);
+        const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+        __syncthreads();
+        if (threadIdx.x <= RG_TERM) {
+            const uint32_t n = s_cnt[threadIdx.x];
+            s_base[threadIdx.x] = n ? rg[RG_BASE + threadIdx.x] + atomicAdd(&rg[RG_CURSOR + threadIdx.x], n) : 0u;
+        }
+        __syncthreads();
+        if (valid) {
+            const uint32_t dst = s_base[key] + wbase + rank;
+            uint8_t* db = out_tiles + (uint64_t)(dst >> 5) * (32ull * S);
+            for (uint32_t c = 0; c < n16; ++c)
+                *reinterpret_cast<uint4*>(db + c * 512u + (dst & 31) * 16u) = *reinterpret_cast<const uint4*>(src + c * 512u + (slot & 31) * 16u);
+            if (half)
+                *reinterpret_cast<uint2*>(db + n16 * 512u + (dst & 31) * 8u) = *reinterpret_cast<const uint2*>(src + n16 * 512u + (slot & 31) * 8u);
+            out_origin[dst] = origin[slot];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_regroup_copyback(uint8_t* __restrict__ tiles, uint32_t S, uint32_t* __restrict__ origin, const uint32_t* __restrict__ rg,
+                                   const uint8_t* __restrict__ in_tiles, const uint32_t* __restrict__ in_origin) {
+    const uint32_t old = rg[RG_OLD];
+    const uint32_t n16 = S / 16;
+    const bool half = (S % 16) != 0;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < old; slot += gridDim.x * blockDim.x) {
+        const uint64_t off = (uint64_t)(slot >> 5) * (32ull * S);
+        for (uint32_t c = 0; c < n16; ++c)
+            *reinterpret_cast<uint4*>(tiles + off + c * 512u + (slot & 31) * 16u) = *reinterpret_cast<const uint4*>(in_tiles + off + c * 512u + (slot & 31) * 16u);
+        if (half)
+            *reinterpret_cast<uint2*>(tiles + off + n16 * 512u + (slot & 31) * 8u) = *reinterpret_cast<const uint2*>(in_tiles + off + n16 * 512u + (slot & 31) * 8u);
+        origin[slot] = in_origin[slot];
     }
 }
 
@@ -609,6 +718,12 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     b->kernel = GE_KERNEL_TPS;
     int rc = ge_batch_clear_stats(b);
     if (rc == GE_OK) rc = init_sessions(b, first_session_id, seed);
+    // tables with a tie -> re-vote loop de-synchronise their sessions: regroup them by phase (k_regroup_*)
+    bool desync = false;
+    for (int i = 0; i < t->dev.h.n_phases; ++i)
+        for (int k = 0; k < t->dev.phase[i].n_branches; ++k)
+            if (t->dev.phase[i].br[k].op == BR_TIE_PENDING) desync = true;
+    if (rc == GE_OK && desync && t->family == FAM_WEREWOLF && b->n <= (1ull << 31)) rc = ge_batch_set_regroup(b, 8, 3);
     if (rc != GE_OK) { ge_batch_destroy(b); return rc; }
     *out = b;
     return GE_OK;
@@ -621,6 +736,7 @@ extern "C" void ge_batch_destroy(ge_batch* b) {
     if (b->own_stream) { cudaStreamSynchronize(b->own_stream); cudaStreamDestroy(b->own_stream); }
     cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_stage); cudaFree(b->d_presence);
     cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
+    cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin);
     delete b;
 }
 
@@ -650,6 +766,29 @@ extern "C" int ge_batch_set_compaction(ge_batch* b, int every_n_steps, int min_d
     if (every_n_steps > 0 && b->scan_blocks > 1024) return fail(GE_ERR_UNSUPPORTED, "compaction supports batches up to 2^25 sessions");
     b->compact_every = every_n_steps;
     b->dead_shift = min_dead_shift;
+    return GE_OK;
+}
+
+extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixed_shift) {
+    if (!b || every_n_steps < 0 || min_mixed_shift < 0 || min_mixed_shift > 16) return fail(GE_ERR_ARG, "bad arguments to ge_batch_set_regroup");
+    if (every_n_steps == 0) { b->regroup_every = 0; return GE_OK; }
+    if (b->tab->family != FAM_WEREWOLF) return fail(GE_ERR_UNSUPPORTED, "phase regrouping covers the werewolf family (TTL sessions never de-synchronise)");
+    if (b->n > (1ull << 31)) return fail(GE_ERR_UNSUPPORTED, "phase regrouping supports batches up to 2^31 sessions");
+    CU(cudaSetDevice(b->device));
+    if (!b->d_rg) {
+        cudaError_t e = cudaMalloc(&b->d_rg, RG_WORDS * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(b->d_rg, 0, RG_WORDS * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_rg_tiles, b->tiles_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_rg_origin, b->n_tiles * 32 * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin);
+            b->d_rg = nullptr; b->d_rg_tiles = nullptr; b->d_rg_origin = nullptr;
+            return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_set_regroup: ") + cudaGetErrorString(e));
+        }
+    }
+    b->regroup_every = every_n_steps;
+    b->rg_mixed_shift = min_mixed_shift;
+    b->since_compact = 0;
     return GE_OK;
 }
 
@@ -698,15 +837,40 @@ static int enqueue_compaction(ge_batch* b, cudaStream_t st) {
     return GE_OK;
 }
 
+// plan -> scatter -> copy back on the histogram of the counted step that just ran (all asynchronous, no host sync)
+static int enqueue_regroup(ge_batch* b, cudaStream_t st) {
+    const uint32_t S = (uint32_t)b->tab->rec_dev;
+    k_regroup_plan<<<1, 32, 0, st>>>(b->d_cstate, b->d_rg, b->tab->dev.nonterm, (uint32_t)b->rg_mixed_shift, (uint32_t)b->dead_shift);
+    uint64_t g = (b->n + 1023) / 1024;
+    if (g > (uint64_t)b->sm_count * 2) g = (uint64_t)b->sm_count * 2;
+    k_regroup_scatter<<<(int)g, 1024, 0, st>>>(b->d_tiles, S, b->d_origin, b->d_rg, b->tab->dev.nonterm, b->d_rg_tiles, b->d_rg_origin);
+    k_regroup_copyback<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->d_tiles, S, b->d_origin, b->d_rg, b->d_rg_tiles, b->d_rg_origin);
+    CU(cudaGetLastError());
+    b->launches += 3;
+    b->since_compact = 0;
+    CU(cudaMemcpyAsync(&b->h_hint[0], b->d_cstate, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&b->h_hint[1], b->d_cstate + 7, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    return GE_OK;
+}
+
 static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaStream_t st) {
     const step_fn fn = b->fn[b->kernel];
     StepArgs a;
     a.tiles = b->d_tiles; a.n_sessions = b->n; a.n_tiles = b->n_tiles; a.first_sid = b->first_sid; a.seed = b->seed;
     a.stats = b->d_stats; a.presence = b->d_presence; a.n_steps = steps_per_launch;
     a.n_active = b->d_cstate; a.live_mask = b->d_live_mask; a.live_count = b->d_cstate + 5;
+    // phase regrouping replaces the swap compaction (it also moves finished games behind the live ones)
+    const bool regroup = b->regroup_every > 0 && b->kernel != GE_KERNEL_COOP && steps_per_launch == 1;
+    a.rg = regroup ? b->d_rg : nullptr;
     for (int i = 0; i < n_launches; ++i) {
-        const bool compact_after = b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
-        a.count_live = compact_after ? 1u : 0u;
+        if (regroup && !b->compacted) {              // the origin map must exist before the first regrouping
+            k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
+            b->compacted = true;
+            b->launches++;
+        }
+        const bool regroup_after = regroup && b->since_compact + 1 >= b->regroup_every;
+        const bool compact_after = !regroup && b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
+        a.count_live = (compact_after || regroup_after) ? 1u : 0u;
         a.launch_idx = b->launch_idx++;
         a.presence_override = b->next_override;
         b->next_override = 0;
@@ -714,7 +878,10 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
         fn<<<b->grid[b->kernel], 128, 0, st>>>(b->tab->dev, a);
         b->launches++;
         b->since_compact++;
-        if (compact_after) {
+        if (regroup_after) {
+            const int rc = enqueue_regroup(b, st);
+            if (rc != GE_OK) return rc;
+        } else if (compact_after) {
             const int rc = enqueue_compaction(b, st);
             if (rc != GE_OK) return rc;
         }

@@ -59,6 +59,10 @@ struct StepArgs {
     uint32_t* live_mask;
     unsigned long long* live_count;   // when count_live != 0 the launch adds its number of live sessions here
     uint32_t count_live;
+    // Phase regrouping (ge_capi.cu, k_regroup_*): on a counted launch (count_live != 0) the werewolf
+    // thread-per-session kernel also adds, per phase index, the sessions that entered it to rg[0..31] and the
+    // number of tiles whose live sessions sit in more than one phase to rg[32].  NULL = not collected.
+    uint32_t* rg;
 };
 
 __device__ __forceinline__ void publish_presence(const StepArgs& A, uint32_t block_present) {
@@ -118,15 +122,19 @@ __device__ __forceinline__ void st64(uint8_t* p, const uint2& v) { *reinterpret_
 struct VisitAcc {
     int phase = -1;
     uint32_t count = 0;
-    __device__ __forceinline__ void add(uint32_t* s_visits, int np, int lane) {
+    // returns the number of distinct phases entered by the tile's sessions
+    __device__ __forceinline__ int add(uint32_t* s_visits, int np, int lane) {
         uint32_t todo = __ballot_sync(0xFFFFFFFFu, np >= 0);
+        int distinct = 0;
         while (todo) {                                   // one iteration per distinct phase in the tile (usually 1)
             const int v = __shfl_sync(0xFFFFFFFFu, np, __ffs(todo) - 1);
             const uint32_t same = __ballot_sync(0xFFFFFFFFu, np == v);
             if (v != phase) { flush(s_visits, lane); phase = v; }
             count += __popc(same);
             todo &= ~same;
+            ++distinct;
         }
+        return distinct;
     }
     __device__ __forceinline__ void flush(uint32_t* s_visits, int lane) {
         if (lane == 0 && count) atomicAdd(&s_visits[phase], count);

@@ -501,10 +501,10 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     constexpr int NT16 = P8 / 16;          // full 16-byte target columns
     constexpr bool THALF = (P8 % 16) != 0; // trailing 8-byte column
     __shared__ uint32_t s_visits[32];
-    __shared__ uint32_t s_present, s_live;
+    __shared__ uint32_t s_present, s_live, s_mixed;
     __shared__ uint32_t s_fields[16][TPS_THREADS];
     if (threadIdx.x < 32) s_visits[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_present = 0; s_live = 0; }
+    if (threadIdx.x == 0) { s_present = 0; s_live = 0; s_mixed = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -517,7 +517,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const uint32_t n_tiles_act = (uint32_t)((n_act + 31) >> 5);
     const bool use_origin = A.origin != nullptr && (need & 8);
     const FieldTable F{s_fields, (int)threadIdx.x};
-    uint32_t present_out = 0, live_cnt = 0;
+    uint32_t present_out = 0, live_cnt = 0, mixed = 0;
     VisitAcc visits;
 
     if (need == 0) {
@@ -564,7 +564,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
                         lm = y0_live ? stepped : 0u;
                         if (stepped != 0xFFFFFFFFu && in_range && np < 0) present_out |= 1u << (c[j].x & 31);
                     } else {
-                        visits.add(s_visits, np, lane);
+                        mixed += visits.add(s_visits, np, lane) > 1;
                         if (in_range) present_out |= 1u << (c[j].x & 31);
                         lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[c[j].x & 31].kind != KIND_TERMINAL);
                     }
@@ -612,7 +612,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
                         np = w_step_spec<P8, Spec>(s, F, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
                     if (np < 0) live = false;
                 }
-                visits.add(s_visits, np, lane);
+                mixed += visits.add(s_visits, np, lane) > 1;
             }
             if (in_range) present_out |= 1u << (s.h0 & 31);
             const uint32_t lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[s.h0 & 31].kind != KIND_TERMINAL);
@@ -634,11 +634,16 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     if (lane == 0) {
         if (present_out) atomicOr(&s_present, present_out);
         if (live_cnt) atomicAdd(&s_live, live_cnt);
+        if (mixed) atomicAdd(&s_mixed, mixed);
     }
     __syncthreads();
     flush_visits(s_visits, A.stats);
     publish_presence(A, s_present);
     if (A.count_live && threadIdx.x == 0 && s_live) atomicAdd(A.live_count, (unsigned long long)s_live);
+    if (A.count_live && A.rg != nullptr) {             // inputs of the phase regrouping check (k_regroup_plan)
+        if (threadIdx.x < 32 && s_visits[threadIdx.x]) atomicAdd(&A.rg[threadIdx.x], s_visits[threadIdx.x]);
+        if (threadIdx.x == 0 && s_mixed) atomicAdd(&A.rg[32], s_mixed);
+    }
 }
 
 // =================================================================================== TTL family

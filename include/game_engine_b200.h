@@ -97,6 +97,14 @@ int ge_batch_set_kernel(ge_batch *b, int kernel);
  * ge_batch_active returns the current prefix length (synchronises). */
 int ge_batch_set_compaction(ge_batch *b, int every_n_steps, int min_dead_shift);
 int ge_batch_active(ge_batch *b, uint64_t *out);
+/* Phase regrouping (thread-per-session werewolf kernels): every `every_n_steps` launches a device-side check runs
+ * and, when at least 1/2^min_mixed_shift of the tiles hold sessions in more than one phase (or the compaction
+ * threshold of dead sessions is reached), the active prefix is counting-sorted by phase, finished games last, so
+ * that a warp's 32 sessions share a phase again.  Needed by tables whose sessions de-synchronise (loops of
+ * data-dependent length such as tie -> re-vote); it replaces the swap compaction while on and is enabled
+ * automatically (8, 3) for tables that use the TIE_PENDING branch.  Costs a second session store.  Results,
+ * session ids, export order and statistics are unaffected.  every_n_steps = 0 turns it off. */
+int ge_batch_set_regroup(ge_batch *b, int every_n_steps, int min_mixed_shift);
 /* Non-blocking variant: the value an asynchronous copy brought to the host after the most recent completed
  * compaction of the current epoch (an upper bound that only decreases; n_sessions until the first one).
  * 0 means every game of the batch is over — the cue to re-initialise it without waiting for a step cap. */

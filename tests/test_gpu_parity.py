@@ -245,3 +245,57 @@ def test_audience_masks_on_gpu(games, oracle_for, game, P):
         np.testing.assert_array_equal(got, want)
         am = b.audience_masks(100, 50)
         np.testing.assert_array_equal(am["werewolves"], want[100:150, list(cg.audience_preds).index("werewolves")])
+
+
+@pytest.mark.parametrize("game,P,n", [(REVOTE, 32, 6000), (REVOTE, 8, 5000), (WEREWOLF, 16, 5000)])
+def test_phase_regrouping_is_invisible(games, oracle_for, game, P, n):
+    """Phase regrouping counting-sorts the slots by phase on the device (and compacts finished games); exports,
+    statistics, session ids and audience masks must not notice, whatever the cadence and threshold."""
+    cg = games(game, P)
+    o = oracle_for(cg)
+    first, seed = (1 << 35) + 5, 2027
+    _, every = _batch(cg, n, first, seed, "tps")
+    _, lazy = _batch(cg, n, first, seed, "tps_generic")
+    _, off = _batch(cg, n, first, seed, "tps")
+    every.set_regroup(1, 16)         # check every step, regroup as soon as one tile is mixed
+    lazy.set_regroup(3, 2)           # check every 3 steps, regroup when >= 1/4 of the tiles are mixed
+    off.set_regroup(0)
+    rec = o.init(n)
+    ost = o.new_stats()
+    term = len(cg.phase_ids) - 1
+    steps = 9 * P - 16 + (2 * cg.table.max_revotes * (P - 2)) + 4
+    prev_active = n
+    for k in range(steps):
+        for b in (every, lazy, off):
+            b.step(1)
+        o.step(rec, first, seed, 1, ost)
+        assert np.array_equal(every.export_state(), rec), "step %d (regroup every step)" % k
+        if k % 7 == 0 or k > steps - 6:
+            assert np.array_equal(lazy.export_state(), rec), "step %d (regroup every 3)" % k
+            assert np.array_equal(off.export_state(), rec), "step %d (no regroup)" % k
+        act = every.active()
+        live = int((rec[:, 0] != term).sum())
+        assert live <= act <= prev_active, (k, live, act, prev_active)
+        prev_active = act
+        if k == steps // 3:
+            want = o.eval_preds(rec, list(cg.audience_preds.values()))
+            np.testing.assert_array_equal(every.eval_preds(list(cg.audience_preds.values())), want)
+    assert every.active() == 0
+    o.stats_final(rec, ost)
+    for b in (every, lazy, off):
+        np.testing.assert_array_equal(b.stats(), ost)
+    np.testing.assert_array_equal(every.export_state(1000, 777), rec[1000:1777])
+    # a regrouped batch can be re-initialised, imported into, and switched to the lane-per-player kernel
+    every.reset(first_session_id=first + n)
+    rec2 = o.init(n)
+    every.step(21)
+    o.step(rec2, first + n, seed, 21)
+    np.testing.assert_array_equal(every.export_state(), rec2)
+    every.set_kernel("coop")
+    every.step(9)
+    o.step(rec2, first + n, seed, 9)
+    np.testing.assert_array_equal(every.export_state(), rec2)
+    every.set_kernel("tps")
+    every.step(30)
+    o.step(rec2, first + n, seed, 30)
+    np.testing.assert_array_equal(every.export_state(), rec2)
