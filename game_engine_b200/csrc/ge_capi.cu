@@ -522,8 +522,19 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     for (int i = 0; i < h.n_phases; ++i) {
         const ge_phase_t& ph = t->dev.phase[i];
         uint8_t need = 0;
-        if (h.family != FAM_WEREWOLF) { t->dev.need[i] = 15; continue; }
         if (ph.kind == KIND_TERMINAL) { t->dev.need[i] = 0; continue; }
+        if (h.family != FAM_WEREWOLF) {
+            // TTL: bit2 = the player words (everything but column 0's header), bit3 = session id.  Header-only
+            // phases: no actors, no predicate / value test in the branches, no entry effect on the way out.
+            if (ph.kind == KIND_ACTION) need |= 4 | (ph.action_op == ACT_PICK_OPTION ? 8 : 0);
+            for (int b = 0; b < ph.n_branches; ++b) {
+                const ge_branch_t& br = ph.br[b];
+                if (br.op == BR_COUNT_EQ0 || br.op == BR_COUNT_GE || br.op == BR_ALL_VAL_GE) need |= 4;
+                if (t->dev.phase[br.next].entry_op != EN_NONE) need |= 4;
+            }
+            t->dev.need[i] = need;
+            continue;
+        }
         if (ph.kind == KIND_ACTION) {
             need |= 8;                                        // bots draw from the session's Philox stream (needs its id)
             need |= pred_need(ph.actor_pred);
@@ -571,7 +582,10 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
 
 // build-time specialised kernels (ge_spec_gen.cuh), matched by byte-identical table blobs
 struct SpecEntry { const unsigned char* blob; size_t len; step_fn fn; };
-#define GE_SPEC_ENTRY(S, FAM, BUCKET) {spec::S##_blob, sizeof(spec::S##_blob), (step_fn)k_step_w_tps<BUCKET, spec::S>},
+template <int FAM, int BUCKET, class S> struct SpecKernel;
+template <int BUCKET, class S> struct SpecKernel<FAM_WEREWOLF, BUCKET, S> { static step_fn fn() { return (step_fn)k_step_w_tps<BUCKET, S>; } };
+template <int BUCKET, class S> struct SpecKernel<FAM_TTL, BUCKET, S> { static step_fn fn() { return (step_fn)k_step_t_tps<BUCKET, S>; } };
+#define GE_SPEC_ENTRY(S, FAM, BUCKET) {spec::S##_blob, sizeof(spec::S##_blob), SpecKernel<FAM, BUCKET, spec::S>::fn()},
 static const SpecEntry g_specs[] = { GE_SPEC_LIST(GE_SPEC_ENTRY) {nullptr, 0, nullptr} };
 
 extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {

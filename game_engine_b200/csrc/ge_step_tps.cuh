@@ -138,6 +138,8 @@ struct RtView {
     __device__ __forceinline__ int n_players() const { return T.h.n_players; }
     __device__ __forceinline__ int n_wolves() const { return T.h.n_wolves; }
     __device__ __forceinline__ int max_revotes() const { return T.h.max_revotes; }
+    __device__ __forceinline__ int rounds() const { return T.h.rounds; }
+    __device__ __forceinline__ ge_pred_t pred_rec(int pi) const { return T.pred[pi]; }
     __device__ __forceinline__ bool wants_fields() const { return ph.kind == KIND_ACTION || ph.n_branches > 1; }
     template <int P8>
     __device__ __forceinline__ uint32_t pred(const FieldTable& F, const WState<P8>&, int pi, uint32_t ALL) const { return F.pred(T, pi, ALL); }
@@ -164,6 +166,8 @@ struct CtView {
     __device__ __forceinline__ static constexpr int n_players() { return Spec::n_players; }
     __device__ __forceinline__ static constexpr int n_wolves() { return Spec::n_wolves; }
     __device__ __forceinline__ static constexpr int max_revotes() { return Spec::max_revotes; }
+    __device__ __forceinline__ static constexpr int rounds() { return Spec::rounds; }
+    __device__ __forceinline__ static constexpr ge_pred_t pred_rec(int pi) { return Spec::pred(pi); }
     __device__ __forceinline__ static constexpr bool wants_fields() { return false; }       // predicates fold to register ops
     template <int P8>
     __device__ __forceinline__ static uint32_t pred(const FieldTable&, const WState<P8>& s, int pi, uint32_t ALL) {
@@ -656,107 +660,152 @@ struct TState {
 
 enum { TF_SPEAKER = 1, TF_STMTS = 2, TF_REVEALED = 4, TF_CANVOTE = 8, TF_VOTED = 16 };
 
+// The per-player flag bytes of four players gathered in one word (byte j = player 4i+j).  A mask field is
+// then one shift + AND away ("byte-sliced"), and converting it to / from a lane mask (bit p = player p) is one
+// multiply: gather  ((w >> f) & 0x01010101) * 0x01020408 >> 24,  spread  (m * 0x00204081) & 0x01010101.
 template <int PB>
-__device__ __forceinline__ int t_step(const DevTable& T, TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi,
-                                      uint32_t k0, uint32_t k1, uint32_t& dirty) {
-    const int P = T.h.n_players;
+struct TFlags {
+    static constexpr int NW = PB / 4;
+    uint32_t w[NW];
+    __device__ __forceinline__ void load(const uint32_t (&pw)[PB]) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i)
+            w[i] = __byte_perm(__byte_perm(pw[4 * i], pw[4 * i + 1], 0x0073), __byte_perm(pw[4 * i + 2], pw[4 * i + 3], 0x0073), 0x5410);
+    }
+    __device__ __forceinline__ void store(uint32_t (&pw)[PB]) const {
+#pragma unroll
+        for (int p = 0; p < PB; ++p) pw[p] = __byte_perm(pw[p], w[p >> 2], ((4u + (p & 3)) << 12) | 0x210u);
+    }
+    __device__ __forceinline__ uint32_t get(int f) const {
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) m |= ((((w[i] >> f) & 0x01010101u) * 0x01020408u) >> 24) << (4 * i);
+        return m;
+    }
+    __device__ __forceinline__ void set(int f, uint32_t m) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i)
+            w[i] = (w[i] & ~(0x01010101u << f)) | (((((m >> (4 * i)) & 0xFu) * 0x00204081u) & 0x01010101u) << f);
+    }
+};
+
+template <class V, class FieldFn>
+__device__ __forceinline__ uint32_t t_pred(const V& v, FieldFn field, int pi, uint32_t ALL) {
+    const ge_pred_t pr = v.pred_rec(pi);
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
+        if (neg & 0x8000u) continue;                       // "& ~ALL": unused clause
+        uint32_t m = ALL;
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+            if ((pos >> f) & 1u) m &= field(f);
+            if ((neg >> f) & 1u) m &= ~field(f);
+        }
+        out |= m;
+    }
+    return out;
+}
+
+// One step of one TTL session in phase X (not terminal, step0 != 0), against a table view (RtView: the run-time
+// table; CtView<Spec, X>: a build-time table, every accessor a constant).  Returns the phase entered.
+template <int PB, class V>
+__device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi,
+                                           uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    const int P = v.n_players();
     const uint32_t ALL = all_mask(P);
-    const int X = s.h0 & 0xFF;
     const uint32_t step0 = s.h0 >> 16;
-    const ge_phase_t& ph = T.phase[X];
-    if (ph.kind == KIND_TERMINAL) return -1;
-    dirty |= DIRTY_C0;
-    if (step0 == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
-
     uint32_t speaker = s.h1 & 0xFF, lie = (s.h1 >> 8) & 0xFF, winner = (s.h1 >> 16) & 0xFF;
-    // lane masks from the per-player flag bytes
-    uint32_t m[5] = {0, 0, 0, 0, 0};
-#pragma unroll
-    for (int p = 0; p < PB; ++p) {
-        const uint32_t fl = s.pw[p] >> 24;
-#pragma unroll
-        for (int f = 0; f < 5; ++f) m[f] |= ((fl >> f) & 1u) << p;
-    }
-    auto field = [&](int f) -> uint32_t { return f == 15 ? ALL : f < 5 ? (f == 0 ? m[0] : f == 1 ? m[1] : f == 2 ? m[2] : f == 3 ? m[3] : m[4]) : 0u; };
-    auto pred = [&](int pi) -> uint32_t {
-        const ge_pred_t pr = T.pred[pi];
-        uint32_t out = 0;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0, mm = ALL;
-            while (pos) { const int f = __ffs(pos) - 1; pos &= pos - 1; mm &= field(f); }
-            while (neg) { const int f = __ffs(neg) - 1; neg &= neg - 1; mm &= ~field(f); }
-            out |= mm;
-        }
-        return out;
-    };
+    TFlags<PB> F;
+    F.load(s.pw);
+    bool flags_dirty = false;
+    auto field = [&](int f) -> uint32_t { return F.get(f); };
 
-    int taken = ph.n_branches - 1;
-    for (int b = 0; b < ph.n_branches; ++b) {
-        const ge_branch_t br = ph.br[b];
-        bool ok;
-        switch (br.op) {
-        case BR_ALWAYS: ok = true; break;
-        case BR_COUNT_EQ0: ok = pred(br.a) == 0; break;
-        case BR_COUNT_GE: ok = __popc(pred(br.a)) >= __popc(pred((int)br.arg)); break;
-        case BR_PREV_IN: ok = (br.arg >> ((s.h0 >> 8) & 0xFF)) & 1u; break;
-        case BR_ALL_VAL_GE: {
-            ok = true;
+    const int nb = v.n_branches();
+    int taken = nb - 1;
+    if (nb > 1) {
+        bool done = false;
+#pragma unroll(V::is_const ? 4 : 1)
+        for (int b = 0; b < 4; ++b) {
+            if (b < nb && !done) {
+                const ge_branch_t br = v.branch(b);
+                bool ok;
+                switch (br.op) {
+                case BR_ALWAYS: ok = true; break;
+                case BR_COUNT_EQ0: ok = t_pred(v, field, br.a, ALL) == 0; break;
+                case BR_COUNT_GE: ok = __popc(t_pred(v, field, br.a, ALL)) >= __popc(t_pred(v, field, (int)br.arg, ALL)); break;
+                case BR_PREV_IN: ok = (br.arg >> ((s.h0 >> 8) & 0xFF)) & 1u; break;
+                case BR_ALL_VAL_GE: {
+                    ok = true;
 #pragma unroll
-            for (int p = 0; p < PB; ++p)
-                if (p < P && ((s.pw[p] >> (8 * br.a)) & 0xFFu) < br.arg) ok = false;
-        } break;
-        default: ok = false; break;
+                    for (int p = 0; p < PB; ++p)
+                        if (p < P && ((s.pw[p] >> (8 * br.a)) & 0xFFu) < br.arg) ok = false;
+                } break;
+                default: ok = false; break;
+                }
+                if (ok) { taken = b; done = true; }
+            }
         }
-        if (ok) { taken = b; break; }
     }
-    const int Y = ph.br[taken].next;
-    const uint32_t tag = ph.br[taken].tag;
+    int Y = 0; uint32_t tag = 0;
+    if constexpr (V::is_const) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (b < nb && b == taken) { Y = v.branch(b).next; tag = v.branch(b).tag; }
+    } else {
+        Y = v.branch(taken).next; tag = v.branch(taken).tag;
+    }
 
-    if (ph.kind == KIND_ACTION) {
-        const uint32_t actors = pred(ph.actor_pred);
+    if (v.kind() == KIND_ACTION) {
+        const uint32_t actors = t_pred(v, field, v.actor_pred(), ALL);
+        const int aop = v.action_op(), exo = v.exit_op();
         uint32_t first_choice = 0; bool have_first = false;
 #pragma unroll
-        for (int b = 0; b < (PB + 3) / 4; ++b) {
+        for (int b = 0; b < PB / 4; ++b) {
             const uint32_t ab = (actors >> (4 * b)) & 0xFu;
             if (ab) {
-                const uint4 r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, k0, k1);
+                uint4 r4 = make_uint4(0, 0, 0, 0);
+                if (aop == ACT_PICK_OPTION) r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, k0, k1);     // MARK draws nothing
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int p = 4 * b + j;
-                    if (p < PB && ((ab >> j) & 1u)) {
-                        const uint32_t r = word_of(r4, j);
-                        const uint32_t choice = ph.action_op == ACT_PICK_OPTION ? 1u + __umulhi(r, (uint32_t)ph.action_arg) : 1u;
+                    if ((ab >> j) & 1u) {
+                        const uint32_t choice = aop == ACT_PICK_OPTION ? 1u + __umulhi(word_of(r4, j), (uint32_t)v.action_arg()) : 1u;
                         if (!have_first) { first_choice = choice; have_first = true; }
-                        if (ph.exit_op == EX_T_VOTES) s.pw[p] = (s.pw[p] & 0xFF00FFFFu) | (choice << 16);
+                        if (exo == EX_T_VOTES) s.pw[p] = (s.pw[p] & 0xFF00FFFFu) | (choice << 16);
                     }
                 }
             }
         }
-        switch (ph.exit_op) {
-        case EX_T_STATEMENTS: m[1] |= actors; break;
+        switch (exo) {
+        case EX_T_STATEMENTS: F.set(1, F.get(1) | actors); flags_dirty = true; break;
         case EX_T_LIE: if (have_first) lie = first_choice; break;
-        case EX_T_VOTES: m[4] |= actors; break;
+        case EX_T_VOTES: F.set(4, F.get(4) | actors); flags_dirty = true; break;
         default: break;
         }
     }
 
-    const int en = T.phase[Y].entry_op;
+    const int en = v.entry_op_after(taken);
     if (en == EN_T_ROUND_START) {
         speaker = 0;
 #pragma unroll
         for (int p = PB - 1; p >= 0; --p)
-            if (p < P && ((s.pw[p] >> 8) & 0xFFu) < T.h.rounds) speaker = p + 1;
+            if (p < P && ((s.pw[p] >> 8) & 0xFFu) < (uint32_t)v.rounds()) speaker = p + 1;
         lie = 0;
-        m[0] = speaker ? 1u << (speaker - 1) : 0u;
-        m[3] = ALL & ~m[0];
-        m[1] = 0; m[2] = 0; m[4] = 0;
+        const uint32_t sp = speaker ? 1u << (speaker - 1) : 0u;
+#pragma unroll
+        for (int i = 0; i < PB / 4; ++i) F.w[i] = 0;
+        F.set(0, sp);
+        F.set(3, ALL & ~sp);
+        flags_dirty = true;
 #pragma unroll
         for (int p = 0; p < PB; ++p) s.pw[p] &= 0xFF00FFFFu;
     } else if (en == EN_T_REVEAL) {
-        m[2] |= m[0];
+        F.set(2, F.get(2) | F.get(0));
+        flags_dirty = true;
     } else if (en == EN_T_SCORE) {
-        const uint32_t voters = m[4] & m[3] & ~m[0];
+        const uint32_t voters = F.get(4) & F.get(3) & ~F.get(0);
         uint32_t fooled = 0;
 #pragma unroll
         for (int p = 0; p < PB; ++p) {
@@ -773,6 +822,7 @@ __device__ __forceinline__ int t_step(const DevTable& T, TState<PB>& s, uint32_t
                 s.pw[p] = (s.pw[p] & 0xFFFF0000u) | sc | (rd << 8);
             }
         }
+        dirty |= DIRTY_PL;
     } else if (en == EN_T_FINAL) {
         uint32_t best = s.pw[0] & 0xFFu; winner = 1;
 #pragma unroll
@@ -780,85 +830,128 @@ __device__ __forceinline__ int t_step(const DevTable& T, TState<PB>& s, uint32_t
             if (p < P && (s.pw[p] & 0xFFu) > best) { best = s.pw[p] & 0xFFu; winner = p + 1; }
     }
     if (tag) winner = tag;
-
-    // write the flag bytes back
-#pragma unroll
-    for (int p = 0; p < PB; ++p) {
-        uint32_t fl = 0;
-#pragma unroll
-        for (int f = 0; f < 5; ++f) fl |= ((m[f] >> p) & 1u) << f;
-        s.pw[p] = (s.pw[p] & 0x00FFFFFFu) | (fl << 24);
-    }
+    if (v.kind() == KIND_ACTION && v.exit_op() == EX_T_VOTES) dirty |= DIRTY_PL;
+    if (flags_dirty) { F.store(s.pw); dirty |= DIRTY_PL; }
     s.h1 = speaker | (lie << 8) | (winner << 16);
     s.h0 = (uint32_t)Y | ((uint32_t)X << 8) | ((step0 + 1u) << 16);
     return Y;
 }
 
 template <int PB>
+__device__ __forceinline__ int t_step(const DevTable& T, TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi,
+                                      uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    const int X = s.h0 & 0xFF;
+    if (T.phase[X].kind == KIND_TERMINAL) return -1;
+    dirty |= DIRTY_C0;
+    if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
+    return t_step_body<PB>(RtView(T, X), X, s, sid_lo, sid_hi, k0, k1, dirty);
+}
+
+template <int PB, class Spec, int X = 0>
+__device__ __forceinline__ int t_step_spec(TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi, uint32_t k0, uint32_t k1, uint32_t& dirty) {
+    if constexpr (X >= Spec::n_phases) {
+        return -1;
+    } else {
+        if ((int)(s.h0 & 0xFF) == X) {
+            if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
+            dirty |= DIRTY_C0;
+            if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
+            return t_step_body<PB>(CtView<Spec, X>{}, X, s, sid_lo, sid_hi, k0, k1, dirty);
+        }
+        return t_step_spec<PB, Spec, X + 1>(s, sid_lo, sid_hi, k0, k1, dirty);
+    }
+}
+
+// Column 0 (16 bytes) holds the header and the first two player words; the host proves per phase whether a
+// step needs the player words at all (DevTable::need bit 2): launches whose sessions are all in header-only
+// phases move one column in and out instead of the whole record.
+template <int PB, class Spec = void>
 __global__ void __launch_bounds__(128)
 k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
-    uint8_t* __restrict__ tiles = A.tiles;
-    const uint64_t n_sessions = A.n_sessions, n_tiles = A.n_tiles, first_sid = A.first_sid, seed = A.seed;
-    unsigned long long* __restrict__ stats = A.stats;
-    const int n_steps = A.n_steps;
     constexpr int S = 8 + 4 * PB;           // device record (PB even => S % 8 == 0)
     constexpr int NW = S / 4;
     constexpr int N16 = S / 16;
     constexpr bool HALF = (S % 16) != 0;
     __shared__ uint32_t s_visits[32];
+    __shared__ uint32_t s_present;
     if (threadIdx.x < 32) s_visits[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_present = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-
+    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
+    const uint32_t present_in = A.presence_override ? A.presence_override : A.presence[A.launch_idx % 3];
+    const uint32_t need = A.n_steps > 1 ? 15u : need_of(T, present_in);
+    const bool full = (need & 4u) != 0;
+    const bool use_origin = A.origin != nullptr && (need & 8u);
     const uint64_t n_act = *A.n_active;
     const uint64_t n_tiles_act = (n_act + 31) >> 5;
-    (void)n_tiles; (void)n_sessions;
+    uint32_t present_out = 0;
+    VisitAcc visits;
     for (uint64_t tile = warp0; tile < n_tiles_act; tile += nwarps) {
-        uint8_t* base = tiles + tile * (uint64_t)(32 * S);
+        uint8_t* base = A.tiles + tile * (uint64_t)(32 * S);
         const uint64_t sess = tile * 32 + lane;
+        const bool in_range = sess < n_act;
         uint64_t org = sess;
-        if (A.origin != nullptr && sess < n_act) org = A.origin[sess];
+        if (use_origin && in_range) org = A.origin[sess];
         uint32_t w[NW];
+        {
+            const uint4 v = ld128(base + lane * 16);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        }
 #pragma unroll
-        for (int c = 0; c < N16; ++c) {
-            const uint4 v = ld128(base + c * 512 + lane * 16);
+        for (int c = 1; c < N16; ++c) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (full) v = ld128(base + c * 512 + lane * 16);
             w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
         }
-        if (HALF) { const uint2 v = ld64(base + N16 * 512 + lane * 8); w[4 * N16] = v.x; w[4 * N16 + 1] = v.y; }
+        if (HALF) {
+            uint2 v = make_uint2(0, 0);
+            if (full) v = ld64(base + N16 * 512 + lane * 8);
+            w[4 * N16] = v.x; w[4 * N16 + 1] = v.y;
+        }
         TState<PB> s;
         s.h0 = w[0]; s.h1 = w[1];
 #pragma unroll
         for (int p = 0; p < PB; ++p) s.pw[p] = w[2 + p];
-        bool live = sess < n_act && T.phase[s.h0 & 0xFF].kind != KIND_TERMINAL;
-        const uint64_t sid = first_sid + org;
+        bool live = in_range;
+        const uint64_t sid = A.first_sid + org;
         uint32_t dirty = 0;
-        for (int it = 0; it < n_steps; ++it) {
+        for (int it = 0; it < A.n_steps; ++it) {
             int np = -1;
             if (live) {
-                np = t_step<PB>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                if constexpr (std::is_void<Spec>::value)
+                    np = t_step<PB>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                else
+                    np = t_step_spec<PB, Spec>(s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
                 if (np < 0) live = false;
             }
-            count_visit(s_visits, np, lane);
+            visits.add(s_visits, np, lane);
         }
+        if (in_range) present_out |= 1u << (s.h0 & 31);
         {
-            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, sess < n_act && T.phase[s.h0 & 31].kind != KIND_TERMINAL);
+            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[s.h0 & 31].kind != KIND_TERMINAL);
             if (lane == 0) { A.live_mask[tile] = lm; if (A.count_live && lm) atomicAdd(A.live_count, (unsigned long long)__popc(lm)); }
         }
         if (dirty) {
             w[0] = s.h0; w[1] = s.h1;
 #pragma unroll
             for (int p = 0; p < PB; ++p) w[2 + p] = s.pw[p];
+            st128(base + lane * 16, make_uint4(w[0], w[1], w[2], w[3]));
+            if (dirty & DIRTY_PL) {
 #pragma unroll
-            for (int c = 0; c < N16; ++c) st128(base + c * 512 + lane * 16, make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
-            if (HALF) st64(base + N16 * 512 + lane * 8, make_uint2(w[4 * N16], w[4 * N16 + 1]));
+                for (int c = 1; c < N16; ++c) st128(base + c * 512 + lane * 16, make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+                if (HALF) st64(base + N16 * 512 + lane * 8, make_uint2(w[4 * N16], w[4 * N16 + 1]));
+            }
         }
     }
+    visits.flush(s_visits, lane);
+    present_out = __reduce_or_sync(0xFFFFFFFFu, present_out);
+    if (lane == 0 && present_out) atomicOr(&s_present, present_out);
     __syncthreads();
-    flush_visits(s_visits, stats);
-    publish_presence(A, 0xFFFFFFFFu);      // this kernel loads every column; make the next launch do the same
+    flush_visits(s_visits, A.stats);
+    publish_presence(A, s_present);
 }
 
 }  // namespace ge
