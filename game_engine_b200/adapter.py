@@ -104,6 +104,11 @@ class SessionCodec:
     def __init__(self, cg: CompiledGame):
         self.cg = cg
         self.P = cg.n_players
+        # canonical field name -> the DSL's name for it (rules `fields:` aliases); identity when not aliased
+        self.dsl_name = {canon: dsl for dsl, canon in (cg.field_alias or {}).items()}
+
+    def _k(self, canon: str) -> str:
+        return self.dsl_name.get(canon, canon)
 
     # ------------------------------------------------------------------ init (utils.py:584-653 + AgentState defaults)
     def initial_state(self, room_players: Optional[List[dict]] = None, game_name: Optional[str] = None) -> Dict[str, Any]:
@@ -120,10 +125,20 @@ class SessionCodec:
             "game_notes": [],
         }
 
+    def initial_record(self) -> np.ndarray:
+        """Canonical record of a freshly created session (what ge_batch_create writes for every slot)."""
+        return self.record_from_state(self.initial_state())
+
     # ------------------------------------------------------------------ record -> player_states
-    def player_states_from_record(self, rec: Record, names: List[str]) -> Dict[str, Dict[str, Any]]:
+    def player_states_from_record(self, rec: Record, names: List[str], prev_ps: Optional[Dict[str, Any]] = None,
+                                  written: Optional[Dict[int, set]] = None) -> Dict[str, Dict[str, Any]]:
+        """Per-player dicts of a record.  Canonical fields the DSL's template does not declare exist in the
+        reference's dict only once a referee tool call has written them (backend_tools.py:204-225 creates the key);
+        with `prev_ps` / `written` (step_update) such a field is emitted only if the previous state had it or
+        this step wrote it, otherwise every canonical field is emitted."""
         cg, P = self.cg, self.P
         out: Dict[str, Dict[str, Any]] = {}
+        tpl_keys = set(cg.template.keys())
         if cg.family == T.FAMILY_WEREWOLF:
             assigned = rec.secret != 0
             village, wolf_team = cg.teams
@@ -135,12 +150,21 @@ class SessionCodec:
                 if assigned and rec.role[p] == 3:
                     for t in _bits(rec.investigated, P):
                         inv[str(t + 1)] = wolf_team if (rec.wolf >> t) & 1 else village
-                out[str(p + 1)] = {
+                entry = {
                     "name": names[p], "role": role, "team": team, "is_alive": bit(rec.alive), "role_revealed": bit(rec.revealed),
                     "can_vote": bit(rec.can_vote), "has_secret_role": bit(rec.secret), "night_action_eligible": bit(rec.eligible),
                     "night_action_submitted": bit(rec.submitted), "selected_target_id": rec.target[p],
                     "investigated_alignments": inv,
                 }
+                if "team_is_wolf" in self.dsl_name:
+                    entry["team_is_wolf"] = assigned and bit(rec.wolf)
+                if self.dsl_name:
+                    entry = {self._k(k): v for k, v in entry.items()}
+                if prev_ps is not None:
+                    old = prev_ps.get(str(p + 1), {})
+                    wr = {self._k(k) for k in (written or {}).get(p, ())}
+                    entry = {k: v for k, v in entry.items() if k in tpl_keys or k in old or k in wr}
+                out[str(p + 1)] = entry
         else:
             for p in range(P):
                 fl = rec.flags[p]
@@ -167,6 +191,9 @@ class SessionCodec:
         step = len(hist)
         r[0], r[1], r[2], r[3] = phase, prev, step & 0xFF, step >> 8
         ps = state.get("player_states") or {}
+        if self.dsl_name:       # read through the aliases: present every entry under its canonical field names
+            canon_of = dict(cg.field_alias)
+            ps = {pid: {canon_of.get(k, k): v for k, v in e.items()} for pid, e in ps.items()}
         get = lambda p: ps.get(str(p + 1), {})
         put32 = lambda off, v: r.__setitem__(slice(off, off + 4), np.frombuffer(int(v).to_bytes(4, "little"), dtype=np.uint8))
         if cg.family == T.FAMILY_WEREWOLF:
@@ -259,13 +286,45 @@ class SessionCodec:
         # ---- PhaseNode part
         history.append({"phase_id": cg.phase_ids[Y], "phase_name": cg.phase_names[Y], "timestamp": now_iso})
         # ---- RefereeNode part
-        new_ps = self.player_states_from_record(a, names)
+        new_ps = self.player_states_from_record(a, names, prev_ps=ps_old, written=self.written_fields(b, a))
         if b.step > 0:
             notes += [format_note(t, c) for t, c in self.notes_for(b, a, names)]
         # the reference's phase-0 first visit returns no current_phase_name (game_agent_v2.py:1043-1052)
         name = cg.phase_names[Y] if b.step > 0 else state.get("current_phase_name", "")
         return {"player_states": new_ps, "playerActions": actions, "current_phase_id": cg.phase_ids[Y],
                 "current_phase_name": name, "phase_history": history, "game_notes": notes}
+
+    def written_fields(self, b: Record, a: Record) -> Dict[int, set]:
+        """{player index: canonical fields the referee writes in the step b -> a} (SPEC.md section 4 effects)."""
+        cg, P = self.cg, self.P
+        w: Dict[int, set] = {p: set() for p in range(P)}
+        if cg.family != T.FAMILY_WEREWOLF or a.step == b.step or b.step == 0:
+            return w
+        phX = cg.table.phases[b.phase]
+        ex, en = phX.exit_op, cg.table.phases[a.phase].entry_op
+        actors = _bits(b.eval_pred(cg.table.preds[phX.actor_pred]), P) if phX.kind == T.KIND_ACTION else []
+        died = _bits(b.alive & ~a.alive, P)
+        if ex in (T.EX_VOTE_KILL, T.EX_PROTECT, T.EX_INVESTIGATE_RESOLVE):
+            for p in actors:
+                w[p] |= {"selected_target_id", "night_action_submitted"}
+        if ex == T.EX_INVESTIGATE_RESOLVE:
+            for p in actors:
+                if a.target[p]:
+                    w[p].add("investigated_alignments")
+        if ex == T.EX_DAY_VOTE:
+            for p in actors:
+                w[p].add("selected_target_id")
+            for p in died:
+                w[p].add("role_revealed")
+        for p in died:
+            w[p] |= {"is_alive", "can_vote", "night_action_eligible"}
+        if en == T.EN_ASSIGN_ROLES:
+            for p in range(P):
+                w[p] |= {"role", "team", "has_secret_role", "night_action_eligible", "team_is_wolf"}
+        if en == T.EN_NIGHT_RESET:
+            for p in range(P):
+                w[p] |= {"night_action_submitted", "selected_target_id"}
+        return w
 
     def action_text(self, phase_index: int, choice: int) -> str:
         tpl = self.cg.action_text.get(phase_index, "acted")

@@ -124,6 +124,14 @@ class SessionBatch:
         assert rec.size % S == 0
         capi.check(capi.lib().ge_import_state(self._h, int(first), rec.size // S, rec.ctypes.data))
 
+    def trace(self, n_steps: int, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Steps the batch n_steps times and returns uint8[n_steps + 1, count, S]: the canonical records of the
+        window after every step (frame 0 = before the first step); see trace.py for the JSON form."""
+        count = self.n - first if count is None else int(count)
+        out = np.empty((int(n_steps) + 1, count, self.table.record_size), dtype=np.uint8)
+        capi.check(capi.lib().ge_trace(self._h, int(first), count, int(n_steps), out.ctypes.data))
+        return out
+
     def run_host(self, records_in: Optional[np.ndarray], records_out: Optional[np.ndarray], n_steps: int,
                  stats_out: Optional[np.ndarray] = None) -> None:
         """End-to-end call with host buffers (H2D, n_steps steps, D2H); synchronous."""

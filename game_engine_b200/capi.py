@@ -41,6 +41,7 @@ SYMBOLS = [
     ("ge_sync", _int, [_vp]),
     ("ge_export_state", _int, [_vp, _u64, _u64, _vp]),
     ("ge_import_state", _int, [_vp, _u64, _u64, _vp]),
+    ("ge_trace", _int, [_vp, _u64, _u64, _int, _vp]),
     ("ge_run_host", _int, [_vp, _vp, _vp, _int, _vp]),
     ("ge_run_host_async", _int, [_vp, _vp, _vp, _int, _vp]),
     ("ge_batch_set_host_fused", _int, [_vp, _int]),

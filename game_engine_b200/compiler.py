@@ -135,12 +135,15 @@ Clause = Tuple[int, int]        # (pos bitset, neg bitset) over mask-field ids
 
 
 class _FieldMap:
-    def __init__(self, family: int, role_names: List[str], wolf_team: str, village_team: str):
+    def __init__(self, family: int, role_names: List[str], wolf_team: str, village_team: str,
+                 alias: Optional[Dict[str, str]] = None):
         self.family, self.roles, self.wolf_team, self.village_team = family, role_names, wolf_team, village_team
+        self.alias = dict(alias or {})           # DSL field name -> canonical field name (rules `fields:`)
 
     def literal(self, name: str, op: str, val: Any) -> List[Clause]:
         """DNF of `player.<name> <op> <val>`."""
         neg = op == "!="
+        name = self.alias.get(name, name)
         if self.family == T.FAMILY_WEREWOLF:
             if name == "role":
                 if val not in self.roles:
@@ -215,6 +218,11 @@ def compile_predicate(cond: str, fm: _FieldMap) -> Tuple[int, int, int, int]:
     return (clauses[0][0], clauses[0][1], clauses[1][0], clauses[1][1])
 
 
+# canonical per-player keys that are not mask fields (targets of a rules `fields:` alias)
+CANONICAL_EXTRA = ("investigated_alignments", "selected_target_id", "role", "team", "name", "statements", "lie_index",
+                   "vote_choice", "total_score", "rounds_as_speaker")
+
+
 # --------------------------------------------------------------------------- compiled game
 @dataclass
 class CompiledGame:
@@ -230,6 +238,7 @@ class CompiledGame:
     action_text: Dict[int, str]                 # phase index -> action text template
     template: Dict[str, Any]                    # declaration.player_states_template entry
     audience_preds: Dict[str, Tuple[int, int, int, int]] = field(default_factory=dict)
+    field_alias: Dict[str, str] = field(default_factory=dict)      # DSL field name -> canonical field name
     dsl: Dict[str, Any] = field(default_factory=dict)
 
     @property
@@ -282,13 +291,20 @@ def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: O
         want = [rules["roles"][k] for k in ("villager", "werewolf", "doctor", "detective")]
         if role_names != want:
             raise DSLCompileError("werewolf family expects declaration.roles == %r, got %r" % (want, role_names))
-    fm = _FieldMap(fam, role_names, wolf_team, village_team)
+    alias = {str(k): str(v) for k, v in (rules.get("fields") or {}).items()}
+    fm = _FieldMap(fam, role_names, wolf_team, village_team, alias)
 
     tpl = _template(dsl)
     fields = T.W_FIELDS if fam == T.FAMILY_WEREWOLF else T.T_FIELDS
+    for dsl_name, canon in alias.items():
+        if dsl_name not in tpl:
+            raise DSLCompileError("rules alias %r is not a field of the DSL's player_states_template" % dsl_name)
+        if canon not in fields and canon not in CANONICAL_EXTRA:
+            raise DSLCompileError("rules alias %r -> %r: unknown canonical field" % (dsl_name, canon))
     init_masks = 0
-    for name, fid in fields.items():
-        if tpl.get(name) is True:
+    for name, val in tpl.items():
+        fid = fields.get(alias.get(name, name))
+        if fid is not None and val is True:
             init_masks |= 1 << fid
 
     phases_dsl = dsl["phases"]
@@ -381,4 +397,5 @@ def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: O
         name=game, family=fam, n_players=n_players, table=tab, blob=tab.pack(), phase_ids=ids,
         phase_names=[get(p).get("name", "Phase %d" % p) for p in ids], role_names=role_names,
         teams=(village_team, wolf_team), action_text=action_text, template=tpl, audience_preds=aud, dsl=dsl,
+        field_alias=alias,
     )

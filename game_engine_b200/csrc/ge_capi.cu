@@ -1024,6 +1024,23 @@ extern "C" int ge_import_state(ge_batch* b, uint64_t first, uint64_t count, cons
     return GE_OK;
 }
 
+// Step log: canonical records of a window of sessions after each of n_steps single-step launches (record 0 =
+// the state before the first of them).  The whole batch is stepped; only the window is exported.
+extern "C" int ge_trace(ge_batch* b, uint64_t first, uint64_t count, int n_steps, void* host_records) {
+    if (!b || !host_records || n_steps < 0 || count == 0 || first + count > b->n) return fail(GE_ERR_ARG, "bad arguments to ge_trace");
+    CU(cudaSetDevice(b->device));
+    const size_t frame = count * b->tab->rec_canon;
+    uint8_t* out = static_cast<uint8_t*>(host_records);
+    int rc = export_async(b, first, count, out);
+    for (int k = 1; rc == GE_OK && k <= n_steps; ++k) {
+        rc = launch_steps(b, 1, 1, b->stream);
+        if (rc == GE_OK) rc = export_async(b, first, count, out + (size_t)k * frame);
+    }
+    if (rc != GE_OK) return rc;
+    CU(cudaStreamSynchronize(b->stream));
+    return GE_OK;
+}
+
 extern "C" int ge_eval_preds(ge_batch* b, const ge_pred_t* preds, int n_preds, uint64_t first, uint64_t count, uint32_t* host_masks) {
     if (!b || !preds || !host_masks || n_preds < 1 || n_preds > 32 || first + count > b->n) return fail(GE_ERR_ARG, "bad arguments to ge_eval_preds");
     if (count == 0) return GE_OK;

@@ -132,6 +132,13 @@ int ge_sync(ge_batch *b);
 int ge_export_state(ge_batch *b, uint64_t first, uint64_t count, void *host_buf);
 int ge_import_state(ge_batch *b, uint64_t first, uint64_t count, const void *host_buf);
 
+/* Step log for replay: applies n_steps single-step launches to the whole batch and writes the canonical records
+ * of sessions [first, first+count) after each of them: host_records holds (n_steps + 1) frames of count * S
+ * bytes, frame 0 = the state before the first step.  The host adapter turns a session's frames into the
+ * reference's on-wire AgentState JSON, one object per graph run (reference src/lib/canvas/types.ts:338-360,
+ * agent/game_agent_v2.py:97-117).  Synchronous. */
+int ge_trace(ge_batch *b, uint64_t first, uint64_t count, int n_steps, void *host_records);
+
 /* End-to-end call with HOST buffers: records_in (NULL = keep current device state) -> device,
  * n_steps steps, records_out (NULL = skip) and stats (NULL = skip) back to the host.  Synchronous.
  * Pinned buffers (ge_host_alloc) make the copies asynchronous DMA. */

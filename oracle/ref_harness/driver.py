@@ -18,6 +18,11 @@ REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 KEEP = ("current_phase_id", "current_phase_name", "player_states", "playerActions", "phase_history", "game_notes")
 
 
+# Games the reference's own loader (agent/tools/utils.py:557-581: games/<gameName>.yaml) finds under another name:
+# its earlier werewolf generation lives in game_draft/, reachable through a relative gameName.
+REFERENCE_GAME_NAME = {"werewolf-draft": "../game_draft/werewolf-(mafia)"}
+
+
 def load_rules(game: str) -> dict:
     with open(os.path.join(REPO, "game_engine_b200", "rules", game + ".rules.yaml"), encoding="utf-8") as f:
         return yaml.safe_load(f)
@@ -40,7 +45,7 @@ async def _run(game: str, n_players: int, seed: int, sid: int, max_steps: int) -
     stub = StubChatModel(load_rules(game), seed, sid)
     shims.set_model(stub)
     players = [{"name": "Player %d" % (i + 1), "gamePlayerId": str(i + 1)} for i in range(n_players)]
-    state: Dict[str, Any] = {"gameName": game, "roomSession": {"players": players}, "messages": [], "current_phase_id": 0,
+    state: Dict[str, Any] = {"gameName": REFERENCE_GAME_NAME.get(game, game), "roomSession": {"players": players}, "messages": [], "current_phase_id": 0,
                              "player_states": {}, "playerActions": {}, "phase_history": [], "game_notes": []}
     trace: List[Dict[str, Any]] = []
     for step in range(max_steps + 1):

@@ -21,13 +21,18 @@ CASES = [
     ("werewolf-(mafia)", 8, 0, 0), ("werewolf-(mafia)", 8, 1, 1), ("werewolf-(mafia)", 8, 7, 123456789012),
     ("werewolf-(mafia)", 8, 20261018, 4242), ("werewolf-(mafia)", 5, 3, 3), ("werewolf-(mafia)", 16, 4, 9),
     ("werewolf-(mafia)", 32, 6, 31),
+    # third table: the reference's earlier 13-phase werewolf generation (game_draft/), aliased state schema
+    ("werewolf-draft", 8, 11, 77), ("werewolf-draft", 6, 12, 1 << 36), ("werewolf-draft", 12, 13, 5),
 ]
 
 
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1] if len(sys.argv) > 1 else None          # optional: regenerate one game's fixtures
     for game, P, seed, sid in CASES:
+        if only and game != only:
+            continue
         trace = run_session(game, P, seed, sid)
         name = "%s_p%d_seed%d_sid%d.json.gz" % (game.replace("(", "").replace(")", ""), P, seed, sid)
         blob = json.dumps({"game": game, "players": P, "seed": seed, "sid": sid, "trace": trace}, ensure_ascii=False,

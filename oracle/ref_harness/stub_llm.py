@@ -72,6 +72,11 @@ class StubChatModel:
         self.rules, self.seed, self.sid = rules, seed, sid
         self.state: Dict[str, Any] = {}
         self.calls = 0
+        # rules `fields:` maps a DSL field name to the canonical one; the referee writes / reads the DSL's names
+        self.dsl_name = {canon: dsl for dsl, canon in (rules.get("fields") or {}).items()}
+
+    def F(self, canon: str) -> str:
+        return self.dsl_name.get(canon, canon)
 
     def bind_tools(self, tools, **kw):
         return _Bound(self, frozenset(t.name for t in tools))
@@ -173,7 +178,7 @@ class StubChatModel:
         step = len(hist) - 1                      # step count at the start of this step
         ids = self._ids()
         calls: List[dict] = []
-        upd = lambda i, k, v: calls.append({"name": "update_player_state", "args": {"player_id": str(i), "state_name": k, "state_value": v}, "id": "r%d" % len(calls)})
+        upd = lambda i, k, v: calls.append({"name": "update_player_state", "args": {"player_id": str(i), "state_name": self.F(k), "state_value": v}, "id": "r%d" % len(calls)})
         note = lambda t, c: calls.append({"name": "add_game_note", "args": {"note_type": t, "content": c}, "id": "n%d" % len(calls)})
         ex, en = self._prules(X).get("exit"), self._prules(Y).get("entry")
         actors = self._actors(phX)
@@ -192,13 +197,13 @@ class StubChatModel:
         if ex == "INVESTIGATE_RESOLVE":
             for i in actors:
                 if choice[i]:
-                    memo = dict(self._ps(i).get("investigated_alignments") or {})
+                    memo = dict(self._ps(i).get(self.F("investigated_alignments")) or {})
                     memo[str(choice[i])] = self._ps(choice[i])["team"]
                     upd(i, "investigated_alignments", memo)
-            wolves = [i for i in ids if self._ps(i)["role"] == roles["werewolf"] and self._ps(i)["night_action_submitted"]]
-            kill = plurality([self._ps(i)["selected_target_id"] for i in wolves])
-            docs = [i for i in ids if self._ps(i)["role"] == roles["doctor"] and self._ps(i)["night_action_submitted"]]
-            protect = self._ps(docs[0])["selected_target_id"] if docs else 0
+            wolves = [i for i in ids if self._ps(i)["role"] == roles["werewolf"] and self._ps(i)[self.F("night_action_submitted")]]
+            kill = plurality([self._ps(i)[self.F("selected_target_id")] for i in wolves])
+            docs = [i for i in ids if self._ps(i)["role"] == roles["doctor"] and self._ps(i)[self.F("night_action_submitted")]]
+            protect = self._ps(docs[0])[self.F("selected_target_id")] if docs else 0
             if kill and kill != protect:
                 role = self._ps(kill)["role"]
                 die(kill)
@@ -238,6 +243,8 @@ class StubChatModel:
                 special = role != roles["villager"]
                 upd(i, "role", role); upd(i, "team", wolf_team if role == roles["werewolf"] else village)
                 upd(i, "has_secret_role", special); upd(i, "night_action_eligible", special)
+                if "team_is_wolf" in self.dsl_name:
+                    upd(i, "team_is_wolf", role == roles["werewolf"])
             note("NEXT_PHASE", "Roles assigned: " + ", ".join("Player %d=%s" % (i, assigned[i]) for i in ids))
         if en == "NIGHT_RESET":
             for i in ids:

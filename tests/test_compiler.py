@@ -134,3 +134,48 @@ def test_revote_variant_compiles_with_tie_branches():
         assert [(b.op, cg.phase_ids[b.next]) for b in br] == [(T.BR_TIE_PENDING, revote), (T.BR_ALWAYS, 9)]
         rv = t.phases[cg.index_of(revote)]
         assert rv.kind == T.KIND_ACTION and rv.exit_op == T.EX_DAY_VOTE and cg.phase_ids[rv.branches[0].next] == announce
+
+
+DRAFT = "werewolf-draft"
+
+
+def test_draft_variant_is_a_third_table(games):
+    """The reference's earlier 13-phase werewolf generation (game_draft/): other phase graph, win check after
+    every dawn, two terminal phases, and a state schema bound through the rules' `fields:` aliases."""
+    cg = games(DRAFT, 8)
+    t = cg.table
+    assert cg.phase_ids == list(range(11)) + [98, 99] and cg.record_size == 56 and t.n_wolves == 2
+    U, M, A, X = T.KIND_UI, T.KIND_TIMER, T.KIND_ACTION, T.KIND_TERMINAL
+    assert [p.kind for p in t.phases] == [U, U, A, A, A, U, U, M, A, U, U, X, X]
+    assert [p.exit_op for p in t.phases] == [0, 0, 1, 2, 3, 0, 0, 0, 4, 0, 0, 0, 0]
+    assert [p.entry_op for p in t.phases] == [0, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]
+    br = t.phases[10].branches
+    assert [(b.op, cg.phase_ids[b.next], b.tag) for b in br] == [
+        (T.BR_COUNT_EQ0, 98, 1), (T.BR_COUNT_GE, 99, 2), (T.BR_PREV_IN, 7, 0), (T.BR_ALWAYS, 2, 0)]
+    assert br[2].arg == 1 << 6                       # "follows Dawn Reveal"
+    assert t.init_masks == 0b11
+    # aliases: has_night_action -> has_secret_role (7), wolf_chat_enabled -> team_is_wolf (6)
+    assert cg.field_alias == {"has_night_action": "has_secret_role", "known_alignments": "investigated_alignments",
+                              "wolf_chat_enabled": "team_is_wolf"}
+    assert cg.audience_preds["night_actors"] == (1 << 7 | 1, 0) + T.CLAUSE_EMPTY
+    assert cg.audience_preds["wolf_chatters"] == (1 << 6 | 1, 0) + T.CLAUSE_EMPTY
+    assert len(cg.audience_preds) == 9
+
+
+def test_alias_must_name_real_fields():
+    dsl, rules = C.load_dsl(DRAFT), C.load_rules(DRAFT)
+    rules["fields"] = {"has_night_action": "no_such_field"}
+    with pytest.raises(DSLCompileError):
+        compile_game(DRAFT, 8, dsl=dsl, rules=rules)
+    rules["fields"] = {"not_in_template": "has_secret_role"}
+    with pytest.raises(DSLCompileError):
+        compile_game(DRAFT, 8, dsl=dsl, rules=rules)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not has_reference(), reason="needs /root/reference")
+def test_reference_draft_yaml_compiles_to_identical_table():
+    with open(os.path.join(REFERENCE, "game_draft", "werewolf-(mafia).yaml"), encoding="utf-8") as f:
+        ref = yaml.safe_load(f)
+    a, b = compile_game(DRAFT, 12, dsl=ref), compile_game(DRAFT, 12)
+    assert a.blob == b.blob and a.phase_names == b.phase_names and a.template == b.template and a.audience_preds == b.audience_preds

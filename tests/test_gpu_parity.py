@@ -7,11 +7,12 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-WEREWOLF, TTL, REVOTE = "werewolf-(mafia)", "two-truths-and-a-lie", "werewolf-revote"
+WEREWOLF, TTL, REVOTE, DRAFT = "werewolf-(mafia)", "two-truths-and-a-lie", "werewolf-revote", "werewolf-draft"
 CASES = [
     (TTL, 4), (TTL, 3), (TTL, 7), (TTL, 12), (TTL, 32),
     (WEREWOLF, 8), (WEREWOLF, 4), (WEREWOLF, 5), (WEREWOLF, 13), (WEREWOLF, 16), (WEREWOLF, 21), (WEREWOLF, 32),
     (REVOTE, 8), (REVOTE, 32),          # extended game: tie -> re-vote phases (BASELINE config 4)
+    (DRAFT, 8), (DRAFT, 19),            # third table (reference game_draft/): generic interpreter kernel, two terminal phases
 ]
 
 
@@ -49,7 +50,8 @@ def test_every_step_bit_exact(games, oracle_for, game, P, kernel):
 
 
 @pytest.mark.parametrize("kernel", ["tps", "tps_generic", "coop"])
-@pytest.mark.parametrize("game,P,n", [(WEREWOLF, 8, 1 << 16), (WEREWOLF, 32, 1 << 14), (TTL, 4, 1 << 16), (REVOTE, 32, 1 << 13)])
+@pytest.mark.parametrize("game,P,n", [(WEREWOLF, 8, 1 << 16), (WEREWOLF, 32, 1 << 14), (TTL, 4, 1 << 16), (REVOTE, 32, 1 << 13),
+                                        (DRAFT, 8, 1 << 15)])
 def test_run_to_completion_matches(games, oracle_for, game, P, n, kernel):
     cg = games(game, P)
     o = oracle_for(cg)
@@ -66,7 +68,8 @@ def test_run_to_completion_matches(games, oracle_for, game, P, n, kernel):
     np.testing.assert_array_equal(gst, ost)
     assert gst[1:4].sum() == n
     # every session must have reached the terminal phase within the cap
-    assert (rec[:, 0] == len(cg.phase_ids) - 1).all()
+    kinds = np.array([p.kind for p in cg.table.phases])
+    assert (kinds[rec[:, 0]] == 3).all()
 
 
 @pytest.mark.parametrize("kernel", ["tps", "coop"])

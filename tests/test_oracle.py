@@ -32,14 +32,15 @@ def _popc(a):
 
 
 @pytest.mark.parametrize("game,P", [(WEREWOLF, 4), (WEREWOLF, 8), (WEREWOLF, 13), (WEREWOLF, 16), (WEREWOLF, 32),
-                                    ("werewolf-revote", 8), ("werewolf-revote", 16)])
+                                    ("werewolf-revote", 8), ("werewolf-revote", 16),
+                                    ("werewolf-draft", 6), ("werewolf-draft", 8), ("werewolf-draft", 32)])
 def test_werewolf_properties(games, oracle_for, game, P):
     cg = games(game, P)
     o = oracle_for(cg)
     n, seed = 2000, 11
     rec = o.init(n)
     st = o.new_stats()
-    term = len(cg.phase_ids) - 1
+    is_term = np.array([ph.kind == T.KIND_TERMINAL for ph in cg.table.phases])
     edges = {i: {b.next for b in ph.branches} for i, ph in enumerate(cg.table.phases)}
     prev_alive = _popc(_fields_w(rec)["alive"])
     for k in range(420 if game != WEREWOLF else 300):
@@ -52,7 +53,7 @@ def test_werewolf_properties(games, oracle_for, game, P):
             assert b in edges[a] or (a == 0 and b == 0), (a, b)
         # terminal sessions are frozen
         np.testing.assert_array_equal(rec[~moved], before[~moved])
-        assert (fb["phase"][~moved] == term).all()
+        assert is_term[fb["phase"][~moved]].all()
         # alive count never increases, at most one death per step
         alive = _popc(f["alive"])
         assert ((prev_alive - alive) >= 0).all() and ((prev_alive - alive) <= 1).all()
@@ -64,7 +65,7 @@ def test_werewolf_properties(games, oracle_for, game, P):
         # dead players cannot vote or act
         assert ((f["can_vote"] & ~f["alive"]) == 0).all() and ((f["eligible"] & ~f["alive"]) == 0).all()
     f = _fields_w(rec)
-    assert (f["phase"] == term).all(), "every game must end"
+    assert is_term[f["phase"]].all(), "every game must end"
     wolves_alive, vill_alive = _popc(f["wolf"] & f["alive"]), _popc(~f["wolf"] & f["alive"])
     assert ((f["winner"] == 1) == (wolves_alive == 0)).all()            # terminal iff win predicate
     assert ((f["winner"] == 2) == ((wolves_alive > 0) & (wolves_alive >= vill_alive))).all()

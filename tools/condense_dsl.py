@@ -11,6 +11,10 @@ tests/test_compiler.py checks (when /root/reference exists) that compiling the r
 the condensed file gives byte-identical tables.
 
 usage: python tools/condense_dsl.py /root/reference/games game_engine_b200/games
+       python tools/condense_dsl.py "/root/reference/game_draft/werewolf-(mafia).yaml" game_engine_b200/games/werewolf-draft.yaml
+(the second form condenses ONE file under another name: the reference's earlier 13-phase werewolf generation,
+ which no reference code loads — utils.py:565 reads games/ only — and which serves here as a third table with a
+ different phase graph, two terminal phases and a different per-player state schema)
 """
 import sys
 import os
@@ -45,6 +49,14 @@ def condense(dsl: dict) -> dict:
 
 def main() -> None:
     src, dst = sys.argv[1], sys.argv[2]
+    if os.path.isfile(src):
+        with open(src, encoding="utf-8") as f:
+            dsl = yaml.safe_load(f)
+        with open(dst, "w", encoding="utf-8") as f:
+            f.write("# condensed by tools/condense_dsl.py from the reference's %s\n" % os.path.relpath(src, "/root/reference"))
+            yaml.safe_dump(condense(dsl), f, sort_keys=False, allow_unicode=True, width=100)
+        print("wrote", dst)
+        return
     os.makedirs(dst, exist_ok=True)
     for fn in sorted(os.listdir(src)):
         if not fn.endswith(".yaml"):
