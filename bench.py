@@ -50,7 +50,10 @@ def parse_args():
     ap.add_argument("--ring", type=int, default=8, help="batches in the ring (footprint must exceed L2)")
     ap.add_argument("--cap", type=int, default=0, help="steps before a batch is re-initialised (0 = by player count)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tps", "tps_generic", "coop"])
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the ring's independent batches are spread over")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the ring's independent batches are spread over")
+    ap.add_argument("--ctas-per-sm", type=int, default=3,
+                    help="persistent grid of a step launch = SMs x this (0 = occupancy limit); small grids let the launches "
+                         "of the ring's other batches be resident at the same time")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--e2e-calls", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -281,6 +284,7 @@ def run_ours(a):
     ring = [SessionBatch(tab, N, first_session_id=sid_base(0, i), seed=a.seed, device=local_rank, kernel=a.kernel) for i in range(R)]
     for i, b in enumerate(ring):
         b.set_stream(streams[i % NS].cuda_stream)
+        b.set_grid(a.ctas_per_sm)
     age = [0] * R
     epoch = [0] * R
     for i, b in enumerate(ring):                     # stagger: batch i starts i*cap/R steps into its games
@@ -453,7 +457,7 @@ def run_ours(a):
         "dtype": "u32", "data": "synthetic",
         "config": {
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
-            "kernel": kern, "streams": NS, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
+            "kernel": kern, "streams": NS, "ctas_per_sm": a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
             "steps_before_reinit": cap, "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
             "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,
         },

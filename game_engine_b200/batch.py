@@ -78,6 +78,11 @@ class SessionBatch:
         (0 steps = off; default (8, 2))."""
         capi.check(capi.lib().ge_batch_set_compaction(self._h, int(every_n_steps), int(min_dead_shift)))
 
+    def set_grid(self, ctas_per_sm: int) -> None:
+        """Persistent grid of the step launches = SMs x ctas_per_sm (0 = as many as fit).  Smaller grids let the
+        launches of other batches on other streams co-reside."""
+        capi.check(capi.lib().ge_batch_set_grid(self._h, int(ctas_per_sm)))
+
     def set_regroup(self, every_n_steps: int, min_mixed_shift: int = 3) -> None:
         """Phase regrouping: check every n steps, counting-sort the active prefix by phase when >= 1/2^shift of
         the tiles are mixed (0 steps = off; on by default for tables with a tie -> re-vote loop)."""

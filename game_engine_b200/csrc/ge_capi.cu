@@ -75,11 +75,12 @@ struct ge_batch {
     uint32_t next_override;       // presence override for the next launch (0 = read the device word)
     int kernel;
     step_fn fn[4];               // by kernel id (COOP, TPS, TPS_GENERIC)
-    int grid[4];
+    int grid[4], occ[4];         // persistent grid size / occupancy limit (CTAs per SM) per kernel id
     uint64_t launches;
 };
 
 static int restore_order(ge_batch* b);
+static int lanes_per_session(const ge_table* t);
 extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixed_shift);
 static int ensure_stage(ge_batch* b, size_t bytes);
 
@@ -722,6 +723,7 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)b->fn[k], 128, 0);
         if (e != cudaSuccess || per_sm < 1) per_sm = 4;
+        b->occ[k] = per_sm;
         const uint64_t warps = k == GE_KERNEL_COOP ? b->n_tiles * (uint64_t)lanes_per_session(t) : b->n_tiles;
         (void)0;
         uint64_t g = (warps + 3) / 4;
@@ -780,6 +782,22 @@ extern "C" int ge_batch_set_compaction(ge_batch* b, int every_n_steps, int min_d
     if (every_n_steps > 0 && b->scan_blocks > 1024) return fail(GE_ERR_UNSUPPORTED, "compaction supports batches up to 2^25 sessions");
     b->compact_every = every_n_steps;
     b->dead_shift = min_dead_shift;
+    return GE_OK;
+}
+
+// Persistent grid of the step launches = SM count x ctas_per_sm (clamped to the kernel's occupancy limit and to
+// the work available); 0 restores the occupancy limit.
+extern "C" int ge_batch_set_grid(ge_batch* b, int ctas_per_sm) {
+    if (!b || ctas_per_sm < 0) return fail(GE_ERR_ARG, "bad arguments to ge_batch_set_grid");
+    for (int k = GE_KERNEL_COOP; k <= GE_KERNEL_TPS_GENERIC; ++k) {
+        int per_sm = b->occ[k];
+        if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
+        const uint64_t warps = k == GE_KERNEL_COOP ? b->n_tiles * (uint64_t)lanes_per_session(b->tab) : b->n_tiles;
+        uint64_t g = (warps + 3) / 4;
+        const uint64_t cap = (uint64_t)b->sm_count * per_sm;
+        if (g > cap) g = cap;
+        b->grid[k] = g < 1 ? 1 : (int)g;
+    }
     return GE_OK;
 }
 
@@ -873,6 +891,10 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
     a.tiles = b->d_tiles; a.n_sessions = b->n; a.n_tiles = b->n_tiles; a.first_sid = b->first_sid; a.seed = b->seed;
     a.stats = b->d_stats; a.presence = b->d_presence; a.n_steps = steps_per_launch;
     a.n_active = b->d_cstate; a.live_mask = b->d_live_mask; a.live_count = b->d_cstate + 5;
+    for (int r = 0; r < 10; ++r) {
+        a.rk[2 * r] = (uint32_t)b->seed + (uint32_t)r * 0x9E3779B9u;
+        a.rk[2 * r + 1] = (uint32_t)(b->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
     // phase regrouping replaces the swap compaction (it also moves finished games behind the live ones)
     const bool regroup = b->regroup_every > 0 && b->kernel != GE_KERNEL_COOP && steps_per_launch == 1;
     a.rg = regroup ? b->d_rg : nullptr;

@@ -63,6 +63,9 @@ struct StepArgs {
     // thread-per-session kernel also adds, per phase index, the sessions that entered it to rg[0..31] and the
     // number of tiles whose live sessions sit in more than one phase to rg[32].  NULL = not collected.
     uint32_t* rg;
+    // Philox round keys (k0 + r*W0, k1 + r*W1 for r = 0..9), expanded once on the host: as kernel parameters they
+    // are constant-bank operands of the round's XOR, so the key schedule costs no instructions.
+    uint32_t rk[20];
 };
 
 __device__ __forceinline__ void publish_presence(const StepArgs& A, uint32_t block_present) {
@@ -83,6 +86,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
         const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// same function with the round keys pre-expanded (StepArgs::rk)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
     }
     return make_uint4(c0, c1, c2, c3);
 }

@@ -193,8 +193,16 @@ struct CtView {
 // phase index entered; `dirty` collects which column groups changed.
 template <int P8, class V>
 __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
-                                           uint32_t k0, uint32_t k1, uint32_t& dirty) {
-    constexpr int NPL = P8 <= 8 ? 4 : P8 <= 16 ? 5 : 6;
+                                           const StepArgs& A, uint32_t& dirty) {
+    // planes of the bit-sliced vote counters: enough for P votes; a build-time table whose phase is the wolves'
+    // vote needs only enough for n_wolves votes
+    constexpr int NPL_FULL = P8 <= 8 ? 4 : P8 <= 16 ? 5 : 6;
+    constexpr int NPL = [] {
+        if constexpr (V::is_const) {
+            if (V::exit_op() == EX_VOTE_KILL) { int w = V::n_wolves(), b = 1; while ((1 << b) <= w) ++b; return b < NPL_FULL ? b : NPL_FULL; }
+        }
+        return NPL_FULL;
+    }();
     const int P = v.n_players();
     const uint32_t ALL = all_mask(P);
     const uint32_t step0 = s.h0 >> 16;
@@ -262,7 +270,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
             uint4 R[P8 / 4];
 #pragma unroll
             for (int b = 0; b < P8 / 4; ++b)
-                R[b] = ((actors >> (4 * b)) & 0xFu) ? philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, k0, k1) : make_uint4(0, 0, 0, 0);
+                R[b] = ((actors >> (4 * b)) & 0xFu) ? philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, A.rk) : make_uint4(0, 0, 0, 0);
             uint32_t rank = 0;
             bool have_first = false;
             nib_used = P8 <= 8;
@@ -300,7 +308,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
             const bool is_first = rem == actors;
             rem &= rem - 1;
             const int blk = p >> 2;
-            if (blk != cur_blk) { r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)blk, k0, k1); cur_blk = blk; }
+            if (blk != cur_blk) { r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)blk, A.rk); cur_blk = blk; }
             const uint32_t r = word_of(r4, p & 3);
             uint32_t choice;
             if (aop == ACT_PICK_PLAYER) {
@@ -369,7 +377,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
 #pragma unroll
         for (int b = 0; b < P8 / 4; ++b) {
             if (4 * b < P) {
-                const uint4 q4 = philox4x32_10(sid_lo, sid_hi, step0, (1u << 16) | (uint32_t)b, k0, k1);
+                const uint4 q4 = philox4x32_10(sid_lo, sid_hi, step0, (1u << 16) | (uint32_t)b, A.rk);
                 key[4 * b] = q4.x; key[4 * b + 1] = q4.y; key[4 * b + 2] = q4.z; key[4 * b + 3] = q4.w;
             } else {
                 key[4 * b] = key[4 * b + 1] = key[4 * b + 2] = key[4 * b + 3] = 0;
@@ -411,32 +419,32 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
 // Generic entry: interpret the run-time table.  Returns the phase entered or -1 for a terminal session.
 template <int P8>
 __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
-                                      uint32_t k0, uint32_t k1, uint32_t& dirty) {
+                                      const StepArgs& A, uint32_t& dirty) {
     const int X = s.h0 & 0xFF;
     if (T.phase[X].kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
-    return w_step_body<P8>(RtView(T, X), X, s, F, sid_lo, sid_hi, k0, k1, dirty);
+    return w_step_body<P8>(RtView(T, X), X, s, F, sid_lo, sid_hi, A, dirty);
 }
 
 // Specialised entry: a warp-uniform switch over the phases of a build-time table.
 template <int P8, class Spec, int X>
 __device__ __forceinline__ int w_step_spec_case(WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
-                                                uint32_t k0, uint32_t k1, uint32_t& dirty) {
+                                                const StepArgs& A, uint32_t& dirty) {
     if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
-    return w_step_body<P8>(CtView<Spec, X>{}, X, s, F, sid_lo, sid_hi, k0, k1, dirty);
+    return w_step_body<P8>(CtView<Spec, X>{}, X, s, F, sid_lo, sid_hi, A, dirty);
 }
 
 template <int P8, class Spec, int X = 0>
 __device__ __forceinline__ int w_step_spec(WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
-                                           uint32_t k0, uint32_t k1, uint32_t& dirty) {
+                                           const StepArgs& A, uint32_t& dirty) {
     if constexpr (X >= Spec::n_phases) {
         return -1;
     } else {
-        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X>(s, F, sid_lo, sid_hi, k0, k1, dirty);
-        return w_step_spec<P8, Spec, X + 1>(s, F, sid_lo, sid_hi, k0, k1, dirty);
+        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X>(s, F, sid_lo, sid_hi, A, dirty);
+        return w_step_spec<P8, Spec, X + 1>(s, F, sid_lo, sid_hi, A, dirty);
     }
 }
 
@@ -513,7 +521,6 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const int lane = threadIdx.x & 31;
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
     // which column groups can any session of this batch need?  (bit0 C1, bit1 C2, bit2 player bytes, bit3 session id)
     const uint32_t present_in = A.presence_override ? A.presence_override : A.presence[A.launch_idx % 3];
     const uint32_t need = A.n_steps > 1 ? 15u : need_of(T, present_in);
@@ -524,6 +531,11 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     uint32_t present_out = 0, live_cnt = 0, mixed = 0;
     VisitAcc visits;
 
+    // Slots [0, n_act): tiles below full_tiles are entirely inside the prefix, the next one has `rem` slots in it.
+    // Tile addresses advance by pointer increments (one 64-bit add per tile instead of a wide multiply per column).
+    const uint32_t full_tiles = (uint32_t)(n_act >> 5), rem = (uint32_t)n_act & 31u;
+    const uint64_t tile_stride = (uint64_t)nwarps * (32 * S);
+    uint8_t* base = A.tiles + (uint64_t)warp0 * (32 * S) + lane * 16;      // column c of this lane: base + c * 512
     if (need == 0) {
         // ---- light path: every present phase touches column 0 only.  Four tiles in flight per warp.
         // Sessions move in lockstep, so usually ONE non-terminal phase x0 is present: its single successor is
@@ -534,43 +546,42 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
             const int x = __ffs(live_present) - 1;
             if (T.phase[x].n_branches == 1 && T.phase[x].br[0].op == BR_ALWAYS) { x0 = x; y0 = T.phase[x].br[0].next; tag0 = T.phase[x].br[0].tag; }
         }
-        const bool y0_live = x0 >= 0 && T.phase[y0].kind != KIND_TERMINAL;
-        for (uint32_t tile = warp0; tile < n_tiles_act; tile += 4 * nwarps) {
+        const bool y0_live = x0 >= 0 && ((T.nonterm >> y0) & 1u);
+        const uint32_t hdr0 = y0 | ((uint32_t)x0 << 8);
+        for (uint32_t tile = warp0; tile < n_tiles_act; tile += 4 * nwarps, base += 4 * tile_stride) {
             uint4 c[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t t = tile + j * nwarps;
-                c[j] = t < n_tiles_act ? ld128(A.tiles + (uint64_t)t * (32 * S) + lane * 16) : make_uint4(0, 0, 0, 0);
-            }
+            for (int j = 0; j < 4; ++j)
+                c[j] = tile + j * nwarps < n_tiles_act ? ld128(base + j * tile_stride) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t t = tile + j * nwarps;
                 if (t < n_tiles_act) {                        // warp-uniform
-                    const bool in_range = (uint64_t)t * 32 + lane < n_act;
+                    const bool in_range = t < full_tiles || (uint32_t)lane < rem;
                     const bool fast = in_range && (int)(c[j].x & 0xFF) == x0 && (c[j].x >> 16) != 0;
-                    int np = -1;
-                    if (fast) {
-                        c[j].x = y0 | ((uint32_t)x0 << 8) | ((c[j].x & 0xFFFF0000u) + 0x10000u);
-                        if (tag0) c[j].y = (c[j].y & ~0xFFu) | tag0;
-                        np = (int)y0;
-                    } else if (in_range) {
-                        np = w_step_light(T, c[j]);
-                    }
-                    const uint32_t stepped = __ballot_sync(0xFFFFFFFFu, np >= 0);
-                    if (np >= 0) st128(A.tiles + (uint64_t)t * (32 * S) + lane * 16, c[j]);
+                    const uint32_t fastm = __ballot_sync(0xFFFFFFFFu, fast);
                     uint32_t lm;
-                    if (__ballot_sync(0xFFFFFFFFu, fast) == stepped) {          // warp-uniform: every stepped lane took the fast route
-                        if (stepped) {
-                            if ((int)y0 != visits.phase) { visits.flush(s_visits, lane); visits.phase = (int)y0; }
-                            visits.count += __popc(stepped);
-                            present_out |= 1u << y0;
-                        }
-                        lm = y0_live ? stepped : 0u;
-                        if (stepped != 0xFFFFFFFFu && in_range && np < 0) present_out |= 1u << (c[j].x & 31);
+                    if (fastm == 0xFFFFFFFFu) {               // whole tile in the common phase: nothing else to look at
+                        c[j].x = hdr0 | ((c[j].x & 0xFFFF0000u) + 0x10000u);
+                        if (tag0) c[j].y = (c[j].y & ~0xFFu) | tag0;
+                        st128(base + j * tile_stride, c[j]);
+                        if ((int)y0 != visits.phase) { visits.flush(s_visits, lane); visits.phase = (int)y0; }
+                        visits.count += 32;
+                        present_out |= 1u << y0;
+                        lm = y0_live ? 0xFFFFFFFFu : 0u;
                     } else {
+                        int np = -1;
+                        if (fast) {
+                            c[j].x = hdr0 | ((c[j].x & 0xFFFF0000u) + 0x10000u);
+                            if (tag0) c[j].y = (c[j].y & ~0xFFu) | tag0;
+                            np = (int)y0;
+                        } else if (in_range) {
+                            np = w_step_light(T, c[j]);
+                        }
+                        if (np >= 0) st128(base + j * tile_stride, c[j]);
                         mixed += visits.add(s_visits, np, lane) > 1;
                         if (in_range) present_out |= 1u << (c[j].x & 31);
-                        lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[c[j].x & 31].kind != KIND_TERMINAL);
+                        lm = __ballot_sync(0xFFFFFFFFu, in_range && ((T.nonterm >> (c[j].x & 31)) & 1u));
                     }
                     if (lane == 0) A.live_mask[t] = lm;
                     live_cnt += __popc(lm);
@@ -578,27 +589,26 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
             }
         }
     } else {
-        for (uint32_t tile = warp0; tile < n_tiles_act; tile += nwarps) {
-            uint8_t* base = A.tiles + (uint64_t)tile * (32 * S);
-            const uint64_t sess = (uint64_t)tile * 32 + lane;
-            const bool in_range = sess < n_act;
-            uint64_t org = sess;
-            if (use_origin && in_range) org = A.origin[sess];
+        for (uint32_t tile = warp0; tile < n_tiles_act; tile += nwarps, base += tile_stride) {
+            const bool in_range = tile < full_tiles || (uint32_t)lane < rem;
+            uint32_t org = tile * 32u + lane;
+            if (use_origin && in_range) org = A.origin[org];
             WState<P8> s;
             // all loads are issued up front (no dependent second round trip)
-            const uint4 c0 = ld128(base + lane * 16);
+            const uint4 c0 = ld128(base);
             uint4 c1 = make_uint4(0, 0, 0, 0), c2 = make_uint4(0, 0, 0, 0);
-            if (need & 1) c1 = ld128(base + 512 + lane * 16);
-            if (need & 2) c2 = ld128(base + 1024 + lane * 16);
+            if (need & 1) c1 = ld128(base + 512);
+            if (need & 2) c2 = ld128(base + 1024);
 #pragma unroll
             for (int c = 0; c < NT16; ++c) {
                 uint4 t = make_uint4(0, 0, 0, 0);
-                if (need & 4) t = ld128(base + (3 + c) * 512 + lane * 16);
+                if (need & 4) t = ld128(base + (3 + c) * 512);
                 s.tw[4 * c] = t.x; s.tw[4 * c + 1] = t.y; s.tw[4 * c + 2] = t.z; s.tw[4 * c + 3] = t.w;
             }
+            uint8_t* const base8 = base - lane * 8 + (3 + NT16) * 512;       // trailing 8-byte column of this lane
             if (THALF) {
                 uint2 t = make_uint2(0, 0);
-                if (need & 4) t = ld64(base + (3 + NT16) * 512 + lane * 8);
+                if (need & 4) t = ld64(base8);
                 s.tw[4 * NT16] = t.x; s.tw[4 * NT16 + 1] = t.y;
             }
             s.h0 = c0.x; s.h1 = c0.y; s.alive = c0.z; s.can_vote = c0.w;
@@ -611,25 +621,25 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
                 int np = -1;
                 if (live) {
                     if constexpr (std::is_void<Spec>::value)
-                        np = w_step<P8>(T, s, F, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                        np = w_step<P8>(T, s, F, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
                     else
-                        np = w_step_spec<P8, Spec>(s, F, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                        np = w_step_spec<P8, Spec>(s, F, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
                     if (np < 0) live = false;
                 }
                 mixed += visits.add(s_visits, np, lane) > 1;
             }
             if (in_range) present_out |= 1u << (s.h0 & 31);
-            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, in_range && T.phase[s.h0 & 31].kind != KIND_TERMINAL);
+            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, in_range && ((T.nonterm >> (s.h0 & 31)) & 1u));
             if (lane == 0) A.live_mask[tile] = lm;
             live_cnt += __popc(lm);
-            if (dirty & DIRTY_C0) st128(base + lane * 16, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
-            if (dirty & DIRTY_C1) st128(base + 512 + lane * 16, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
-            if (dirty & DIRTY_C2) st128(base + 1024 + lane * 16, make_uint4(s.wolf, s.secret, s.role_lo, s.role_hi));
+            if (dirty & DIRTY_C0) st128(base, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
+            if (dirty & DIRTY_C1) st128(base + 512, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
+            if (dirty & DIRTY_C2) st128(base + 1024, make_uint4(s.wolf, s.secret, s.role_lo, s.role_hi));
             if (dirty & DIRTY_PL) {
 #pragma unroll
                 for (int c = 0; c < NT16; ++c)
-                    st128(base + (3 + c) * 512 + lane * 16, make_uint4(s.tw[4 * c], s.tw[4 * c + 1], s.tw[4 * c + 2], s.tw[4 * c + 3]));
-                if (THALF) st64(base + (3 + NT16) * 512 + lane * 8, make_uint2(s.tw[4 * NT16], s.tw[4 * NT16 + 1]));
+                    st128(base + (3 + c) * 512, make_uint4(s.tw[4 * c], s.tw[4 * c + 1], s.tw[4 * c + 2], s.tw[4 * c + 3]));
+                if (THALF) st64(base8, make_uint2(s.tw[4 * NT16], s.tw[4 * NT16 + 1]));
             }
         }
     }
@@ -712,7 +722,7 @@ __device__ __forceinline__ uint32_t t_pred(const V& v, FieldFn field, int pi, ui
 // table; CtView<Spec, X>: a build-time table, every accessor a constant).  Returns the phase entered.
 template <int PB, class V>
 __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi,
-                                           uint32_t k0, uint32_t k1, uint32_t& dirty) {
+                                           const StepArgs& A, uint32_t& dirty) {
     const int P = v.n_players();
     const uint32_t ALL = all_mask(P);
     const uint32_t step0 = s.h0 >> 16;
@@ -766,7 +776,7 @@ __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s
             const uint32_t ab = (actors >> (4 * b)) & 0xFu;
             if (ab) {
                 uint4 r4 = make_uint4(0, 0, 0, 0);
-                if (aop == ACT_PICK_OPTION) r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, k0, k1);     // MARK draws nothing
+                if (aop == ACT_PICK_OPTION) r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, A.rk);     // MARK draws nothing
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int p = 4 * b + j;
@@ -839,16 +849,16 @@ __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s
 
 template <int PB>
 __device__ __forceinline__ int t_step(const DevTable& T, TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi,
-                                      uint32_t k0, uint32_t k1, uint32_t& dirty) {
+                                      const StepArgs& A, uint32_t& dirty) {
     const int X = s.h0 & 0xFF;
     if (T.phase[X].kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
-    return t_step_body<PB>(RtView(T, X), X, s, sid_lo, sid_hi, k0, k1, dirty);
+    return t_step_body<PB>(RtView(T, X), X, s, sid_lo, sid_hi, A, dirty);
 }
 
 template <int PB, class Spec, int X = 0>
-__device__ __forceinline__ int t_step_spec(TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi, uint32_t k0, uint32_t k1, uint32_t& dirty) {
+__device__ __forceinline__ int t_step_spec(TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi, const StepArgs& A, uint32_t& dirty) {
     if constexpr (X >= Spec::n_phases) {
         return -1;
     } else {
@@ -856,9 +866,9 @@ __device__ __forceinline__ int t_step_spec(TState<PB>& s, uint32_t sid_lo, uint3
             if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
             dirty |= DIRTY_C0;
             if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
-            return t_step_body<PB>(CtView<Spec, X>{}, X, s, sid_lo, sid_hi, k0, k1, dirty);
+            return t_step_body<PB>(CtView<Spec, X>{}, X, s, sid_lo, sid_hi, A, dirty);
         }
-        return t_step_spec<PB, Spec, X + 1>(s, sid_lo, sid_hi, k0, k1, dirty);
+        return t_step_spec<PB, Spec, X + 1>(s, sid_lo, sid_hi, A, dirty);
     }
 }
 
@@ -880,7 +890,6 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
     const uint32_t present_in = A.presence_override ? A.presence_override : A.presence[A.launch_idx % 3];
     const uint32_t need = A.n_steps > 1 ? 15u : need_of(T, present_in);
     const bool full = (need & 4u) != 0;
@@ -922,9 +931,9 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
             int np = -1;
             if (live) {
                 if constexpr (std::is_void<Spec>::value)
-                    np = t_step<PB>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                    np = t_step<PB>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
                 else
-                    np = t_step_spec<PB, Spec>(s, (uint32_t)sid, (uint32_t)(sid >> 32), k0, k1, dirty);
+                    np = t_step_spec<PB, Spec>(s, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
                 if (np < 0) live = false;
             }
             visits.add(s_visits, np, lane);

@@ -97,6 +97,12 @@ int ge_batch_set_kernel(ge_batch *b, int kernel);
  * ge_batch_active returns the current prefix length (synchronises). */
 int ge_batch_set_compaction(ge_batch *b, int every_n_steps, int min_dead_shift);
 int ge_batch_active(ge_batch *b, uint64_t *out);
+/* Launch geometry: the step kernels run a persistent grid of (SM count x ctas_per_sm) CTAs of 128 threads, by
+ * default as many as fit (the kernel's occupancy limit, 8 at 8 players).  A smaller grid leaves room for the
+ * step launches of OTHER batches on other streams to be resident at the same time, so that one launch's ramp
+ * and tail overlap another's steady state (ring of 8 batches on 8 streams: 3 CTAs per SM is ~12% faster than 8).
+ * 0 restores the default. */
+int ge_batch_set_grid(ge_batch *b, int ctas_per_sm);
 /* Phase regrouping (thread-per-session werewolf kernels): every `every_n_steps` launches a device-side check runs
  * and, when at least 1/2^min_mixed_shift of the tiles hold sessions in more than one phase (or the compaction
  * threshold of dead sessions is reached), the active prefix is counting-sorted by phase, finished games last, so
