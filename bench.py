@@ -148,6 +148,16 @@ def build_oracle_native():
         return False
 
 
+def host_threads(o) -> int:
+    """Threads the CPU arm uses: every core this process may run on.  torchrun exports OMP_NUM_THREADS=1, which
+    would otherwise throttle the baseline to one thread."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    return max(int(o.max_threads()), cores)
+
+
 def cpu_oracle_rate(cg, n_sessions: int, cap: int, seed: int, threads: int, native: bool):
     """Times Oracle B (the CPU port) on n_sessions full games; returns (steps, seconds)."""
     from oracle.oracle import Oracle
@@ -162,7 +172,7 @@ def cpu_oracle_rate(cg, n_sessions: int, cap: int, seed: int, threads: int, nati
 def cpu_baseline(cg, cap: int, seed: int, target_seconds: float):
     native = build_oracle_native()
     from oracle.oracle import Oracle
-    threads = Oracle(cg.blob, native=native).max_threads()
+    threads = host_threads(Oracle(cg.blob, native=native))
     steps, dt = cpu_oracle_rate(cg, 1 << 13, cap, seed, threads, native)          # calibration
     per_session = dt / (1 << 13)
     n = int(max(1 << 13, min(1 << 22, target_seconds / max(per_session, 1e-9))))
@@ -185,7 +195,7 @@ def run_reference(a):
     cap = a.cap or game_cap(cg.family, a.players, cg.table.max_revotes)
     native = build_oracle_native()
     o = Oracle(cg.blob, native=native)
-    threads = o.max_threads()
+    threads = host_threads(o)
     # size the per-step sample so that K+W steps take about a minute
     steps, dt = cpu_oracle_rate(cg, 1 << 13, cap, a.seed, threads, native)
     per_sess_step = dt / ((1 << 13) * cap)                 # seconds per session per pass (terminal passes are cheap)
