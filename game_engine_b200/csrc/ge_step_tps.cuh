@@ -33,6 +33,7 @@ constexpr int TPS_THREADS = 128;
 struct FieldTable {
     uint32_t (*f)[TPS_THREADS];
     int tid;
+    uint8_t* lut;       // this thread's column of the legal-position table (P8 > 16 only): entry j at lut[j * TPS_THREADS]
     template <int P8>
     __device__ __forceinline__ void fill(const WState<P8>& s, uint32_t ALL) const {
         f[0][tid] = s.alive;      f[1][tid] = s.can_vote;  f[2][tid] = s.eligible;  f[3][tid] = s.submitted;
@@ -72,6 +73,23 @@ struct Tally {
         uint32_t carry = onehot;
 #pragma unroll
         for (int b = 0; b < NPL; ++b) { const uint32_t t = pl[b] & carry; pl[b] ^= carry; carry = t; }
+    }
+    // adds a 3-bit bit-sliced number (one count 0..7 per candidate): full adders on the low planes (one LOP3 per
+    // sum and per carry), half adders above
+    __device__ __forceinline__ void add3(uint32_t b0, uint32_t b1, uint32_t b2) {
+        uint32_t carry;
+        { const uint32_t t = pl[0] & b0; pl[0] ^= b0; carry = t; }
+        if (NPL > 1) { const uint32_t a = pl[1]; pl[1] = a ^ b1 ^ carry; carry = (a & b1) | (a & carry) | (b1 & carry); }
+        if (NPL > 2) { const uint32_t a = pl[2]; pl[2] = a ^ b2 ^ carry; carry = (a & b2) | (a & carry) | (b2 & carry); }
+#pragma unroll
+        for (int b = 3; b < NPL; ++b) { const uint32_t t = pl[b] & carry; pl[b] ^= carry; carry = t; }
+    }
+    // seven one-hot votes -> their per-candidate sum as three bit planes (carry-save adder tree, 8 LOP3), added in
+    __device__ __forceinline__ void add7(const uint32_t (&g)[7]) {
+        const uint32_t s1 = g[0] ^ g[1] ^ g[2], c1 = (g[0] & g[1]) | (g[0] & g[2]) | (g[1] & g[2]);
+        const uint32_t s2 = g[3] ^ g[4] ^ g[5], c2 = (g[3] & g[4]) | (g[3] & g[5]) | (g[4] & g[5]);
+        const uint32_t b0 = s1 ^ s2 ^ g[6], c3 = (s1 & s2) | (s1 & g[6]) | (s2 & g[6]);
+        add3(b0, c1 ^ c2 ^ c3, (c1 & c2) | (c1 & c3) | (c2 & c3));
     }
     // returns the mask of candidates that share the highest (non-zero) count
     __device__ __forceinline__ uint32_t top() const {
@@ -271,33 +289,48 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
 #pragma unroll
             for (int b = 0; b < P8 / 4; ++b)
                 R[b] = ((actors >> (4 * b)) & 0xFu) ? philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, A.rk) : make_uint4(0, 0, 0, 0);
+            if (P8 > 16) {
+                // more than 16 players: the positions of the legal players go to a per-thread byte column in shared
+                // memory (entry j = position of the j-th legal player), a pick is one LDS
+                uint32_t j = 0;
+#pragma unroll
+                for (int q = 0; q < P8; ++q)
+                    if ((legal0 >> q) & 1u) { F.lut[j * TPS_THREADS] = (uint8_t)q; ++j; }
+            }
             uint32_t rank = 0;
             bool have_first = false;
             nib_used = P8 <= 8;
+            uint32_t g[7];                      // P8 > 8: one-hot votes of seven consecutive players (carry-save tally)
 #pragma unroll
             for (int p = 0; p < P8; ++p) {
                 const uint32_t self_in = (legal0 >> p) & 1u;
+                uint32_t vote = 0;
                 if ((actors >> p) & 1u) {
                     const uint32_t r = word_of(R[p >> 2], p & 3);
                     const uint32_t skip = excl & self_in;                 // 1 when this actor must skip itself
                     const uint32_t n = n0 - skip;
                     const uint32_t k = __umulhi(r, n);
+                    const uint32_t j = k + ((skip && k >= rank) ? 1u : 0u);
                     int idx;
-                    if (P8 <= 16) {
-                        const uint32_t j = k + ((skip && k >= rank) ? 1u : 0u);
-                        idx = (int)((lut >> (4 * j)) & 0xFu);
-                    } else {
-                        idx = kth_set_bit<P8>(legal0 & ~(skip << p), k);
-                    }
+                    if (P8 <= 16) idx = (int)((lut >> (4 * j)) & 0xFu);
+                    else idx = n ? (int)F.lut[j * TPS_THREADS] : 0;
                     const uint32_t choice = n ? (uint32_t)idx + 1u : 0u;
                     if (n) {
                         chosen |= 1u << idx;
-                        if (tallying) { if (P8 <= 8) nib += 1u << (4 * idx); else tally.add(1u << idx); }
+                        if (tallying) { if (P8 <= 8) nib += 1u << (4 * idx); else vote = 1u << idx; }
                     }
                     if (!have_first) { first_choice = choice; have_first = true; }
                     if (record) s.tw[p >> 2] = (s.tw[p >> 2] & ~(0xFFu << (8 * (p & 3)))) | (choice << (8 * (p & 3)));
                 }
                 rank += self_in;
+                if (P8 > 8) {
+                    g[p % 7] = vote;
+                    if (p % 7 == 6 || p == P8 - 1) {
+#pragma unroll
+                        for (int i = (p % 7) + 1; i < 7; ++i) g[i] = 0;
+                        tally.add7(g);
+                    }
+                }
             }
         } else {
         uint32_t rem = actors;
@@ -527,7 +560,8 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const uint64_t n_act = *A.n_active;                 // slots beyond it hold only terminal sessions
     const uint32_t n_tiles_act = (uint32_t)((n_act + 31) >> 5);
     const bool use_origin = A.origin != nullptr && (need & 8);
-    const FieldTable F{s_fields, (int)threadIdx.x};
+    __shared__ uint8_t s_lut[P8 > 16 ? P8 : 1][TPS_THREADS];
+    const FieldTable F{s_fields, (int)threadIdx.x, &s_lut[0][P8 > 16 ? threadIdx.x : 0]};
     uint32_t present_out = 0, live_cnt = 0, mixed = 0;
     VisitAcc visits;
 
