@@ -257,14 +257,36 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
+def bind_to_gpu_numa(index: int):
+    """Multi-rank runs: pin this process to the CPUs nearest to its GPU (NVML's ideal CPU affinity) before anything
+    is allocated, so that the pinned host buffers of the end-to-end call sit on the GPU's own NUMA node (what
+    `numactl` does for a production launcher).  Returns the CPU list, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(c for c in (64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1) if c in allowed)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(a):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
+
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -480,6 +502,7 @@ def run_ours(a):
         "clocks": clocks,
         "stats_allreduce_ms": allreduce_ms,
         "host_enqueue_ms": enqueue_ms,
+        "cpu_binding": ("%d CPUs near the GPU (NVML affinity)" % len(numa_cpus)) if numa_cpus else "none",
         "win_rate": {"villagers": float(stats[2]) / max(1.0, float(stats[2] + stats[3])),
                      "werewolves": float(stats[3]) / max(1.0, float(stats[2] + stats[3])),
                      "sessions_finished": int(stats[2] + stats[3])} if cg.family == 1 else None,
