@@ -488,6 +488,16 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
         const ge_phase_t& ph = t->dev.phase[i];
         if (ph.kind > KIND_TERMINAL || ph.n_branches > 4) return fail(GE_ERR_ARG, "bad phase record");
         if (ph.kind != KIND_TERMINAL && ph.n_branches == 0) return fail(GE_ERR_ARG, "non-terminal phase without next_phase");
+        // well-formedness (SPEC.md section 7): effects belong to the table's family and to action phases
+        const bool wolfy = h.family == FAM_WEREWOLF;
+        if (ph.exit_op != EX_NONE && ph.kind != KIND_ACTION) return fail(GE_ERR_ARG, "exit effect on a phase without actors");
+        if (wolfy ? ph.exit_op > EX_DAY_VOTE : (ph.exit_op != EX_NONE && (ph.exit_op < EX_T_STATEMENTS || ph.exit_op > EX_T_VOTES)))
+            return fail(GE_ERR_ARG, "exit effect of another rule family");
+        if (wolfy ? ph.entry_op > EN_NIGHT_RESET : (ph.entry_op != EN_NONE && (ph.entry_op < EN_T_ROUND_START || ph.entry_op > EN_T_FINAL)))
+            return fail(GE_ERR_ARG, "entry effect of another rule family");
+        if (ph.kind == KIND_ACTION && (ph.action_op < ACT_PICK_PLAYER || ph.action_op > ACT_MARK)) return fail(GE_ERR_ARG, "action phase without an action op");
+        if (wolfy && ph.exit_op != EX_NONE && ph.action_op != ACT_PICK_PLAYER) return fail(GE_ERR_ARG, "werewolf exit effects record a chosen player: the action must be PICK_PLAYER");
+        if (!wolfy && ph.kind == KIND_ACTION && ph.action_op == ACT_PICK_PLAYER) return fail(GE_ERR_ARG, "the TTL family has no player picks (PICK_OPTION or MARK)");
         if (ph.kind == KIND_ACTION) {
             if (ph.actor_pred >= h.n_preds) return fail(GE_ERR_ARG, "actor predicate out of range");
             if (ph.action_op == ACT_PICK_PLAYER && ph.action_arg >= h.n_preds) return fail(GE_ERR_ARG, "legal-set predicate out of range");
@@ -500,6 +510,8 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             if (br.op == BR_COUNT_GE && br.arg >= h.n_preds) return fail(GE_ERR_ARG, "branch predicate out of range");
             if (br.op == BR_ALL_VAL_GE && br.a > 2) return fail(GE_ERR_ARG, "value field out of range");
             if (br.op > BR_TIE_PENDING) return fail(GE_ERR_ARG, "unknown branch op");
+            if (h.family == FAM_WEREWOLF ? (br.op == BR_ALL_VAL_GE || br.tag > 2) : br.op == BR_TIE_PENDING)
+                return fail(GE_ERR_ARG, "branch op / winner tag of another rule family");
         }
     }
     // Column groups a step that STARTS in phase i must read besides column 0 (bit0 = dynamic masks C1:

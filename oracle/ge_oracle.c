@@ -53,6 +53,7 @@ static uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); 
 static void wr32(uint8_t *p, uint32_t v) { p[0] = v; p[1] = v >> 8; p[2] = v >> 16; p[3] = v >> 24; }
 static void wr16(uint8_t *p, uint16_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
 
+static int wolfy_counts_bad(const void *tv);
 static int tab_open(tab_t *t, const uint8_t *blob, size_t n) {
     if (n < 32 || memcmp(blob, "GETB", 4) != 0 || rd16(blob + 4) != 1) return -1;
     t->blob = blob;
@@ -61,7 +62,37 @@ static int tab_open(tab_t *t, const uint8_t *blob, size_t n) {
     t->init_masks = rd32(blob + 16);
     if (n < (size_t)(32 + 48 * t->n_phases + 8 * t->n_preds)) return -1;
     if (t->P < 2 || t->P > MAXP || t->n_phases < 1 || t->n_phases > 32) return -1;
+    if (t->family != FAM_WEREWOLF && t->family != FAM_TTL) return -1;
+    /* well-formedness (SPEC.md section 7), the same rules as the CUDA library's ge_table_create */
+    for (int i = 0; i < t->n_phases; ++i) {
+        const uint8_t *ph = blob + 32 + 48 * i;
+        const int kind = ph[1], aop = ph[2], exo = ph[5], eno = ph[6], nbr = ph[7], wolfy = t->family == FAM_WEREWOLF;
+        if (kind > KIND_TERMINAL || nbr > 4 || (kind != KIND_TERMINAL && nbr == 0)) return -1;
+        if (exo != EX_NONE && kind != KIND_ACTION) return -1;
+        if (wolfy ? exo > EX_DAY_VOTE : (exo != EX_NONE && (exo < EX_T_STATEMENTS || exo > EX_T_VOTES))) return -1;
+        if (wolfy ? eno > EN_NIGHT_RESET : (eno != EN_NONE && (eno < EN_T_ROUND_START || eno > EN_T_FINAL))) return -1;
+        if (kind == KIND_ACTION) {
+            if (aop < ACT_PICK_PLAYER || aop > ACT_MARK || ph[8] >= t->n_preds) return -1;
+            if (aop == ACT_PICK_PLAYER && ph[3] >= t->n_preds) return -1;
+            if (aop == ACT_PICK_OPTION && ph[3] == 0) return -1;
+            if (wolfy && exo != EX_NONE && aop != ACT_PICK_PLAYER) return -1;
+            if (!wolfy && aop == ACT_PICK_PLAYER) return -1;
+        }
+        for (int b = 0; b < nbr; ++b) {
+            const uint8_t *br = ph + 16 + 8 * b;
+            if (br[0] > BR_TIE_PENDING || br[1] >= t->n_phases) return -1;
+            if ((br[0] == BR_COUNT_EQ0 || br[0] == BR_COUNT_GE) && br[3] >= t->n_preds) return -1;
+            if (br[0] == BR_COUNT_GE && rd32(br + 4) >= (uint32_t)t->n_preds) return -1;
+            if (br[0] == BR_ALL_VAL_GE && br[3] > 2) return -1;
+            if (wolfy ? (br[0] == BR_ALL_VAL_GE || br[2] > 2) : br[0] == BR_TIE_PENDING) return -1;
+        }
+    }
+    if (wolfy_counts_bad(t)) return -1;
     return 0;
+}
+static int wolfy_counts_bad(const void *tv) {
+    const tab_t *t = (const tab_t *)tv;
+    return t->family == FAM_WEREWOLF && (t->n_wolves < 1 || t->n_wolves + 2 > t->P);
 }
 static const uint8_t *tab_phase(const tab_t *t, int i) { return t->blob + 32 + 48 * i; }
 static const uint8_t *tab_branch(const tab_t *t, int i, int b) { return tab_phase(t, i) + 16 + 8 * b; }
