@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--ctas-per-sm", type=int, default=3,
                     help="persistent grid of a step launch = SMs x this (0 = occupancy limit); small grids let the launches "
                          "of the ring's other batches be resident at the same time")
+    ap.add_argument("--regroup", default="", help="phase regrouping 'every,shift' (default: the library's choice for the table)")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--e2e-calls", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -317,6 +318,8 @@ def run_ours(a):
     for i, b in enumerate(ring):
         b.set_stream(streams[i % NS].cuda_stream)
         b.set_grid(a.ctas_per_sm)
+        if a.regroup:
+            b.set_regroup(*[int(x) for x in a.regroup.split(",")])
     age = [0] * R
     epoch = [0] * R
     for i, b in enumerate(ring):                     # stagger: batch i starts i*cap/R steps into its games
@@ -413,6 +416,39 @@ def run_ours(a):
         ms_max, counted_all, launches_all = ms, float(counted), int(launches)
     value = counted_all / (ms_max * 1e-3)
 
+    # ---- fused mode, reported separately (never the roofline number): whole games of one fresh 2^20-session batch per
+    #      launch, state in registers across the steps (ge_run_fused) — what a run-to-completion user gets on the device
+    fused = None
+    if not a.no_e2e:
+        fb = [SessionBatch(tab, N, first_session_id=sid_base((1 << 19) + j, 0), seed=a.seed, device=local_rank, kernel=a.kernel)
+              for j in range(4)]
+        for j, b in enumerate(fb):
+            b.set_stream(streams[j % NS].cuda_stream)
+            b.run_fused(cap)
+        torch.cuda.synchronize()
+        f0 = sum(b.counted_steps() for b in fb)
+        for b in fb:
+            b.reset()
+        torch.cuda.synchronize()
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fe0.record(stream)
+        for st in streams[1:]:
+            st.wait_event(fe0)
+        for b in fb:
+            b.run_fused(cap)
+        for st in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(st)
+            stream.wait_event(e)
+        fe1.record(stream)
+        torch.cuda.synchronize()
+        f_counted = sum(b.counted_steps() for b in fb) - f0
+        fused = {"value": f_counted / (fe0.elapsed_time(fe1) * 1e-3), "unit": UNIT,
+                 "note": "ge_run_fused: %d steps per launch, state in registers; 4 fresh batches of %d sessions; per GPU, "
+                         "not part of value / roofline" % (cap, N)}
+        for b in fb:
+            b.close()
+
     # ---- e2e: the public host-buffer call (H2D of the initial records, `cap` steps, D2H of the final
     #      records + statistics), pinned host memory, wall clock around synchronous calls
     e2e = None
@@ -498,6 +534,7 @@ def run_ours(a):
                      "algorithmic_bytes_per_step": B, "kernel": "k_step_%s_%s" % ("w" if cg.family == 1 else "t", kern),
                      "steps_per_launch": counted_all / world / a.steps},
         "e2e": e2e,
+        "fused": fused,
         "gpu_launches": launches_all,
         "clocks": clocks,
         "stats_allreduce_ms": allreduce_ms,

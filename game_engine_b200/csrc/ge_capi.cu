@@ -737,7 +737,6 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
         if (e != cudaSuccess || per_sm < 1) per_sm = 4;
         b->occ[k] = per_sm;
         const uint64_t warps = k == GE_KERNEL_COOP ? b->n_tiles * (uint64_t)lanes_per_session(t) : b->n_tiles;
-        (void)0;
         uint64_t g = (warps + 3) / 4;
         const uint64_t cap = (uint64_t)b->sm_count * per_sm;      // persistent grid: whole multiples of the SM count
         if (g > cap) g = cap;
@@ -1144,18 +1143,8 @@ extern "C" int ge_run_host_async(ge_batch* b, const void* records_in, void* reco
 }
 
 extern "C" int ge_run_host(ge_batch* b, const void* records_in, void* records_out, int n_steps, uint64_t* host_stats) {
-    if (!b || n_steps < 0) return fail(GE_ERR_ARG, "bad arguments to ge_run_host");
-    CU(cudaSetDevice(b->device));
-    int rc;
-    if (records_in && (rc = import_async(b, 0, b->n, records_in)) != GE_OK) return rc;
-    if (b->host_fused && n_steps > 1) rc = launch_steps(b, 1, n_steps, b->stream);
-    else rc = launch_steps(b, n_steps, 1, b->stream);
+    const int rc = ge_run_host_async(b, records_in, records_out, n_steps, host_stats);
     if (rc != GE_OK) return rc;
-    if (records_out && (rc = export_async(b, 0, b->n, records_out)) != GE_OK) return rc;
-    if (host_stats) {
-        if ((rc = ge_stats_refresh(b, nullptr)) != GE_OK) return rc;
-        CU(cudaMemcpyAsync(host_stats, b->d_stats_out, GE_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
-    }
     CU(cudaStreamSynchronize(b->stream));
     return GE_OK;
 }

@@ -179,3 +179,60 @@ def test_reference_draft_yaml_compiles_to_identical_table():
         ref = yaml.safe_load(f)
     a, b = compile_game(DRAFT, 12, dsl=ref), compile_game(DRAFT, 12)
     assert a.blob == b.blob and a.phase_names == b.phase_names and a.template == b.template and a.audience_preds == b.audience_preds
+
+
+# ---- property: the DNF compiler agrees with a direct evaluation of the condition on random player states
+def _random_condition(rng, depth=0):
+    fields = ["is_alive", "can_vote", "night_action_eligible", "night_action_submitted", "role_revealed", "has_secret_role"]
+    r = rng.random()
+    if depth >= 2 or r < 0.45:
+        k = rng.integers(0, 4)
+        if k == 0:
+            return "player.%s %s %s" % (fields[rng.integers(0, len(fields))], ["==", "!="][rng.integers(0, 2)], ["true", "false"][rng.integers(0, 2)])
+        if k == 1:
+            return "player.role %s '%s'" % (["==", "!="][rng.integers(0, 2)], ["Villager", "Werewolf", "Doctor", "Detective"][rng.integers(0, 4)])
+        if k == 2:
+            return "player.team %s '%s'" % (["==", "!="][rng.integers(0, 2)], ["werewolves", "villagers"][rng.integers(0, 2)])
+        roles = ["Villager", "Werewolf", "Doctor", "Detective"]
+        pick = [roles[i] for i in sorted(rng.choice(4, size=2, replace=False))]
+        return "player.role in ['%s', '%s']" % tuple(pick)
+    if r < 0.6:
+        return "not (%s)" % _random_condition(rng, depth + 1)
+    op = "and" if r < 0.85 else "or"
+    return "(%s) %s (%s)" % (_random_condition(rng, depth + 1), op, _random_condition(rng, depth + 1))
+
+
+def test_dnf_compiler_agrees_with_direct_evaluation():
+    import re
+    import numpy as np
+    roles = ["Villager", "Werewolf", "Doctor", "Detective"]
+    fm = C._FieldMap(T.FAMILY_WEREWOLF, roles, "werewolves", "villagers")
+    rng = np.random.default_rng(2026)
+    checked = 0
+    for _ in range(600):
+        cond = _random_condition(rng)
+        try:
+            pred = C.compile_predicate(cond, fm)
+        except DSLCompileError:
+            continue                                  # more than two DNF clauses: rejected, never mis-compiled
+        src = re.sub(r"\btrue\b", "True", re.sub(r"\bfalse\b", "False", cond))
+        for _ in range(24):
+            assigned = bool(rng.integers(0, 2))
+            role = roles[rng.integers(0, 4)] if assigned else ""
+            st = {"is_alive": bool(rng.integers(0, 2)), "can_vote": bool(rng.integers(0, 2)),
+                  "night_action_eligible": bool(rng.integers(0, 2)), "night_action_submitted": bool(rng.integers(0, 2)),
+                  "role_revealed": bool(rng.integers(0, 2)), "has_secret_role": assigned and role != "Villager",
+                  "role": role, "team": ("werewolves" if role == "Werewolf" else "villagers") if assigned else ""}
+            want = bool(eval(src, {"__builtins__": {}}, {"player": type("P", (), st)}))
+            # mask fields of ONE player (bit 0), SPEC section 2
+            f = {0: st["is_alive"], 1: st["can_vote"], 2: st["night_action_eligible"], 3: st["night_action_submitted"],
+                 4: st["role_revealed"], 5: False, 6: st["team"] == "werewolves", 7: st["has_secret_role"],
+                 8: assigned and role == "Villager", 9: role == "Werewolf", 10: role == "Doctor", 11: role == "Detective",
+                 12: assigned, 15: True}
+            got = False
+            for pos, neg in ((pred[0], pred[1]), (pred[2], pred[3])):
+                ok = all(f.get(b, False) for b in range(16) if (pos >> b) & 1) and not any(f.get(b, False) for b in range(16) if (neg >> b) & 1)
+                got = got or ok
+            assert got == want, (cond, st, pred)
+            checked += 1
+    assert checked > 3000
