@@ -10,7 +10,8 @@
  *   - PhaseNode            agent/game_agent_v2.py:987-1241 (+ prompt/PhaseNode_system_prompt.txt)
  *   - RefereeNode          agent/game_agent_v2.py:619-803  (+ prompt/referee_system_prompt_{1,2}.txt)
  *   - _execute_update_player_state  agent/tools/backend_tools.py:204-225 (field writes)
- *   - phase graphs         games/werewolf-(mafia).yaml:166-666, games/two-truths-and-a-lie.yaml:145-403
+ *   - phase graphs         games/werewolf-(mafia).yaml:166-666, games/two-truths-and-a-lie.yaml:145-403,
+ *                          game_draft/werewolf-(mafia).yaml:146-430 (third table)
  * with every decision the reference leaves to its LLM frozen by /root/repo/SPEC.md.
  *
  * PARITY STATUS: the reference has no executable tests, golden vectors or fixtures for this path

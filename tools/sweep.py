@@ -19,6 +19,8 @@ from game_engine_b200.batch import SessionBatch, Table  # noqa: E402
 def run(game, P, n, kernel, cap, ring, stream):
     cg = compile_game(game, P)
     tab = Table(cg)
+    fused = kernel.endswith("-fused")           # whole game in ONE launch per batch (ge_run_fused), state in registers
+    kernel = kernel.replace("-fused", "")
     bs = [SessionBatch(tab, n, first_session_id=i * n, seed=5, kernel=kernel) for i in range(ring)]
     for b in bs:
         b.set_stream(stream.cuda_stream)
@@ -29,9 +31,13 @@ def run(game, P, n, kernel, cap, ring, stream):
     c0 = sum(b.counted_steps() for b in bs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(cap):
+    if fused:
         for b in bs:
-            b.step(1)
+            b.run_fused(cap)
+    else:
+        for _ in range(cap):
+            for b in bs:
+                b.step(1)
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -56,6 +62,9 @@ def main():
         ring = max(1, min(8, (512 << 20) // (n * 24)))
         c, ms, S, unfinished = run("two-truths-and-a-lie", 4, n, "tps", 34, ring, stream)
         rows.append(("two-truths-and-a-lie", 4, n, ring, "tps", c, ms, S, unfinished))
+        if lg <= 20:                            # launch-bound sizes: the fused launch is the right call
+            c, ms, S, unfinished = run("two-truths-and-a-lie", 4, n, "tps-fused", 34, ring, stream)
+            rows.append(("two-truths-and-a-lie", 4, n, ring, "tps-fused", c, ms, S, unfinished))
     for game, P, n, cap in (("werewolf-(mafia)", 8, 1 << 20, 56), ("werewolf-(mafia)", 16, 1 << 20, 128),
                             ("werewolf-(mafia)", 32, 1 << 20, 272), ("werewolf-revote", 32, 1 << 20, 392),
                             ("werewolf-(mafia)", 16, 1 << 24, 128), ("werewolf-(mafia)", 32, 1 << 23, 272)):
