@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--ctas-per-sm", type=int, default=3,
                     help="persistent grid of a step launch = SMs x this (0 = occupancy limit); small grids let the launches "
                          "of the ring's other batches be resident at the same time")
+    ap.add_argument("--autoreset", action="store_true",
+                    help="re-initialise a batch on the device as soon as all its games are over (ge_batch_set_autoreset) instead "
+                         "of from the host after `cap` steps; measured: no gain at 2^20 sessions (some game always runs to the cap)")
     ap.add_argument("--regroup", default="", help="phase regrouping 'every,shift' (default: the library's choice for the table)")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--e2e-calls", type=int, default=6)
@@ -320,6 +323,14 @@ def run_ours(a):
         b.set_grid(a.ctas_per_sm)
         if a.regroup:
             b.set_regroup(*[int(x) for x in a.regroup.split(",")])
+    # Steady state: a batch whose games are all over starts over with fresh session ids — from the host after `cap`
+    # steps (the longest possible game; default) or, with --autoreset, on the device as soon as the periodic
+    # compaction check finds no live session (ge_batch_set_autoreset).
+    auto = a.autoreset and a.kernel != "coop"
+    if auto:
+        for b in ring:
+            b.set_autoreset(world * R * N)           # sid_base(epoch + 1, slot) - sid_base(epoch, slot)
+    host_cap = (1 << 60) if auto else cap
     age = [0] * R
     epoch = [0] * R
     for i, b in enumerate(ring):                     # stagger: batch i starts i*cap/R steps into its games
@@ -338,13 +349,13 @@ def run_ours(a):
         nonlocal k_global, resets
         while n > 0:
             i = k_global % R
-            if age[i] >= cap:
+            if age[i] >= host_cap:
                 epoch[i] += 1
                 ring[i].reset(first_session_id=sid_base(epoch[i], i))
                 age[i] = 0
                 resets += 1
             run = 0                                   # launches until some batch hits the cap, walking from slot i
-            while run < n and age[(i + run) % R] + (run // R) < cap:
+            while run < n and age[(i + run) % R] + (run // R) < host_cap:
                 run += 1
             run = max(run, 1)
             head = min(run, (R - i) % R)              # finish the current round first
@@ -364,6 +375,7 @@ def run_ours(a):
     torch.cuda.synchronize()
     counted0 = sum(b.counted_steps() for b in ring)
     launches0 = sum(b.launch_count() for b in ring)
+    epochs0 = sum(b.epochs() for b in ring) if auto else 0
     agg = torch.zeros(560, dtype=torch.int64, device=dev)
 
     sampler = ClockSampler(local_rank)
@@ -392,6 +404,8 @@ def run_ours(a):
 
     counted = sum(b.counted_steps() for b in ring) - counted0
     launches = sum(b.launch_count() for b in ring) - launches0
+    if auto:
+        resets = sum(b.epochs() for b in ring) - epochs0
 
     # the job's only exchange step: statistics all-reduce (win rate + phase-length histogram) over NCCL
     t_ar0 = time.perf_counter()
@@ -526,7 +540,8 @@ def run_ours(a):
         "config": {
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
             "kernel": kern, "streams": NS, "ctas_per_sm": a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
-            "steps_before_reinit": cap, "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
+            "steps_before_reinit": "when every game of the batch is over (device-side auto-reset, checked every 8 steps)" if auto else cap,
+            "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
             "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -83,6 +83,17 @@ class SessionBatch:
         launches of other batches on other streams co-reside."""
         capi.check(capi.lib().ge_batch_set_grid(self._h, int(ctas_per_sm)))
 
+    def set_autoreset(self, sid_stride: int) -> None:
+        """Continuous simulation: when every game of the batch is over it restarts on the device with session ids
+        first_session_id + epoch * sid_stride + i (0 = off; needs compaction or regrouping on)."""
+        capi.check(capi.lib().ge_batch_set_autoreset(self._h, int(sid_stride)))
+
+    def epochs(self) -> int:
+        """Device-side re-initialisations so far (synchronises)."""
+        v = ctypes.c_uint64()
+        capi.check(capi.lib().ge_batch_epochs(self._h, ctypes.byref(v)))
+        return int(v.value)
+
     def set_regroup(self, every_n_steps: int, min_mixed_shift: int = 3) -> None:
         """Phase regrouping: check every n steps, counting-sort the active prefix by phase when >= 1/2^shift of
         the tiles are mixed (0 steps = off; on by default for tables with a tie -> re-vote loop)."""

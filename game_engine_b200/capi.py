@@ -33,6 +33,8 @@ SYMBOLS = [
     ("ge_batch_set_compaction", _int, [_vp, _int, _int]),
     ("ge_batch_set_regroup", _int, [_vp, _int, _int]),
     ("ge_batch_set_grid", _int, [_vp, _int]),
+    ("ge_batch_set_autoreset", _int, [_vp, _u64]),
+    ("ge_batch_epochs", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_active", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_active_hint", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_get_kernel", _int, [_vp]),

@@ -70,6 +70,7 @@ struct ge_batch {
     uint8_t* d_rg_tiles;          // scratch session store (same size as d_tiles)
     uint32_t* d_rg_origin;
     int regroup_every, rg_mixed_shift;
+    uint64_t sid_stride;          // auto-reset: session ids of device epoch e start at first_sid + e * sid_stride (0 = off)
     uint32_t* d_presence;         // 3 rotating phase-presence words (StepArgs::presence)
     uint32_t launch_idx;          // index of the next step launch
     uint32_t next_override;       // presence override for the next launch (0 = read the device word)
@@ -133,41 +134,81 @@ __global__ void k_import(uint8_t* tiles, uint32_t S_dev, uint32_t S_canon, uint6
     }
 }
 
-// final-state histograms (SPEC.md section 6): winner, length, survivors / scores
-__global__ void __launch_bounds__(256)
-k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev, uint64_t n, unsigned long long* stats) {
-    __shared__ uint32_t sh[3 + 256 + 256];
-    for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
+// final-state histograms (SPEC.md section 6): winner, length, survivors / scores.  sh = 515 shared counters.
+__device__ __forceinline__ void stats_one(const DevTable& T, const uint8_t* tiles, uint32_t S_dev, uint64_t i, uint32_t* sh) {
     const uint32_t n16 = S_dev / 16;
     const int P = T.h.n_players;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
-        const uint32_t sl = (uint32_t)(i & 31);
-        const uint4 c0 = *reinterpret_cast<const uint4*>(base + sl * 16);
-        const bool terminal = T.phase[c0.x & 31].kind == KIND_TERMINAL;
-        const uint32_t step = c0.x >> 16;
-        if (T.h.family == FAM_WEREWOLF) {
-            const uint32_t w = c0.y & 0xFF;
-            atomicAdd(&sh[w <= 2 ? w : 0], 1u);
-            if (terminal) atomicAdd(&sh[3 + 256 + __popc(c0.z)], 1u);
-        } else {
-            atomicAdd(&sh[terminal ? 1 : 0], 1u);
-            if (terminal)
-                for (int p = 0; p < P; ++p) {
-                    const uint32_t pw = *reinterpret_cast<const uint32_t*>(base + rt_tile_off(8 + 4 * p, sl, n16));
-                    atomicAdd(&sh[3 + 256 + (pw & 0xFF)], 1u);
-                }
-        }
-        if (terminal) atomicAdd(&sh[3 + (step < 255 ? step : 255)], 1u);
+    const uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
+    const uint32_t sl = (uint32_t)(i & 31);
+    const uint4 c0 = *reinterpret_cast<const uint4*>(base + sl * 16);
+    const bool terminal = T.phase[c0.x & 31].kind == KIND_TERMINAL;
+    const uint32_t step = c0.x >> 16;
+    if (T.h.family == FAM_WEREWOLF) {
+        const uint32_t w = c0.y & 0xFF;
+        atomicAdd(&sh[w <= 2 ? w : 0], 1u);
+        if (terminal) atomicAdd(&sh[3 + 256 + __popc(c0.z)], 1u);
+    } else {
+        atomicAdd(&sh[terminal ? 1 : 0], 1u);
+        if (terminal)
+            for (int p = 0; p < P; ++p) {
+                const uint32_t pw = *reinterpret_cast<const uint32_t*>(base + rt_tile_off(8 + 4 * p, sl, n16));
+                atomicAdd(&sh[3 + 256 + (pw & 0xFF)], 1u);
+            }
     }
-    __syncthreads();
+    if (terminal) atomicAdd(&sh[3 + (step < 255 ? step : 255)], 1u);
+}
+__device__ __forceinline__ void stats_flush(const uint32_t* sh, unsigned long long* stats) {
     for (int i = threadIdx.x; i < 515; i += blockDim.x) {
         const uint32_t v = sh[i];
         if (!v) continue;
         const int dst = i < 3 ? ST_WINNER + i : i < 259 ? ST_LENGTH + (i - 3) : ST_TAIL + (i - 259);
         atomicAdd(&stats[dst], (unsigned long long)v);
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev, uint64_t n, unsigned long long* stats) {
+    __shared__ uint32_t sh[3 + 256 + 256];
+    for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        stats_one(T, tiles, S_dev, i, sh);
+    __syncthreads();
+    stats_flush(sh, stats);
+}
+
+// Auto-reset (ge_batch_set_autoreset): when the check that follows a counted step finds no live session left
+// (n_active == 0), the batch starts over ON THE DEVICE with fresh session ids, no host round trip:
+// k_autoreset_apply folds the finished sessions' histograms into the accumulator and rewrites every slot with the
+// initial record (slot order back to identity); k_autoreset_commit then republishes n_active, bumps the device
+// epoch (session id = first_sid + epoch * sid_stride + index) and announces "phase 0" to the next launch.
+// Both are no-ops (one uniform load) while games are still running.
+__global__ void __launch_bounds__(256)
+k_autoreset_apply(const __grid_constant__ DevTable T, uint8_t* tiles, uint32_t S_dev, uint64_t n, uint64_t n_tiles,
+                  const __grid_constant__ InitRec rec, uint32_t* origin, unsigned long long* stats, const unsigned long long* cstate) {
+    __shared__ uint32_t sh[3 + 256 + 256];
+    if (cstate[0] != 0) return;
+    for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t n16 = S_dev / 16;
+    const uint64_t total = n_tiles * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (i < n) stats_one(T, tiles, S_dev, i, sh);            // read the finished game first ...
+        uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
+        const uint32_t sl = (uint32_t)(i & 31);
+        for (uint32_t k = 0; k < S_dev / 8; ++k)                   // ... then overwrite the same slot
+            *reinterpret_cast<uint2*>(base + rt_tile_off(8 * k, sl, n16)) = make_uint2(rec.w[2 * k], rec.w[2 * k + 1]);
+        origin[i] = (uint32_t)i;
+    }
+    __syncthreads();
+    stats_flush(sh, stats);
+}
+
+__global__ void k_autoreset_commit(unsigned long long* cstate, uint32_t* presence, uint32_t* rg, uint32_t next_launch_idx, unsigned long long n) {
+    if (threadIdx.x != 0 || cstate[0] != 0) return;
+    cstate[0] = n; cstate[5] = 0; cstate[8] += 1;
+    presence[next_launch_idx % 3] = 1u;                            // every session is in phase index 0
+    if (rg) for (int i = 0; i <= 33; ++i) rg[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------ compaction
@@ -186,7 +227,8 @@ __global__ void k_iota(uint32_t* origin, uint64_t n) {
 }
 
 __global__ void k_cstate_reset(unsigned long long* cstate, unsigned long long n, unsigned long long epoch) {
-    if (threadIdx.x < 8) cstate[threadIdx.x] = threadIdx.x == 0 ? n : threadIdx.x == 7 ? epoch : 0ull;   // [7] = epoch tag
+    // [7] = host epoch tag, [8] = number of device-side re-initialisations (auto-reset) since the last host one
+    if (threadIdx.x < 16) cstate[threadIdx.x] = threadIdx.x == 0 ? n : threadIdx.x == 7 ? epoch : 0ull;
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t* total) {
@@ -714,7 +756,7 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (e == cudaSuccess) e = cudaMalloc(&b->d_live_mask, mask_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(b->d_live_mask, 0, mask_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_prefix, mask_words * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_cstate, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_cstate, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc(&b->h_hint, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) { b->h_hint[0] = n_sessions; b->h_hint[1] = 0; }
     b->scan_blocks = (int)((b->n_tiles + CS_TILES - 1) / CS_TILES);
@@ -835,6 +877,21 @@ extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixe
     return GE_OK;
 }
 
+extern "C" int ge_batch_set_autoreset(ge_batch* b, uint64_t sid_stride) {
+    if (!b) return fail(GE_ERR_ARG, "batch is NULL");
+    if (sid_stride != 0 && sid_stride < b->n) return fail(GE_ERR_ARG, "sid_stride must be 0 (off) or >= n_sessions (ids of different epochs must not overlap)");
+    b->sid_stride = sid_stride;
+    return GE_OK;
+}
+
+extern "C" int ge_batch_epochs(ge_batch* b, uint64_t* out) {
+    if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_batch_epochs");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(out, b->d_cstate + 8, sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return GE_OK;
+}
+
 extern "C" int ge_batch_set_host_fused(ge_batch* b, int on) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     b->host_fused = on != 0;
@@ -902,6 +959,7 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
     a.tiles = b->d_tiles; a.n_sessions = b->n; a.n_tiles = b->n_tiles; a.first_sid = b->first_sid; a.seed = b->seed;
     a.stats = b->d_stats; a.presence = b->d_presence; a.n_steps = steps_per_launch;
     a.n_active = b->d_cstate; a.live_mask = b->d_live_mask; a.live_count = b->d_cstate + 5;
+    a.sid_stride = b->sid_stride;
     for (int r = 0; r < 10; ++r) {
         a.rk[2 * r] = (uint32_t)b->seed + (uint32_t)r * 0x9E3779B9u;
         a.rk[2 * r + 1] = (uint32_t)(b->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
@@ -931,6 +989,15 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
         } else if (compact_after) {
             const int rc = enqueue_compaction(b, st);
             if (rc != GE_OK) return rc;
+        }
+        if ((regroup_after || compact_after) && b->sid_stride != 0) {      // every game over? start the next epoch on the device
+            InitRec rec;
+            memcpy(rec.w, b->tab->init_words, sizeof rec.w);
+            k_autoreset_apply<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(
+                b->tab->dev, b->d_tiles, (uint32_t)b->tab->rec_dev, b->n, b->n_tiles, rec, b->d_origin, b->d_stats, b->d_cstate);
+            k_autoreset_commit<<<1, 32, 0, st>>>(b->d_cstate, b->d_presence, regroup ? b->d_rg : nullptr, b->launch_idx, b->n);
+            CU(cudaGetLastError());
+            b->launches += 2;
         }
     }
     CU(cudaGetLastError());

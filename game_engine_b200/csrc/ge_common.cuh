@@ -66,7 +66,14 @@ struct StepArgs {
     // Philox round keys (k0 + r*W0, k1 + r*W1 for r = 0..9), expanded once on the host: as kernel parameters they
     // are constant-bank operands of the round's XOR, so the key schedule costs no instructions.
     uint32_t rk[20];
+    // Auto-reset (ge_capi.cu, k_autoreset_*): n_active[8] counts the device-side re-initialisations; the session
+    // in slot i then has id first_sid + n_active[8] * sid_stride + origin[i].  0 = off.
+    uint64_t sid_stride;
 };
+
+__device__ __forceinline__ uint64_t first_sid_of(const StepArgs& A) {
+    return A.sid_stride ? A.first_sid + A.n_active[8] * A.sid_stride : A.first_sid;
+}
 
 __device__ __forceinline__ void publish_presence(const StepArgs& A, uint32_t block_present) {
     // called by all threads after a __syncthreads() that orders the block's shared accumulation

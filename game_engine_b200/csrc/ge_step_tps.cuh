@@ -558,6 +558,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const uint32_t present_in = A.presence_override ? A.presence_override : A.presence[A.launch_idx % 3];
     const uint32_t need = A.n_steps > 1 ? 15u : need_of(T, present_in);
     const uint64_t n_act = *A.n_active;                 // slots beyond it hold only terminal sessions
+    const uint64_t sid0 = first_sid_of(A);
     const uint32_t n_tiles_act = (uint32_t)((n_act + 31) >> 5);
     const bool use_origin = A.origin != nullptr && (need & 8);
     __shared__ uint8_t s_lut[P8 > 16 ? P8 : 1][TPS_THREADS];
@@ -649,7 +650,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
             s.eligible = c1.x; s.submitted = c1.y; s.revealed = c1.z; s.investigated = c1.w;
             s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
             bool live = in_range;
-            const uint64_t sid = A.first_sid + org;
+            const uint64_t sid = sid0 + org;
             uint32_t dirty = 0;
             for (int it = 0; it < A.n_steps; ++it) {
                 int np = -1;
@@ -929,6 +930,7 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const bool full = (need & 4u) != 0;
     const bool use_origin = A.origin != nullptr && (need & 8u);
     const uint64_t n_act = *A.n_active;
+    const uint64_t sid0 = first_sid_of(A);
     const uint64_t n_tiles_act = (n_act + 31) >> 5;
     uint32_t present_out = 0;
     VisitAcc visits;
@@ -959,7 +961,7 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
 #pragma unroll
         for (int p = 0; p < PB; ++p) s.pw[p] = w[2 + p];
         bool live = in_range;
-        const uint64_t sid = A.first_sid + org;
+        const uint64_t sid = sid0 + org;
         uint32_t dirty = 0;
         for (int it = 0; it < A.n_steps; ++it) {
             int np = -1;

@@ -111,6 +111,14 @@ int ge_batch_set_grid(ge_batch *b, int ctas_per_sm);
  * automatically (8, 3) for tables that use the TIE_PENDING branch.  Costs a second session store.  Results,
  * session ids, export order and statistics are unaffected.  every_n_steps = 0 turns it off. */
 int ge_batch_set_regroup(ge_batch *b, int every_n_steps, int min_mixed_shift);
+/* Auto-reset (continuous simulation): with sid_stride != 0, whenever the compaction / regrouping check finds that
+ * every game of the batch is over, the batch starts its next EPOCH on the device — final-state histograms folded
+ * into the statistics, all slots re-initialised, session i gets id first_session_id + epoch * sid_stride + i — with
+ * no host round trip and no launches wasted on finished games.  Needs compaction or regrouping on (the thread-per-
+ * session kernels); sid_stride must be >= n_sessions.  ge_batch_reset returns to epoch 0.  ge_batch_epochs
+ * reports the number of device-side re-initialisations so far (synchronises). */
+int ge_batch_set_autoreset(ge_batch *b, uint64_t sid_stride);
+int ge_batch_epochs(ge_batch *b, uint64_t *out);
 /* Non-blocking variant: the value an asynchronous copy brought to the host after the most recent completed
  * compaction of the current epoch (an upper bound that only decreases; n_sessions until the first one).
  * 0 means every game of the batch is over — the cue to re-initialise it without waiting for a step cap. */

@@ -302,3 +302,48 @@ def test_phase_regrouping_is_invisible(games, oracle_for, game, P, n):
     every.step(30)
     o.step(rec2, first + n, seed, 30)
     np.testing.assert_array_equal(every.export_state(), rec2)
+
+
+@pytest.mark.parametrize("game,P,every,regroup", [(WEREWOLF, 8, 4, False), (TTL, 4, 8, False), (REVOTE, 8, 4, True), (DRAFT, 6, 2, False)])
+def test_autoreset_runs_epochs_on_the_device(games, oracle_for, game, P, every, regroup):
+    """Continuous simulation: when the periodic check finds every game over, the batch restarts on the device with
+    session ids first + epoch * stride + i.  The oracle replays the same rule on the host."""
+    cg = games(game, P)
+    o = oracle_for(cg)
+    n, first, seed, stride = 1500, 10_000, 77, 1 << 20
+    _, b = _batch(cg, n, first, seed, "tps")
+    if regroup:
+        b.set_regroup(every, 3)
+    else:
+        b.set_regroup(0)
+        b.set_compaction(every, 2)
+    b.set_autoreset(stride)
+    kinds = np.array([p.kind for p in cg.table.phases])
+    rec = o.init(n)
+    ost = o.new_stats()
+    harvested = o.new_stats()
+    epoch = 0
+    steps = 3 * (9 * P - 16 + 2 * cg.table.max_revotes * (P - 2) if game != TTL else 2 + 8 * P) + 40
+    for k in range(steps):
+        b.step(1)
+        o.step(rec, first + epoch * stride, seed, 1, ost)
+        if (k + 1) % every == 0 and (kinds[rec[:, 0]] == 3).all():       # the device-side check after this launch
+            fin = o.new_stats()
+            o.stats_final(rec, fin)                                       # (stats_final SETS the final-state histograms)
+            harvested += fin
+            rec = o.init(n)
+            epoch += 1
+        if k % 3 == 0 or epoch:
+            assert np.array_equal(b.export_state(), rec), "step %d epoch %d" % (k, epoch)
+    assert epoch >= 2 and b.epochs() == epoch
+    o.stats_final(rec, ost)
+    ost[1:260] += harvested[1:260]
+    ost[292:548] += harvested[292:548]
+    np.testing.assert_array_equal(b.stats(), ost)
+    # a host reset goes back to epoch 0
+    b.reset(first_session_id=5)
+    assert b.epochs() == 0
+    rec = o.init(n)
+    b.step(20)
+    o.step(rec, 5, seed, 20)
+    np.testing.assert_array_equal(b.export_state(), rec)
