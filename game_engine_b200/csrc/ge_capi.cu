@@ -594,7 +594,11 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             need |= 8;                                        // bots draw from the session's Philox stream (needs its id)
             need |= pred_need(ph.actor_pred);
             if (ph.action_op == ACT_PICK_PLAYER) need |= pred_need(ph.action_arg);
-            if (ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE) need |= 1 | 4;
+            // recording exits read-modify-write the submitted mask (C1).  Only the day vote goes through the player
+            // bytes in registers; night actions store their few target bytes directly (ge_step_tps.cuh: PlSink)
+            if (ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE) need |= 1;
+            // (up to 8 players the bytes are one 8-byte column: through registers is as cheap, measured)
+            if (ph.exit_op == EX_DAY_VOTE || (h.n_players <= 8 && ph.exit_op >= EX_VOTE_KILL)) need |= 4;
         }
         for (int b = 0; b < ph.n_branches; ++b) {
             const ge_branch_t& br = ph.br[b];

@@ -116,6 +116,21 @@ __device__ __forceinline__ void set_byte(uint32_t (&w)[NW], int p, uint32_t v) {
         if (i == wi) w[i] = (w[i] & ~(0xFFu << sh)) | (v << sh);
 }
 
+// Where a night action's target byte goes when the per-player columns were NOT loaded for this launch (the host
+// proves per phase that nothing reads them, DevTable::need bit 2): straight to its final place in the tile, one
+// byte store per actor, instead of a read-modify-write of the whole player columns through registers.
+struct PlSink {
+    uint8_t* p16;       // this lane's 16 bytes of the first full player column (column 3)
+    uint8_t* p8;        // this lane's 8 bytes of the trailing half column (P8 % 16 == 8)
+    bool direct;
+};
+template <int P8>
+__device__ __forceinline__ void pl_store(const PlSink& K, int p, uint32_t v) {
+    constexpr int NT16 = P8 / 16;
+    uint8_t* a = ((P8 % 16) != 0 && p >= 16 * NT16) ? K.p8 + (p - 16 * NT16) : K.p16 + (p >> 4) * 512 + (p & 15);
+    *a = (uint8_t)v;
+}
+
 // ---- table views -----------------------------------------------------------------------------------
 // The step body below is written once against a "view" of the phase it runs in.  RtView reads the
 // table passed at run time (any game).  CtView<Spec, X> reads a table generated at BUILD time from the
@@ -210,7 +225,7 @@ struct CtView {
 // One step of one session in phase X (already known not to be terminal and step0 != 0).  Returns the
 // phase index entered; `dirty` collects which column groups changed.
 template <int P8, class V>
-__device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
+__device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
                                            const StepArgs& A, uint32_t& dirty) {
     // planes of the bit-sliced vote counters: enough for P votes; a build-time table whose phase is the wolves'
     // vote needs only enough for n_wolves votes
@@ -274,7 +289,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
         uint32_t chosen = 0, first_choice = 0;
         uint32_t nib = 0;                       // P8 <= 8: nibble-packed vote counters (one candidate per nibble)
         bool nib_used = false;
-        if (aop == ACT_PICK_PLAYER && (uint32_t)__popc(actors) * 3u > (uint32_t)P8) {
+        if (aop == ACT_PICK_PLAYER && !K.direct && (uint32_t)__popc(actors) * 3u > (uint32_t)P8) {
             // ---- many actors (day vote): one statically unrolled pass over the players.  Philox words, target
             // bytes and ranks are static; the pick is a lookup in a nibble LUT of the legal players' positions.
             const uint32_t n0 = __popc(legal0);
@@ -356,7 +371,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
                 choice = 1u;
             }
             if (is_first) first_choice = choice;
-            if (record) set_byte(s.tw, p, choice);
+            if (record) { if (K.direct) pl_store<P8>(K, p, choice); else set_byte(s.tw, p, choice); }
         }
         }
         // plurality: candidates sharing the highest non-zero count (lowest id wins ties)
@@ -373,7 +388,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
                 top = tally.top();
             }
         }
-        if (record) dirty |= DIRTY_PL;
+        if (record && !K.direct) dirty |= DIRTY_PL;
         // ---- RefereeNode, effects of the phase just left
         switch (exo) {
         case EX_VOTE_KILL:
@@ -451,33 +466,33 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
 
 // Generic entry: interpret the run-time table.  Returns the phase entered or -1 for a terminal session.
 template <int P8>
-__device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
+__device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
                                       const StepArgs& A, uint32_t& dirty) {
     const int X = s.h0 & 0xFF;
     if (T.phase[X].kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
-    return w_step_body<P8>(RtView(T, X), X, s, F, sid_lo, sid_hi, A, dirty);
+    return w_step_body<P8>(RtView(T, X), X, s, F, K, sid_lo, sid_hi, A, dirty);
 }
 
 // Specialised entry: a warp-uniform switch over the phases of a build-time table.
 template <int P8, class Spec, int X>
-__device__ __forceinline__ int w_step_spec_case(WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
+__device__ __forceinline__ int w_step_spec_case(WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
                                                 const StepArgs& A, uint32_t& dirty) {
     if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
-    return w_step_body<P8>(CtView<Spec, X>{}, X, s, F, sid_lo, sid_hi, A, dirty);
+    return w_step_body<P8>(CtView<Spec, X>{}, X, s, F, K, sid_lo, sid_hi, A, dirty);
 }
 
 template <int P8, class Spec, int X = 0>
-__device__ __forceinline__ int w_step_spec(WState<P8>& s, const FieldTable& F, uint32_t sid_lo, uint32_t sid_hi,
+__device__ __forceinline__ int w_step_spec(WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
                                            const StepArgs& A, uint32_t& dirty) {
     if constexpr (X >= Spec::n_phases) {
         return -1;
     } else {
-        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X>(s, F, sid_lo, sid_hi, A, dirty);
-        return w_step_spec<P8, Spec, X + 1>(s, F, sid_lo, sid_hi, A, dirty);
+        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X>(s, F, K, sid_lo, sid_hi, A, dirty);
+        return w_step_spec<P8, Spec, X + 1>(s, F, K, sid_lo, sid_hi, A, dirty);
     }
 }
 
@@ -646,6 +661,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
                 if (need & 4) t = ld64(base8);
                 s.tw[4 * NT16] = t.x; s.tw[4 * NT16 + 1] = t.y;
             }
+            const PlSink K{base + 3 * 512, base8, (need & 4u) == 0};
             s.h0 = c0.x; s.h1 = c0.y; s.alive = c0.z; s.can_vote = c0.w;
             s.eligible = c1.x; s.submitted = c1.y; s.revealed = c1.z; s.investigated = c1.w;
             s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
@@ -656,9 +672,9 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
                 int np = -1;
                 if (live) {
                     if constexpr (std::is_void<Spec>::value)
-                        np = w_step<P8>(T, s, F, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
+                        np = w_step<P8>(T, s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
                     else
-                        np = w_step_spec<P8, Spec>(s, F, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
+                        np = w_step_spec<P8, Spec>(s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
                     if (np < 0) live = false;
                 }
                 mixed += visits.add(s_visits, np, lane) > 1;
