@@ -5,14 +5,15 @@
     python bench.py --impl reference [--gpus N] [--steps K] ...     # CPU arm (oracle port, all host threads)
     torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, NCCL
 
-Workload (BASELINE.json configs[1]): werewolf-(mafia).yaml, 8 players, 2^20 sessions per GPU, synthetic
-(Philox bots).  A "step" is ONE launch of the step kernel over ONE 2^20-session batch (every non-terminal
-session advances one phase; the state is read and written once).  To keep the inputs out of L2 the
-launches round-robin over a ring of batches whose footprint exceeds 2x L2, and to make the number
-independent of K the ring is a steady state: batch i starts i*G/R steps into its games and a batch that
-has been stepped G times is re-initialised with fresh session ids (the re-initialisation kernels are
-inside the timed region and counted in gpu_launches).  value = counted session-phase-steps (terminal
-sessions do not count) of all ranks / max-over-ranks device time.
+Workload (BASELINE.json configs[1]): werewolf-(mafia).yaml, 8 players, 2^20 sessions per batch per GPU, synthetic
+(Philox bots).  To keep the inputs out of L2 the resident data set is a RING of batches whose footprint exceeds
+2x L2.  A "step" is ONE PASS of the hot path over that data set: one launch of the step kernel per batch of the
+ring (every non-terminal session advances one phase; the state is read and written once) — the same unit in the
+CUDA arm and in the CPU reference arm.  To make the number independent of K the ring is a steady state: batch i
+starts i*G/R steps into its games and a batch that has been stepped G times (the longest possible game) is
+re-initialised with fresh session ids (the re-initialisation kernels are inside the timed region and counted in
+gpu_launches).  value = counted session-phase-steps (terminal sessions do not count) of all ranks /
+max-over-ranks device time.
 """
 from __future__ import annotations
 
@@ -41,8 +42,8 @@ def game_cap(family: int, players: int, max_revotes: int = 0) -> int:
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2500, help="timed steps; one step = one pass over the ring (one launch per batch)")
+    ap.add_argument("--warmup", type=int, default=25)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--game", default="werewolf-(mafia)")
     ap.add_argument("--players", type=int, default=8)
@@ -371,7 +372,7 @@ def run_ours(a):
             k_global += run
             n -= run
 
-    run_steps(max(3, a.warmup))
+    run_steps(max(3, a.warmup) * R)
     torch.cuda.synchronize()
     counted0 = sum(b.counted_steps() for b in ring)
     launches0 = sum(b.launch_count() for b in ring)
@@ -388,7 +389,7 @@ def run_ours(a):
     for st in streams[1:]:
         st.wait_event(ev0)
     t_enq0 = time.perf_counter()
-    run_steps(a.steps)
+    run_steps(a.steps * R)                                   # one step = one pass over the ring = R launches
     enqueue_ms = (time.perf_counter() - t_enq0) * 1e3        # host time to enqueue K steps
     for st in streams[1:]:                                   # join: ev1 fires when the work of ALL streams is done
         e = torch.cuda.Event()
@@ -547,7 +548,7 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(wl_key), "peak_source": peak_src,
                      "algorithmic_bytes_per_step": B, "kernel": "k_step_%s_%s" % ("w" if cg.family == 1 else "t", kern),
-                     "steps_per_launch": counted_all / world / a.steps},
+                     "steps_per_launch": counted_all / world / (a.steps * R), "launches_per_step": R},
         "e2e": e2e,
         "fused": fused,
         "gpu_launches": launches_all,

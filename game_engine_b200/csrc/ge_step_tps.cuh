@@ -335,7 +335,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
                         if (tallying) { if (P8 <= 8) nib += 1u << (4 * idx); else vote = 1u << idx; }
                     }
                     if (!have_first) { first_choice = choice; have_first = true; }
-                    if (record) s.tw[p >> 2] = (s.tw[p >> 2] & ~(0xFFu << (8 * (p & 3)))) | (choice << (8 * (p & 3)));
+                    if (record) s.tw[p >> 2] = __byte_perm(s.tw[p >> 2], choice, 0x3210u + ((4u - (p & 3)) << (4 * (p & 3))));   // byte p&3 <- choice (one PRMT)
                 }
                 rank += self_in;
                 if (P8 > 8) {

@@ -25,6 +25,6 @@ PY
 }
 S3=$(( (1 << 24) / N )); S4=$(( (1 << 26) / N )); S5=$(( (1 << 28) / N ))
 run cfg2 
-run cfg3 --players 16 --sessions $S3 --ring 4 --streams 4 --steps 4000 --no-e2e
-run cfg4 --game werewolf-revote --players 32 --sessions $S4 --ring 1 --streams 1 --ctas-per-sm 0 --steps 800 --warmup 50 --no-e2e
-run cfg5 --game two-truths-and-a-lie --players 4 --sessions $S5 --ring 2 --streams 2 --ctas-per-sm 0 --steps 400 --warmup 40 --no-e2e
+run cfg3 --players 16 --sessions $S3 --ring 4 --streams 4 --steps 500 --no-e2e
+run cfg4 --game werewolf-revote --players 32 --sessions $S4 --ring 1 --streams 1 --ctas-per-sm 0 --steps 400 --warmup 25 --no-e2e
+run cfg5 --game two-truths-and-a-lie --players 4 --sessions $S5 --ring 2 --streams 2 --ctas-per-sm 0 --steps 200 --warmup 20 --no-e2e
