@@ -201,10 +201,12 @@ def run_reference(a):
     native = build_oracle_native()
     o = Oracle(cg.blob, native=native)
     threads = host_threads(o)
-    # size the per-step sample so that K+W steps take about a minute
-    steps, dt = cpu_oracle_rate(cg, 1 << 13, cap, a.seed, threads, native)
-    per_sess_step = dt / ((1 << 13) * cap)                 # seconds per session per pass (terminal passes are cheap)
-    n = int(max(1 << 10, min(a.sessions, 60.0 / max(per_sess_step * (a.steps + a.warmup), 1e-12))))
+    # size the per-step sample so that K+W steps take about a minute and a half (first call discarded: thread
+    # start-up and page faults); never below 2^16 sessions per step, where OpenMP overhead would dominate
+    cpu_oracle_rate(cg, 1 << 15, cap, a.seed, threads, native)
+    steps, dt = cpu_oracle_rate(cg, 1 << 17, cap, a.seed, threads, native)
+    per_sess_step = dt / ((1 << 17) * cap)                 # seconds per session per pass (terminal passes are cheap)
+    n = int(min(a.sessions, max(1 << 16, 90.0 / max(per_sess_step * (a.steps + a.warmup), 1e-12))))
     # same steady-state ring as the CUDA arm: R sub-batches staggered through their games
     R = a.ring
     n = max(R, n // R * R)
