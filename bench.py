@@ -536,6 +536,8 @@ def run_ours(a):
     achieved = counted_all / world * B / (ms_max * 1e-3) / 1e9          # per GPU
     kern = ring[0].kernel
     wl_key = "%s_p%d_%s" % (a.game, a.players, kern)
+    traffic = ncu_traffic(wl_key)
+    launches_per_s = a.steps * R / (ms_max * 1e-3)                        # step-kernel launches per second per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
         "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -548,7 +550,10 @@ def run_ours(a):
             "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(wl_key), "peak_source": peak_src,
+                     "traffic": traffic, "peak_source": peak_src,
+                     # what actually crosses the DRAM pins: ncu bytes per launch x the live launch rate (column skipping
+                     # and compaction keep it below the algorithmic bytes)
+                     "dram_gbs_from_traffic": (traffic * launches_per_s / 1e9) if traffic else None,
                      "algorithmic_bytes_per_step": B, "kernel": "k_step_%s_%s" % ("w" if cg.family == 1 else "t", kern),
                      "steps_per_launch": counted_all / world / (a.steps * R), "launches_per_step": R},
         "e2e": e2e,
