@@ -13,7 +13,8 @@ whose decisions come from the CUDA step kernel instead of three LLM calls:
 Each node is stateless: it rebuilds the packed record of the session from the incoming dict, runs ONE step on
 the GPU and returns only the keys its reference counterpart returns, so the three nodes can sit in the
 reference graph unchanged (three tiny launches per graph run instead of three LLM round-trips).
-`step_session(state)` is the fused form: the union of the three updates.
+`step_session(state)` is the fused form: the union of the three updates.  `ActionExecutorV3` serves the newer
+graph variant (agent/game_agent_v3.py), whose single backend node merges the phase and referee decisions.
 
 Error behaviour follows the reference: a node never raises into the graph; on failure it degrades to
 "no change / stay at phase" and logs.  The batch API (`SessionBatch`) raises instead.
@@ -117,6 +118,31 @@ class GpuReferee:
         return Command(goto="ActionExecutor", update={
             "player_states": ps, "game_notes": notes, "roomSession": state.get("roomSession", {}),
             "dsl": state.get("dsl", {}), "phase_history": state.get("phase_history", [])})
+
+
+    async def ActionExecutorV3(self, state: Dict[str, Any], config: Any = None) -> Command:
+        """Drop-in for the backend half of the NEWER graph's merged node (reference agent/game_agent_v3.py:540-874:
+        one LLM call bound to `update_complete_player_states` + `set_next_phase`): same phase-0 rule (:615-633), same
+        update keys and `goto` (:862-874), history appended only when the phase changes and without a timestamp
+        (:838-849).  Runs after BotBehaviorNode, which already recorded the bots' actions, so `playerActions` passes
+        through unchanged; v3 does not return `game_notes`."""
+        hist = list(state.get("phase_history", []))
+        cur = state.get("current_phase_id", 0)
+        try:
+            upd = await asyncio.to_thread(self.step_session, state)
+            if cur == 0 and not any(e.get("phase_id") == 0 for e in hist):
+                return Command(goto="UIUpdateNode", update={"current_phase_id": 0, "phase_history": upd["phase_history"]})
+            new_id = upd["current_phase_id"]
+            if new_id != cur:
+                hist.append({"phase_id": new_id, "phase_name": upd["current_phase_name"]})
+            return Command(goto="UIUpdateNode", update={
+                "player_states": upd["player_states"], "playerActions": dict(state.get("playerActions", {})),
+                "phase_history": hist, "current_phase_id": new_id, "current_phase_name": upd["current_phase_name"]})
+        except Exception as e:      # reference: invalid phase id -> keep the current phase (:833-836)
+            logger.error("[ActionExecutorV3] GPU step failed, staying at phase %s: %s", cur, e)
+            return Command(goto="UIUpdateNode", update={
+                "player_states": state.get("player_states", {}), "playerActions": dict(state.get("playerActions", {})),
+                "phase_history": hist, "current_phase_id": cur, "current_phase_name": state.get("current_phase_name", "")})
 
 
 def terminal(cg, state: Dict[str, Any]) -> bool:

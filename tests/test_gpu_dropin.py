@@ -90,3 +90,34 @@ def test_drop_in_nodes_follow_the_reference_graph(path):
         return trace
 
     _assert_traces_equal(g["trace"], asyncio.run(run()))
+
+
+@pytest.mark.parametrize("path", [GOLDEN[1], GOLDEN[6], GOLDEN[9]], ids=[IDS[1], IDS[6], IDS[9]])
+def test_v3_merged_node_follows_the_reference(path):
+    """BotBehaviorNode -> ActionExecutorV3 (the newer graph, reference agent/game_agent_v3.py:1099-1117): same
+    player_states / playerActions / phase ids as the v2 fixtures; history entries carry no timestamp and are only
+    appended when the phase changes; game_notes are not part of v3's update."""
+    from game_engine_b200.nodes import GpuReferee, terminal
+    g = load(path)
+    ref = GpuReferee(g["game"], g["players"], seed=g["seed"], session_id=g["sid"])
+
+    async def run():
+        state = ref.initial_state()
+        for k in range(len(g["trace"]) - 1):
+            cmd = await ref.BotBehaviorNode(state, {})
+            state.update(cmd.update)
+            cmd = await ref.ActionExecutorV3(state, {})
+            assert cmd.goto == "UIUpdateNode"
+            if k == 0:
+                assert set(cmd.update) == {"current_phase_id", "phase_history"}
+            else:
+                assert set(cmd.update) == {"player_states", "playerActions", "phase_history", "current_phase_id", "current_phase_name"}
+                assert "timestamp" not in cmd.update["phase_history"][-1]
+            state.update(cmd.update)
+            want = g["trace"][k + 1]
+            got = json.loads(json.dumps(normalise(state)))
+            for key in ("current_phase_id", "player_states", "playerActions", "phase_history"):
+                d = first_diff(want[key], got[key], "/" + key)
+                assert d is None, "step %d: %s" % (k + 1, d)
+        assert terminal(ref.cg, state) and state["game_notes"] == []
+    asyncio.run(run())
