@@ -12,7 +12,7 @@ SOURCES = ["ge_capi.cu"]
 HEADERS = ["ge_common.cuh", "ge_step_tps.cuh", "ge_step_coop.cuh", "ge_spec_gen.cuh", os.path.join("..", "..", "include", "game_engine_b200.h")]
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", *(os.environ.get("GE_EXTRA_NVCC", "").split()),
     "--shared", "-Xcompiler", "-fPIC", "-cudart", "static",
 ]
 

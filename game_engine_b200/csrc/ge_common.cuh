@@ -133,6 +133,8 @@ __device__ __host__ __forceinline__ constexpr uint32_t tile_off(uint32_t o, uint
                                           : (uint32_t)(S / 16) * 512u + sl * 8u + (o - 16u * (uint32_t)(S / 16));
 }
 
+// L1 prefetch of the 128-byte line that holds p (one warp instruction covers a 512-byte column of a tile)
+__device__ __forceinline__ void prefetch_l1(const uint8_t* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 ld128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ uint2 ld64(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
 __device__ __forceinline__ void st128(uint8_t* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
