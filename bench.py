@@ -290,6 +290,11 @@ def run_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
+    # stdout carries exactly ONE JSON line: whatever libraries print there (the image sets NCCL_DEBUG=VERSION, so NCCL
+    # prints a banner with printf) is sent to stderr; the result line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -576,7 +581,8 @@ def run_ours(a):
     }
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cg, cap, a.seed, a.cpu_seconds)
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
