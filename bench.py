@@ -59,6 +59,8 @@ def parse_args():
                     help="re-initialise a batch on the device as soon as all its games are over (ge_batch_set_autoreset) instead "
                          "of from the host after `cap` steps; measured: no gain at 2^20 sessions (some game always runs to the cap)")
     ap.add_argument("--regroup", default="", help="phase regrouping 'every,shift' (default: the library's choice for the table)")
+    ap.add_argument("--head-start-us", type=int, default=3000,
+                    help="length of the spin kernel the timed launches are queued behind (host head start; 0 = none)")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--e2e-calls", type=int, default=24)
     ap.add_argument("--e2e-subs", type=int, default=4, help="pipelined sub-batches of the end-to-end call")
@@ -347,7 +349,7 @@ def run_ours(a):
         if pre:
             b.step(pre)
         age[i] = pre
-    from game_engine_b200.batch import step_many
+    from game_engine_b200.batch import step_many, stream_delay
     k_global = 0
     resets = 0
 
@@ -382,18 +384,27 @@ def run_ours(a):
 
     run_steps(max(3, a.warmup) * R)
     torch.cuda.synchronize()
-    counted0 = sum(b.counted_steps() for b in ring)
-    launches0 = sum(b.launch_count() for b in ring)
-    epochs0 = sum(b.epochs() for b in ring) if auto else 0
     agg = torch.zeros(560, dtype=torch.int64, device=dev)
+    snap_pin = PinnedBuffer(8 * R)                           # counter snapshots at the start of the timed region
+    snap = snap_pin.array.view(np.uint64)
+    epochs0 = sum(b.epochs() for b in ring) if auto else 0
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    # The timed launches are queued BEHIND a short spin kernel on stream 0 (every other stream waits for ev0, which
+    # follows it), so that the host is hundreds of launches ahead when the device starts the timed region — as it is
+    # in steady state — instead of feeding an empty GPU one launch at a time: without it a short run (small K)
+    # measures the host's start-up, not the device.  The spin itself is outside [ev0, ev1].
+    for i, b in enumerate(ring):
+        b.counted_steps_async(snap[i:i + 1])
+    launches0 = sum(b.launch_count() for b in ring)
+    resets0 = resets
+    stream_delay(local_rank, stream.cuda_stream, a.head_start_us)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)                                       # every stream is idle here (device synchronised above)
+    ev0.record(stream)
     for st in streams[1:]:
         st.wait_event(ev0)
     t_enq0 = time.perf_counter()
@@ -411,10 +422,9 @@ def run_ours(a):
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
 
-    counted = sum(b.counted_steps() for b in ring) - counted0
+    counted = sum(b.counted_steps() for b in ring) - int(snap[:R].sum())
     launches = sum(b.launch_count() for b in ring) - launches0
-    if auto:
-        resets = sum(b.epochs() for b in ring) - epochs0
+    resets = (sum(b.epochs() for b in ring) - epochs0) if auto else resets - resets0
 
     # the job's only exchange step: statistics all-reduce (win rate + phase-length histogram) over NCCL
     t_ar0 = time.perf_counter()

@@ -202,6 +202,12 @@ class SessionBatch:
         capi.check(capi.lib().ge_counted_steps(self._h, ctypes.byref(v)))
         return int(v.value)
 
+    def counted_steps_async(self, pinned_u64: np.ndarray) -> None:
+        """Enqueues a copy of the counted-steps word (as of this point of the batch's stream) into a one-element
+        uint64 view of a PinnedBuffer; read it after sync()."""
+        assert pinned_u64.dtype == np.uint64 and pinned_u64.size == 1
+        capi.check(capi.lib().ge_counted_steps_async(self._h, pinned_u64.ctypes.data))
+
     def launch_count(self) -> int:
         return int(capi.lib().ge_launch_count(self._h))
 
@@ -227,6 +233,11 @@ def step_many(batches, n_rounds: int = 1) -> None:
     """n_rounds round-robin passes: one step of every batch in order (one C call; see ge_step_many)."""
     arr = (ctypes.c_void_p * len(batches))(*[b._h for b in batches])
     capi.check(capi.lib().ge_step_many(arr, len(batches), int(n_rounds)))
+
+
+def stream_delay(device: int, stream: int, microseconds: int) -> None:
+    """Measurement helper: keeps a CUDA stream busy for about `microseconds` (see ge_stream_delay)."""
+    capi.check(capi.lib().ge_stream_delay(int(device), ctypes.c_void_p(stream), int(microseconds)))
 
 
 class PinnedBuffer:

@@ -55,9 +55,11 @@ SYMBOLS = [
     ("ge_stats", _int, [_vp, _vp, _sz]),
     ("ge_stats_device_ptr", _vp, [_vp]),
     ("ge_counted_steps", _int, [_vp, ctypes.POINTER(_u64)]),
+    ("ge_counted_steps_async", _int, [_vp, _vp]),
     ("ge_state_device_ptr", _vp, [_vp]),
     ("ge_state_device_bytes", _sz, [_vp]),
     ("ge_launch_count", _u64, [_vp]),
+    ("ge_stream_delay", _int, [_int, _vp, ctypes.c_uint]),
     ("ge_last_error", ctypes.c_char_p, []),
     ("ge_version", ctypes.c_char_p, []),
 ]

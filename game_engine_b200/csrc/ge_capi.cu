@@ -1197,6 +1197,31 @@ extern "C" int ge_counted_steps(ge_batch* b, uint64_t* out) {
     return GE_OK;
 }
 
+// Measurement helper: occupies `cuda_stream` for about `microseconds` (one thread spinning on %globaltimer).  A
+// benchmark enqueues it in front of its first timing event so that the host can queue the timed launches while
+// the device is still busy — the timed region then measures the device, not the host's launch rate from a cold queue.
+__global__ void k_delay(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+extern "C" int ge_stream_delay(int device, void* cuda_stream, unsigned microseconds) {
+    if (microseconds > 1000000u) return fail(GE_ERR_ARG, "ge_stream_delay: at most one second");
+    CU(cudaSetDevice(device));
+    k_delay<<<1, 1, 0, (cudaStream_t)cuda_stream>>>((unsigned long long)microseconds * 1000ull);
+    CU(cudaGetLastError());
+    return GE_OK;
+}
+
+// Asynchronous variant for pipelined measurement: the counted-steps word as of this point of the batch's stream is
+// copied to *pinned_out (page-locked host memory) without synchronising; valid after the next ge_sync.
+extern "C" int ge_counted_steps_async(ge_batch* b, uint64_t* pinned_out) {
+    if (!b || !pinned_out) return fail(GE_ERR_ARG, "bad arguments to ge_counted_steps_async");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(pinned_out, b->d_stats, sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
+    return GE_OK;
+}
+
 extern "C" int ge_run_host_async(ge_batch* b, const void* records_in, void* records_out, int n_steps, uint64_t* host_stats) {
     if (!b || n_steps < 0) return fail(GE_ERR_ARG, "bad arguments to ge_run_host_async");
     CU(cudaSetDevice(b->device));

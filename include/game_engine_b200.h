@@ -180,12 +180,19 @@ int ge_stats_refresh(ge_batch *b, void *cuda_stream);
 int ge_stats(ge_batch *b, uint64_t *host_hist, size_t n);
 void *ge_stats_device_ptr(ge_batch *b);
 int ge_counted_steps(ge_batch *b, uint64_t *out);
+/* Non-blocking: copies the counter as of this point of the batch's stream to page-locked host memory (ge_host_alloc);
+ * the value is valid after the next ge_sync. */
+int ge_counted_steps_async(ge_batch *b, uint64_t *pinned_out);
 
 /* device pointer / size of the tiled session store (for profiling and tests) */
 void *ge_state_device_ptr(ge_batch *b);
 size_t ge_state_device_bytes(const ge_batch *b);
 /* number of kernel launches (step + glue kernels) issued by this batch since creation */
 uint64_t ge_launch_count(const ge_batch *b);
+
+/* Measurement helper: keeps `cuda_stream` of `device` busy for about `microseconds` (<= 1 s) with a one-thread spin
+ * kernel, so that a benchmark can queue its timed launches behind it (see bench.py). */
+int ge_stream_delay(int device, void *cuda_stream, unsigned microseconds);
 
 const char *ge_last_error(void);
 const char *ge_version(void);
