@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libgame_engine_b200.so")
 SOURCES = ["ge_capi.cu"]
-HEADERS = ["ge_common.cuh", "ge_step_tps.cuh", "ge_step_coop.cuh", "ge_spec_gen.cuh", os.path.join("..", "..", "include", "game_engine_b200.h")]
+HEADERS = ["ge_common.cuh", "ge_step_tps.cuh", "ge_step_coop.cuh", "ge_spec_gen.cuh", "ge_glue.cuh", os.path.join("..", "..", "include", "game_engine_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", *(os.environ.get("GE_EXTRA_NVCC", "").split()),

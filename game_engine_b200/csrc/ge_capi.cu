@@ -14,6 +14,7 @@
 #include "ge_step_tps.cuh"
 #include "ge_step_coop.cuh"
 #include "ge_spec_gen.cuh"
+#include "ge_glue.cuh"
 
 using namespace ge;
 
@@ -84,433 +85,6 @@ static int restore_order(ge_batch* b);
 static int lanes_per_session(const ge_table* t);
 extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixed_shift);
 static int ensure_stage(ge_batch* b, size_t bytes);
-
-// ------------------------------------------------------------------------------------ glue kernels
-struct InitRec { uint32_t w[40]; };
-
-__device__ __forceinline__ uint32_t rt_tile_off(uint32_t o, uint32_t sl, uint32_t n16) {
-    return (o / 16u < n16) ? (o / 16u) * 512u + sl * 16u + (o % 16u) : n16 * 512u + sl * 8u + (o - 16u * n16);
-}
-
-__global__ void k_set_u64(unsigned long long* p, unsigned long long v) { *p = v; }
-
-__global__ void k_init(uint8_t* tiles, uint64_t n_tiles, uint32_t S, const __grid_constant__ InitRec rec) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t total = n_tiles * 32;
-    const uint32_t n16 = S / 16;
-    for (uint64_t i = t; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S);
-        const uint32_t sl = (uint32_t)(i & 31);
-        for (uint32_t k = 0; k < S / 8; ++k)
-            *reinterpret_cast<uint2*>(base + rt_tile_off(8 * k, sl, n16)) = make_uint2(rec.w[2 * k], rec.w[2 * k + 1]);
-    }
-}
-
-// tiles -> canonical AoS records (count sessions starting at `first`)
-__global__ void k_export(const uint8_t* tiles, uint32_t S_dev, uint32_t S_canon, uint64_t first, uint64_t count, uint8_t* out) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n16 = S_dev / 16;
-    for (uint64_t j = t; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = first + j;
-        const uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
-        const uint32_t sl = (uint32_t)(i & 31);
-        for (uint32_t k = 0; k < S_canon / 8; ++k)
-            *reinterpret_cast<uint2*>(out + j * S_canon + 8 * k) = *reinterpret_cast<const uint2*>(base + rt_tile_off(8 * k, sl, n16));
-    }
-}
-
-__global__ void k_import(uint8_t* tiles, uint32_t S_dev, uint32_t S_canon, uint64_t first, uint64_t count, const uint8_t* in) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n16 = S_dev / 16;
-    for (uint64_t j = t; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = first + j;
-        uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
-        const uint32_t sl = (uint32_t)(i & 31);
-        for (uint32_t k = 0; k < S_dev / 8; ++k) {
-            uint2 v = make_uint2(0, 0);
-            if (k < S_canon / 8) v = *reinterpret_cast<const uint2*>(in + j * S_canon + 8 * k);
-            *reinterpret_cast<uint2*>(base + rt_tile_off(8 * k, sl, n16)) = v;
-        }
-    }
-}
-
-// final-state histograms (SPEC.md section 6): winner, length, survivors / scores.  sh = 515 shared counters.
-__device__ __forceinline__ void stats_one(const DevTable& T, const uint8_t* tiles, uint32_t S_dev, uint64_t i, uint32_t* sh) {
-    const uint32_t n16 = S_dev / 16;
-    const int P = T.h.n_players;
-    const uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
-    const uint32_t sl = (uint32_t)(i & 31);
-    const uint4 c0 = *reinterpret_cast<const uint4*>(base + sl * 16);
-    const bool terminal = T.phase[c0.x & 31].kind == KIND_TERMINAL;
-    const uint32_t step = c0.x >> 16;
-    if (T.h.family == FAM_WEREWOLF) {
-        const uint32_t w = c0.y & 0xFF;
-        atomicAdd(&sh[w <= 2 ? w : 0], 1u);
-        if (terminal) atomicAdd(&sh[3 + 256 + __popc(c0.z)], 1u);
-    } else {
-        atomicAdd(&sh[terminal ? 1 : 0], 1u);
-        if (terminal)
-            for (int p = 0; p < P; ++p) {
-                const uint32_t pw = *reinterpret_cast<const uint32_t*>(base + rt_tile_off(8 + 4 * p, sl, n16));
-                atomicAdd(&sh[3 + 256 + (pw & 0xFF)], 1u);
-            }
-    }
-    if (terminal) atomicAdd(&sh[3 + (step < 255 ? step : 255)], 1u);
-}
-__device__ __forceinline__ void stats_flush(const uint32_t* sh, unsigned long long* stats) {
-    for (int i = threadIdx.x; i < 515; i += blockDim.x) {
-        const uint32_t v = sh[i];
-        if (!v) continue;
-        const int dst = i < 3 ? ST_WINNER + i : i < 259 ? ST_LENGTH + (i - 3) : ST_TAIL + (i - 259);
-        atomicAdd(&stats[dst], (unsigned long long)v);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev, uint64_t n, unsigned long long* stats) {
-    __shared__ uint32_t sh[3 + 256 + 256];
-    for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        stats_one(T, tiles, S_dev, i, sh);
-    __syncthreads();
-    stats_flush(sh, stats);
-}
-
-// Auto-reset (ge_batch_set_autoreset): when the check that follows a counted step finds no live session left
-// (n_active == 0), the batch starts over ON THE DEVICE with fresh session ids, no host round trip:
-// k_autoreset_apply folds the finished sessions' histograms into the accumulator and rewrites every slot with the
-// initial record (slot order back to identity); k_autoreset_commit then republishes n_active, bumps the device
-// epoch (session id = first_sid + epoch * sid_stride + index) and announces "phase 0" to the next launch.
-// Both are no-ops (one uniform load) while games are still running.
-__global__ void __launch_bounds__(256)
-k_autoreset_apply(const __grid_constant__ DevTable T, uint8_t* tiles, uint32_t S_dev, uint64_t n, uint64_t n_tiles,
-                  const __grid_constant__ InitRec rec, uint32_t* origin, unsigned long long* stats, const unsigned long long* cstate) {
-    __shared__ uint32_t sh[3 + 256 + 256];
-    if (cstate[0] != 0) return;
-    for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const uint32_t n16 = S_dev / 16;
-    const uint64_t total = n_tiles * 32;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (i < n) stats_one(T, tiles, S_dev, i, sh);            // read the finished game first ...
-        uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
-        const uint32_t sl = (uint32_t)(i & 31);
-        for (uint32_t k = 0; k < S_dev / 8; ++k)                   // ... then overwrite the same slot
-            *reinterpret_cast<uint2*>(base + rt_tile_off(8 * k, sl, n16)) = make_uint2(rec.w[2 * k], rec.w[2 * k + 1]);
-        origin[i] = (uint32_t)i;
-    }
-    __syncthreads();
-    stats_flush(sh, stats);
-}
-
-__global__ void k_autoreset_commit(unsigned long long* cstate, uint32_t* presence, uint32_t* rg, uint32_t next_launch_idx, unsigned long long n) {
-    if (threadIdx.x != 0 || cstate[0] != 0) return;
-    cstate[0] = n; cstate[5] = 0; cstate[8] += 1;
-    presence[next_launch_idx % 3] = 1u;                            // every session is in phase index 0
-    if (rg) for (int i = 0; i <= 33; ++i) rg[i] = 0;
-}
-
-// ------------------------------------------------------------------------------------ compaction
-// Active-prefix compaction.  All live sessions of a batch advance in lockstep, so finished games leave
-// holes that still cost issue slots.  Periodically the live sessions at the back are swapped, in place,
-// with terminal sessions at the front; step kernels then walk only slots [0, n_active).  Inputs are the
-// per-tile live masks and the live count the step kernel publishes — no pass over the records.  A swap
-// costs about one step of traffic, so it only runs when a quarter of the prefix is dead (dead_shift = 2).
-// Deterministic: ranks come from an exclusive scan, not from atomics.
-// cstate: [0] n_active [1] n_live [2] pairs [3] live already in front [4] tiles of the old prefix
-//         [5] live sessions after the last counted step (written by the step kernel) [6] scan ticket
-constexpr int CS_TILES = 1024;          // tiles per scan block
-
-__global__ void k_iota(uint32_t* origin, uint64_t n) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) origin[i] = (uint32_t)i;
-}
-
-__global__ void k_cstate_reset(unsigned long long* cstate, unsigned long long n, unsigned long long epoch) {
-    // [7] = host epoch tag, [8] = number of device-side re-initialisations (auto-reset) since the last host one
-    if (threadIdx.x < 16) cstate[threadIdx.x] = threadIdx.x == 0 ? n : threadIdx.x == 7 ? epoch : 0ull;
-}
-
-__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += u; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t w = s_warp[lane];
-        uint32_t wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += u; }
-        s_warp[lane] = wi - w;
-        if (lane == 31) *total = wi;
-    }
-    __syncthreads();
-    return s_warp[warp] + incl - v;
-}
-
-// grid = ceil(max tiles / 1024) blocks of 1024 threads.  loc[t] = live sessions in tiles of the same block
-// before t, blk[b] = live sessions in blocks before b (filled in by the last block to finish).
-__global__ void __launch_bounds__(1024)
-k_compact_scan(const uint32_t* __restrict__ live_mask, uint32_t* loc, uint32_t* blk, unsigned long long* cstate, uint32_t dead_shift) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_total;
-    __shared__ uint32_t s_last;
-    const uint64_t n_act = cstate[0];
-    const uint64_t live_now = cstate[5];
-    const uint64_t nt = (n_act + 31) >> 5;
-    const uint32_t nblk = (uint32_t)((nt + CS_TILES - 1) / CS_TILES);
-    // every block takes the same decision from the same two words (nobody writes them in this kernel)
-    if (live_now > n_act || ((n_act - live_now) << dead_shift) < n_act) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { cstate[1] = n_act; cstate[2] = 0; }
-        return;
-    }
-    if (blockIdx.x >= nblk) return;
-    const uint64_t t = (uint64_t)blockIdx.x * CS_TILES + threadIdx.x;
-    const uint32_t cnt = t < nt ? (uint32_t)__popc(live_mask[t]) : 0u;
-    const uint32_t excl = block_excl_scan_1024(cnt, s_warp, &s_total);
-    if (t < nt) loc[t] = excl;
-    if (threadIdx.x == 0) {
-        blk[blockIdx.x] = s_total;
-        __threadfence();
-        s_last = atomicAdd(&cstate[6], 1ull) == (unsigned long long)(nblk - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // last block: exclusive scan of the block totals (nblk <= 1024), then the bounds of the swap
-    const uint32_t bt = threadIdx.x < nblk ? ((volatile uint32_t*)blk)[threadIdx.x] : 0u;
-    const uint32_t be = block_excl_scan_1024(bt, s_warp, &s_total);
-    if (threadIdx.x < nblk) blk[threadIdx.x] = be;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint64_t n_live = s_total;
-        uint64_t pairs = 0, in_front = n_live;
-        if (n_live < n_act) {
-            const uint64_t tb = n_live >> 5;
-            const uint32_t lb = (uint32_t)(n_live & 31);
-            in_front = ((volatile uint32_t*)blk)[tb / CS_TILES] + ((volatile uint32_t*)loc)[tb] + __popc(live_mask[tb] & ((1u << lb) - 1u));
-            pairs = n_live - in_front;
-        }
-        cstate[0] = n_live; cstate[1] = n_live; cstate[2] = pairs; cstate[3] = in_front; cstate[4] = nt; cstate[6] = 0;
-    }
-}
-
-// Pair i swaps the i-th terminal session of the front region [0, n_live) with the i-th live session of the
-// back region [n_live, old prefix).  Both are located by binary search over the two-level prefix
-// P(t) = blk[t / 1024] + loc[t] (terminals before tile t = 32t - P(t)).  One thread per pair.
-__global__ void k_compact_swap(uint8_t* tiles, uint32_t S, uint32_t* origin, const uint32_t* __restrict__ live_mask,
-                               const uint32_t* __restrict__ loc, const uint32_t* __restrict__ blk, unsigned long long* cstate) {
-    const uint64_t n_live = cstate[1], pairs = cstate[2], in_front = cstate[3], nt = cstate[4];
-    if (blockIdx.x == 0 && threadIdx.x == 0) cstate[5] = 0;      // the next counted step starts from zero
-    if (pairs == 0) return;
-    const uint32_t n16 = S / 16;
-    const bool half = (S % 16) != 0;
-    const uint64_t tb = n_live >> 5;
-    const uint32_t lb = (uint32_t)(n_live & 31);
-    auto P = [&](uint64_t t) -> uint64_t { return (uint64_t)blk[t / CS_TILES] + loc[t]; };
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t lo = 0, hi = tb;                                // front: largest t in [0, tb] with 32t - P(t) <= i
-        while (lo < hi) {
-            const uint64_t mid = (lo + hi + 1) >> 1;
-            if (32 * mid - P(mid) <= i) lo = mid; else hi = mid - 1;
-        }
-        const uint32_t valid_a = lo == tb ? ((1u << lb) - 1u) : 0xFFFFFFFFu;
-        const uint32_t a = (uint32_t)(32 * lo) + (uint32_t)kth_set_bit<32>(~live_mask[lo] & valid_a, (uint32_t)(i - (32 * lo - P(lo))));
-        const uint64_t r = in_front + i;                          // back: largest t in [tb, nt-1] with P(t) <= r
-        lo = tb; hi = nt - 1;
-        while (lo < hi) {
-            const uint64_t mid = (lo + hi + 1) >> 1;
-            if (P(mid) <= r) lo = mid; else hi = mid - 1;
-        }
-        const uint32_t b = (uint32_t)(32 * lo) + (uint32_t)kth_set_bit<32>(live_mask[lo], (uint32_t)(r - P(lo)));
-        uint8_t* ba = tiles + (uint64_t)(a >> 5) * (32ull * S);
-        uint8_t* bb = tiles + (uint64_t)(b >> 5) * (32ull * S);
-        for (uint32_t c = 0; c < n16; ++c) {
-            uint4* pa = reinterpret_cast<uint4*>(ba + c * 512u + (a & 31) * 16u);
-            uint4* pb = reinterpret_cast<uint4*>(bb + c * 512u + (b & 31) * 16u);
-            const uint4 t = *pa; *pa = *pb; *pb = t;
-        }
-        if (half) {
-            uint2* pa = reinterpret_cast<uint2*>(ba + n16 * 512u + (a & 31) * 8u);
-            uint2* pb = reinterpret_cast<uint2*>(bb + n16 * 512u + (b & 31) * 8u);
-            const uint2 t = *pa; *pa = *pb; *pb = t;
-        }
-        const uint32_t t = origin[a]; origin[a] = origin[b]; origin[b] = t;
-    }
-}
-
-// tiles -> canonical records in ORIGINAL session order when slots have been permuted by compaction
-__global__ void k_export_perm(const uint8_t* tiles, uint32_t S_dev, uint32_t S_canon, const uint32_t* __restrict__ origin,
-                              uint64_t n, uint64_t first, uint64_t count, uint8_t* out) {
-    const uint32_t n16 = S_dev / 16;
-    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t o = origin[slot];
-        if (o < first || o >= first + count) continue;
-        const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S_dev);
-        const uint32_t sl = (uint32_t)(slot & 31);
-        for (uint32_t k = 0; k < S_canon / 8; ++k)
-            *reinterpret_cast<uint2*>(out + (o - first) * S_canon + 8 * k) = *reinterpret_cast<const uint2*>(base + rt_tile_off(8 * k, sl, n16));
-    }
-}
-
-// ------------------------------------------------------------------------------------ phase regrouping
-// Sessions of one batch normally advance in lockstep, so a warp's 32 sessions are in the same phase and the
-// warp-uniform phase switch of the step kernel costs one body.  Tables with loops of data-dependent length
-// (the tie -> re-vote loop of werewolf-revote) de-synchronise them: every warp then runs every phase body
-// present in its tile, i.e. each launch pays for the most expensive phase.  Regrouping is a counting sort of
-// the active prefix by phase index (terminal sessions last, which also makes it a compaction): afterwards at
-// most one tile per phase is mixed.  It is decided and done on the device (no host synchronisation):
-//   step kernel (counted launch): rg[0..31] += sessions that entered phase i, rg[32] += mixed tiles
-//   k_regroup_plan: trigger when >= 1/2^mixed_shift of the tiles are mixed or >= 1/2^dead_shift of the prefix
-//                   is dead; exclusive scan of the live phases' counts -> first slot of every phase
-//   k_regroup_scatter: blocks of 1024 slots; ranks inside a block from warp match + shared counters, the
-//                   block's range inside each phase from one global atomic per phase; record -> scratch
-//   k_regroup_copyback: scratch -> session store (the prefix only)
-// Slot order inside a phase is not deterministic, and does not have to be: session ids come from the origin
-// map, exports are in original order and the statistics are sums.
-enum { RG_HIST = 0, RG_MIXED = 32, RG_OLD = 33, RG_BASE = 64, RG_CURSOR = 100, RG_WORDS = 160, RG_TERM = 32 };
-
-__global__ void k_regroup_plan(unsigned long long* cstate, uint32_t* rg, uint32_t nonterm, uint32_t mixed_shift, uint32_t dead_shift) {
-    const int lane = threadIdx.x;                      // one warp
-    const uint64_t n_act = cstate[0];
-    const uint32_t cnt = ((nonterm >> lane) & 1u) ? rg[RG_HIST + lane] : 0u;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += u; }
-    const uint64_t n_live = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    const uint64_t mixed = rg[RG_MIXED];
-    const uint64_t tiles = (n_act + 31) >> 5;
-    const bool trig = n_act > 0 && n_live <= n_act &&
-                      (((mixed << mixed_shift) >= tiles && mixed > 0) || (((n_act - n_live) << dead_shift) >= n_act && n_live < n_act));
-    __syncwarp();
-    rg[RG_BASE + lane] = incl - cnt;
-    rg[RG_CURSOR + lane] = 0;
-    rg[RG_HIST + lane] = 0;
-    if (lane == 0) {
-        rg[RG_BASE + RG_TERM] = (uint32_t)n_live;
-        rg[RG_CURSOR + RG_TERM] = 0;
-        rg[RG_MIXED] = 0;
-        rg[RG_OLD] = trig ? (uint32_t)n_act : 0u;
-        if (trig) cstate[0] = n_live;
-        cstate[5] = 0;
-    }
-}
-
-__global__ void __launch_bounds__(1024)
-k_regroup_scatter(const uint8_t* __restrict__ tiles, uint32_t S, const uint32_t* __restrict__ origin, uint32_t* rg, uint32_t nonterm,
-                  uint8_t* __restrict__ out_tiles, uint32_t* __restrict__ out_origin) {
-    __shared__ uint32_t s_cnt[RG_TERM + 1], s_base[RG_TERM + 1];
-    const uint32_t old = rg[RG_OLD];
-    if (old == 0) return;
-    const uint32_t n16 = S / 16;
-    const bool half = (S % 16) != 0;
-    const int lane = threadIdx.x & 31;
-    for (uint32_t c0 = blockIdx.x * 1024u; c0 < old; c0 += gridDim.x * 1024u) {
-        if (threadIdx.x <= RG_TERM) s_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        const uint32_t slot = c0 + threadIdx.x;
-        const bool valid = slot < old;
-        const uint8_t* src = tiles + (uint64_t)(slot >> 5) * (32ull * S);
-        int key = -1;
-        if (valid) {
-            const uint32_t ph = *reinterpret_cast<const uint32_t*>(src + (slot & 31) * 16u) & 31u;
-            key = ((nonterm >> ph) & 1u) ? (int)ph : RG_TERM;
-        }
-        const uint32_t same = __match_any_sync(0xFFFFFFFFu, key);
-        const int leader = __ffs(same) - 1;
-        uint32_t wbase = 0;
-        if (valid && lane == leader) wbase = atomicAdd(&s_cnt[key], (uint32_t)__popc(same));
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, leader);
-        const uint32_t rank = __popc(same & ((1u << lane) - 1u));
-        __syncthreads();
-        if (threadIdx.x <= RG_TERM) {
-            const uint32_t n = s_cnt[threadIdx.x];
-            s_base[threadIdx.x] = n ? rg[RG_BASE + threadIdx.x] + atomicAdd(&rg[RG_CURSOR + threadIdx.x], n) : 0u;
-        }
-        __syncthreads();
-        if (valid) {
-            const uint32_t dst = s_base[key] + wbase + rank;
-            uint8_t* db = out_tiles + (uint64_t)(dst >> 5) * (32ull * S);
-            for (uint32_t c = 0; c < n16; ++c)
-                *reinterpret_cast<uint4*>(db + c * 512u + (dst & 31) * 16u) = *reinterpret_cast<const uint4*>(src + c * 512u + (slot & 31) * 16u);
-            if (half)
-                *reinterpret_cast<uint2*>(db + n16 * 512u + (dst & 31) * 8u) = *reinterpret_cast<const uint2*>(src + n16 * 512u + (slot & 31) * 8u);
-            out_origin[dst] = origin[slot];
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void k_regroup_copyback(uint8_t* __restrict__ tiles, uint32_t S, uint32_t* __restrict__ origin, const uint32_t* __restrict__ rg,
-                                   const uint8_t* __restrict__ in_tiles, const uint32_t* __restrict__ in_origin) {
-    const uint32_t old = rg[RG_OLD];
-    const uint32_t n16 = S / 16;
-    const bool half = (S % 16) != 0;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < old; slot += gridDim.x * blockDim.x) {
-        const uint64_t off = (uint64_t)(slot >> 5) * (32ull * S);
-        for (uint32_t c = 0; c < n16; ++c)
-            *reinterpret_cast<uint4*>(tiles + off + c * 512u + (slot & 31) * 16u) = *reinterpret_cast<const uint4*>(in_tiles + off + c * 512u + (slot & 31) * 16u);
-        if (half)
-            *reinterpret_cast<uint2*>(tiles + off + n16 * 512u + (slot & 31) * 8u) = *reinterpret_cast<const uint2*>(in_tiles + off + n16 * 512u + (slot & 31) * 8u);
-        origin[slot] = in_origin[slot];
-    }
-}
-
-// ------------------------------------------------------------------------------------ audience masks
-// Evaluates up to 32 DNF predicates (same encoding as the table's) for every session of a window: the lane
-// masks of the DSL's audience_groups (reference games/werewolf-(mafia).yaml:138-165; consumed by the UI tools'
-// audience_ids, src/lib/canvas/types.ts:14-17).  Output row = session (original order), column = predicate.
-struct PredList { ge_pred_t p[32]; int n; };
-
-__global__ void k_eval_preds(const __grid_constant__ DevTable T, const __grid_constant__ PredList PL, const uint8_t* tiles,
-                             uint32_t S_dev, const uint32_t* __restrict__ origin, uint64_t n, uint64_t first, uint64_t count,
-                             uint32_t* out) {
-    const uint32_t n16 = S_dev / 16;
-    const int P = T.h.n_players;
-    const uint32_t ALL = P >= 32 ? 0xFFFFFFFFu : ((1u << P) - 1u);
-    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t o = origin ? origin[slot] : slot;
-        if (o < first || o >= first + count) continue;
-        const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S_dev);
-        const uint32_t sl = (uint32_t)(slot & 31);
-        uint32_t F[16];
-#pragma unroll
-        for (int f = 0; f < 16; ++f) F[f] = 0;
-        F[15] = ALL;
-        if (T.h.family == FAM_WEREWOLF) {
-            const uint4 c0 = *reinterpret_cast<const uint4*>(base + sl * 16);
-            const uint4 c1 = *reinterpret_cast<const uint4*>(base + 512 + sl * 16);
-            const uint4 c2 = *reinterpret_cast<const uint4*>(base + 1024 + sl * 16);
-            F[0] = c0.z; F[1] = c0.w; F[2] = c1.x; F[3] = c1.y; F[4] = c1.z; F[5] = c1.w; F[6] = c2.x; F[7] = c2.y;
-            F[8] = c2.y ? ~(c2.z | c2.w) & ALL : 0u; F[9] = c2.z & ~c2.w; F[10] = ~c2.z & c2.w; F[11] = c2.z & c2.w;
-            F[12] = c2.y ? ALL : 0u;
-        } else {
-            for (int p = 0; p < P; ++p) {
-                const uint32_t fl = *reinterpret_cast<const uint32_t*>(base + rt_tile_off(8 + 4 * p, sl, n16)) >> 24;
-#pragma unroll
-                for (int f = 0; f < 5; ++f) F[f] |= ((fl >> f) & 1u) << p;
-            }
-        }
-        for (int j = 0; j < PL.n; ++j) {
-            const ge_pred_t pr = PL.p[j];
-            uint32_t res = 0;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
-                uint32_t m = ALL;
-#pragma unroll
-                for (int f = 0; f < 16; ++f) {
-                    if ((pos >> f) & 1u) m &= F[f];
-                    if ((neg >> f) & 1u) m &= ~F[f];
-                }
-                res |= m;
-            }
-            out[(o - first) * PL.n + j] = res;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------ table
 static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
@@ -1197,14 +771,6 @@ extern "C" int ge_counted_steps(ge_batch* b, uint64_t* out) {
     return GE_OK;
 }
 
-// Measurement helper: occupies `cuda_stream` for about `microseconds` (one thread spinning on %globaltimer).  A
-// benchmark enqueues it in front of its first timing event so that the host can queue the timed launches while
-// the device is still busy — the timed region then measures the device, not the host's launch rate from a cold queue.
-__global__ void k_delay(unsigned long long ns) {
-    unsigned long long t0, t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
-}
 extern "C" int ge_stream_delay(int device, void* cuda_stream, unsigned microseconds) {
     if (microseconds > 1000000u) return fail(GE_ERR_ARG, "ge_stream_delay: at most one second");
     CU(cudaSetDevice(device));
