@@ -55,9 +55,11 @@ class GpuReferee:
 
     # ---- the GPU step on one dict-described session
     def _gpu_step(self, before: np.ndarray) -> np.ndarray:
-        self.batch.import_state(before.reshape(1, -1))
-        self.batch.step(1)
-        return self.batch.export_state()[0]
+        # one C call: record in -> one step -> record out (ge_run_host), a single synchronisation
+        rec_in = np.ascontiguousarray(before.reshape(1, -1), dtype=np.uint8)
+        rec_out = np.empty_like(rec_in)
+        self.batch.run_host(rec_in, rec_out, 1)
+        return rec_out[0]
 
     def step_session(self, state: Dict[str, Any], now_ms: Optional[int] = None, now_iso: Optional[str] = None) -> Dict[str, Any]:
         """L1 adapter: AgentState dict -> union of the update dicts of the three hot-path nodes."""
