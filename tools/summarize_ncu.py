@@ -46,6 +46,8 @@ def main():
             e[n] = to_us(v, u) if n.startswith("gpu__time") else to_bytes(v, u) if "bytes" in n else v
     agg = collections.defaultdict(list)
     for e in data.values():
+        if e["k"].startswith("k_delay"):          # bench.py's head-start spin kernel: outside the timed region
+            continue
         agg[e["k"]].append(e)
     tot = sum(x.get("gpu__time_duration.sum", 0) for v in agg.values() for x in v)
     out = ["# %s — ncu launch list" % a.tag, "", "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
