@@ -965,6 +965,71 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const uint64_t n_tiles_act = (n_act + 31) >> 5;
     uint32_t present_out = 0;
     VisitAcc visits;
+    if (!full) {
+        // ---- light path: every phase present only rewrites the header (no actors, no predicate or value test, no
+        // entry effect behind its branches: DevTable::need).  Four tiles in flight per warp; a tile whose 32 sessions
+        // are all in the one live phase present takes a branch-free route, like the werewolf kernel's light path.
+        const uint32_t live_present = present_in & T.nonterm;
+        int x0 = -1; uint32_t y0 = 0, tag0 = 0;
+        if (__popc(live_present) == 1) {
+            const int x = __ffs(live_present) - 1;
+            if (T.phase[x].n_branches == 1 && T.phase[x].br[0].op == BR_ALWAYS) { x0 = x; y0 = T.phase[x].br[0].next; tag0 = T.phase[x].br[0].tag; }
+        }
+        const bool y0_live = x0 >= 0 && ((T.nonterm >> y0) & 1u);
+        const uint32_t hdr0 = y0 | ((uint32_t)x0 << 8);
+        const uint64_t full_tiles = n_act >> 5;
+        const uint32_t rem = (uint32_t)n_act & 31u;
+        const uint64_t tile_stride = nwarps * (uint64_t)(32 * S);
+        uint8_t* base = A.tiles + warp0 * (uint64_t)(32 * S) + lane * 16;
+        auto light = [&](uint4& c) -> int {             // one header-only step from the run-time table; -1 = terminal
+            const int X = c.x & 0xFF;
+            const ge_phase_t& ph = T.phase[X];
+            if (ph.kind == KIND_TERMINAL) return -1;
+            if ((c.x >> 16) == 0) { c.x = (c.x & 0xFFFFu) | (1u << 16); return X; }
+            int taken = ph.n_branches - 1;
+            for (int b = 0; b < ph.n_branches; ++b) {
+                const ge_branch_t br = ph.br[b];
+                const bool ok = br.op == BR_ALWAYS || (br.op == BR_PREV_IN && ((br.arg >> ((c.x >> 8) & 0xFF)) & 1u));
+                if (ok) { taken = b; break; }
+            }
+            const uint32_t tag = ph.br[taken].tag;
+            if (tag) c.y = (c.y & ~0xFF0000u) | (tag << 16);
+            c.x = (uint32_t)ph.br[taken].next | ((uint32_t)X << 8) | ((c.x & 0xFFFF0000u) + 0x10000u);
+            return ph.br[taken].next;
+        };
+        for (uint64_t tile = warp0; tile < n_tiles_act; tile += 4 * nwarps, base += 4 * tile_stride) {
+            uint4 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                c[j] = tile + j * nwarps < n_tiles_act ? ld128(base + j * tile_stride) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t t = tile + j * nwarps;
+                if (t < n_tiles_act) {                        // warp-uniform
+                    const bool in_range = t < full_tiles || (uint32_t)lane < rem;
+                    const bool fast = in_range && (int)(c[j].x & 0xFF) == x0 && (c[j].x >> 16) != 0;
+                    uint32_t lm;
+                    if (__ballot_sync(0xFFFFFFFFu, fast) == 0xFFFFFFFFu) {
+                        c[j].x = hdr0 | ((c[j].x & 0xFFFF0000u) + 0x10000u);
+                        if (tag0) c[j].y = (c[j].y & ~0xFF0000u) | (tag0 << 16);
+                        st128(base + j * tile_stride, c[j]);
+                        if ((int)y0 != visits.phase) { visits.flush(s_visits, lane); visits.phase = (int)y0; }
+                        visits.count += 32;
+                        present_out |= 1u << y0;
+                        lm = y0_live ? 0xFFFFFFFFu : 0u;
+                    } else {
+                        int np = -1;
+                        if (in_range) np = light(c[j]);
+                        if (np >= 0) st128(base + j * tile_stride, c[j]);
+                        visits.add(s_visits, np, lane);
+                        if (in_range) present_out |= 1u << (c[j].x & 31);
+                        lm = __ballot_sync(0xFFFFFFFFu, in_range && ((T.nonterm >> (c[j].x & 31)) & 1u));
+                    }
+                    if (lane == 0) { A.live_mask[t] = lm; if (A.count_live && lm) atomicAdd(A.live_count, (unsigned long long)__popc(lm)); }
+                }
+            }
+        }
+    } else
     for (uint64_t tile = warp0; tile < n_tiles_act; tile += nwarps) {
         uint8_t* base = A.tiles + tile * (uint64_t)(32 * S);
         const uint64_t sess = tile * 32 + lane;
