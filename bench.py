@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--autoreset", action="store_true",
                     help="re-initialise a batch on the device as soon as all its games are over (ge_batch_set_autoreset) instead "
                          "of from the host after `cap` steps; measured: no gain at 2^20 sessions (some game always runs to the cap)")
+    ap.add_argument("--compaction", default="", help="active-prefix compaction 'every,shift' (default: the library's choice for the family)")
     ap.add_argument("--regroup", default="", help="phase regrouping 'every,shift' (default: the library's choice for the table)")
     ap.add_argument("--head-start-us", type=int, default=3000,
                     help="length of the spin kernel the timed launches are queued behind (host head start; 0 = none)")
@@ -334,6 +335,8 @@ def run_ours(a):
         b.set_grid(a.ctas_per_sm)
         if a.regroup:
             b.set_regroup(*[int(x) for x in a.regroup.split(",")])
+        if a.compaction:
+            b.set_compaction(*[int(x) for x in a.compaction.split(",")])
     # Steady state: a batch whose games are all over starts over with fresh session ids — from the host after `cap`
     # steps (the longest possible game; default) or, with --autoreset, on the device as soon as the periodic
     # compaction check finds no live session (ge_batch_set_autoreset).

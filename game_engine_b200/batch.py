@@ -75,7 +75,7 @@ class SessionBatch:
 
     def set_compaction(self, every_n_steps: int, min_dead_shift: int = 2) -> None:
         """Active-prefix compaction: check every n steps, compact when >= 1/2^shift of the prefix is dead
-        (0 steps = off; default (8, 2))."""
+        (0 steps = off; default (5, 2) for the werewolf family, off for TTL)."""
         capi.check(capi.lib().ge_batch_set_compaction(self._h, int(every_n_steps), int(min_dead_shift)))
 
     def set_grid(self, ctas_per_sm: int) -> None:

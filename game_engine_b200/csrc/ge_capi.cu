@@ -340,7 +340,11 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     b->scan_blocks = (int)((b->n_tiles + CS_TILES - 1) / CS_TILES);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_blk, ((size_t)b->scan_blocks + 2) * sizeof(uint32_t));
     b->dead_shift = 2;                                   // compact when >= 1/4 of the active prefix is dead
-    b->compact_every = b->scan_blocks <= 1024 ? 8 : 0;   // one finishing block scans the block totals
+    // Default cadence of the compaction check: every 5 steps for the werewolf family (measured best at 8 players:
+    // +7 % over every 8; neutral at 16 / 32), off for the TTL family, whose games all have the same length (nothing
+    // to compact until every game ends at once: the check only costs launches, −4 %).  One finishing block scans
+    // the block totals, hence the size limit.
+    b->compact_every = (b->scan_blocks <= 1024 && t->family == FAM_WEREWOLF) ? 5 : 0;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking);
     b->stream = b->own_stream;
     if (e != cudaSuccess) {
@@ -459,6 +463,8 @@ extern "C" int ge_batch_set_autoreset(ge_batch* b, uint64_t sid_stride) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     if (sid_stride != 0 && sid_stride < b->n) return fail(GE_ERR_ARG, "sid_stride must be 0 (off) or >= n_sessions (ids of different epochs must not overlap)");
     b->sid_stride = sid_stride;
+    if (sid_stride != 0 && b->compact_every == 0 && b->regroup_every == 0 && b->scan_blocks <= 1024)
+        b->compact_every = 8;                 // the check that notices "every game is over" rides on compaction
     return GE_OK;
 }
 

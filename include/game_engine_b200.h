@@ -93,7 +93,8 @@ int ge_batch_set_kernel(ge_batch *b, int kernel);
 /* Active-prefix compaction (thread-per-session kernels): every `every_n_steps` launches a device-side check
  * runs and, when at least 1/2^min_dead_shift of the active prefix holds finished games, the live sessions
  * are swapped in front of them (on the device, no host sync) so later launches walk only the live prefix.
- * Session ids, export order and statistics are unaffected.  every_n_steps = 0 turns it off; default (8, 2).
+ * Session ids, export order and statistics are unaffected.  every_n_steps = 0 turns it off; default (5, 2) for the
+ * werewolf family and off for the TTL family (fixed-length games: nothing to compact).
  * ge_batch_active returns the current prefix length (synchronises). */
 int ge_batch_set_compaction(ge_batch *b, int every_n_steps, int min_dead_shift);
 int ge_batch_active(ge_batch *b, uint64_t *out);
@@ -115,7 +116,7 @@ int ge_batch_set_regroup(ge_batch *b, int every_n_steps, int min_mixed_shift);
  * every game of the batch is over, the batch starts its next EPOCH on the device — final-state histograms folded
  * into the statistics, all slots re-initialised, session i gets id first_session_id + epoch * sid_stride + i — with
  * no host round trip and no launches wasted on finished games.  Needs compaction or regrouping on (the thread-per-
- * session kernels); sid_stride must be >= n_sessions.  ge_batch_reset returns to epoch 0.  ge_batch_epochs
+ * session kernels; switched on (8, 2) if neither is); sid_stride must be >= n_sessions.  ge_batch_reset returns to epoch 0.  ge_batch_epochs
  * reports the number of device-side re-initialisations so far (synchronises). */
 int ge_batch_set_autoreset(ge_batch *b, uint64_t sid_stride);
 int ge_batch_epochs(ge_batch *b, uint64_t *out);

@@ -30,7 +30,7 @@ def test_full_size_run(games, oracle_for, game, P, n):
     tab = Table(cg)
     first, seed, cap = 3 << 40, 20261018, _cap(cg, game, P)
     b = SessionBatch(tab, n, first_session_id=first, seed=seed)
-    b.step(cap)
+    b.step(cap + 5)                 # the longest possible game, plus no-op launches up to the next compaction check
     st = b.stats()
     kinds = np.array([p.kind for p in cg.table.phases])
     # ---- internal consistency
