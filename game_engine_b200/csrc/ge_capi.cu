@@ -374,7 +374,7 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     for (int i = 0; i < t->dev.h.n_phases; ++i)
         for (int k = 0; k < t->dev.phase[i].n_branches; ++k)
             if (t->dev.phase[i].br[k].op == BR_TIE_PENDING) desync = true;
-    if (rc == GE_OK && desync && t->family == FAM_WEREWOLF && b->n <= (1ull << 31)) rc = ge_batch_set_regroup(b, 8, 3);
+    if (rc == GE_OK && desync && t->family == FAM_WEREWOLF && b->n <= (1ull << 31)) rc = ge_batch_set_regroup(b, 5, 3);
     if (rc != GE_OK) { ge_batch_destroy(b); return rc; }
     *out = b;
     return GE_OK;

@@ -109,7 +109,7 @@ int ge_batch_set_grid(ge_batch *b, int ctas_per_sm);
  * threshold of dead sessions is reached), the active prefix is counting-sorted by phase, finished games last, so
  * that a warp's 32 sessions share a phase again.  Needed by tables whose sessions de-synchronise (loops of
  * data-dependent length such as tie -> re-vote); it replaces the swap compaction while on and is enabled
- * automatically (8, 3) for tables that use the TIE_PENDING branch.  Costs a second session store.  Results,
+ * automatically (5, 3) for tables that use the TIE_PENDING branch.  Costs a second session store.  Results,
  * session ids, export order and statistics are unaffected.  every_n_steps = 0 turns it off. */
 int ge_batch_set_regroup(ge_batch *b, int every_n_steps, int min_mixed_shift);
 /* Auto-reset (continuous simulation): with sid_stride != 0, whenever the compaction / regrouping check finds that
