@@ -113,7 +113,6 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             return fail(GE_ERR_ARG, "entry effect of another rule family");
         if (ph.kind == KIND_ACTION && (ph.action_op < ACT_PICK_PLAYER || ph.action_op > ACT_MARK)) return fail(GE_ERR_ARG, "action phase without an action op");
         if (wolfy && ph.exit_op != EX_NONE && ph.action_op != ACT_PICK_PLAYER) return fail(GE_ERR_ARG, "werewolf exit effects record a chosen player: the action must be PICK_PLAYER");
-        if (!wolfy && ph.kind == KIND_ACTION && ph.action_op == ACT_PICK_PLAYER) return fail(GE_ERR_ARG, "the TTL family has no player picks (PICK_OPTION or MARK)");
         if (ph.kind == KIND_ACTION) {
             if (ph.actor_pred >= h.n_preds) return fail(GE_ERR_ARG, "actor predicate out of range");
             if (ph.action_op == ACT_PICK_PLAYER && ph.action_arg >= h.n_preds) return fail(GE_ERR_ARG, "legal-set predicate out of range");
@@ -155,7 +154,7 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
         if (h.family != FAM_WEREWOLF) {
             // TTL: bit2 = the player words (everything but column 0's header), bit3 = session id.  Header-only
             // phases: no actors, no predicate / value test in the branches, no entry effect on the way out.
-            if (ph.kind == KIND_ACTION) need |= 4 | (ph.action_op == ACT_PICK_OPTION ? 8 : 0);
+            if (ph.kind == KIND_ACTION) need |= 4 | (ph.action_op != ACT_MARK ? 8 : 0);
             for (int b = 0; b < ph.n_branches; ++b) {
                 const ge_branch_t& br = ph.br[b];
                 if (br.op == BR_COUNT_EQ0 || br.op == BR_COUNT_GE || br.op == BR_ALL_VAL_GE) need |= 4;

@@ -363,7 +363,16 @@ k_step_t_coop(const __grid_constant__ DevTable T, const __grid_constant__ StepAr
                 i_act = is_player && (actors & me);
                 const uint4 r4 = philox4x32_10((uint32_t)sid, (uint32_t)(sid >> 32), step0, (uint32_t)(p >> 2), k0, k1);
                 const uint32_t r = word_of(r4, p & 3);
-                if (i_act) choice = ph.action_op == ACT_PICK_OPTION ? 1u + __umulhi(r, (uint32_t)ph.action_arg) : 1u;
+                if (i_act) {
+                    if (ph.action_op == ACT_PICK_PLAYER) {
+                        uint32_t legal = pred(ph.action_arg);
+                        if (ph.action_flags & 1) legal &= ~me;
+                        const uint32_t n = __popc(legal);
+                        choice = n ? 1u + (uint32_t)kth_set_bit<PB>(legal, __umulhi(r, n)) : 0u;
+                    } else {
+                        choice = ph.action_op == ACT_PICK_OPTION ? 1u + __umulhi(r, (uint32_t)ph.action_arg) : 1u;
+                    }
+                }
             }
             const int la = actors ? __ffs(actors) - 1 : 0;
             const uint32_t first_choice = __shfl_sync(0xFFFFFFFFu, choice, gshift + la);

@@ -836,18 +836,26 @@ __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s
     if (v.kind() == KIND_ACTION) {
         const uint32_t actors = t_pred(v, field, v.actor_pred(), ALL);
         const int aop = v.action_op(), exo = v.exit_op();
+        const uint32_t legal0 = aop == ACT_PICK_PLAYER ? t_pred(v, field, v.action_arg(), ALL) : 0u;
         uint32_t first_choice = 0; bool have_first = false;
 #pragma unroll
         for (int b = 0; b < PB / 4; ++b) {
             const uint32_t ab = (actors >> (4 * b)) & 0xFu;
             if (ab) {
                 uint4 r4 = make_uint4(0, 0, 0, 0);
-                if (aop == ACT_PICK_OPTION) r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, A.rk);     // MARK draws nothing
+                if (aop != ACT_MARK) r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)b, A.rk);     // MARK draws nothing
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int p = 4 * b + j;
                     if ((ab >> j) & 1u) {
-                        const uint32_t choice = aop == ACT_PICK_OPTION ? 1u + __umulhi(word_of(r4, j), (uint32_t)v.action_arg()) : 1u;
+                        uint32_t choice;
+                        if (aop == ACT_PICK_PLAYER) {
+                            const uint32_t legal = (v.action_flags() & 1) ? legal0 & ~(1u << p) : legal0;
+                            const uint32_t n = __popc(legal);
+                            choice = n ? 1u + (uint32_t)kth_set_bit<PB>(legal, __umulhi(word_of(r4, j), n)) : 0u;
+                        } else {
+                            choice = aop == ACT_PICK_OPTION ? 1u + __umulhi(word_of(r4, j), (uint32_t)v.action_arg()) : 1u;
+                        }
                         if (!have_first) { first_choice = choice; have_first = true; }
                         if (exo == EX_T_VOTES) s.pw[p] = (s.pw[p] & 0xFF00FFFFu) | (choice << 16);
                     }

@@ -77,7 +77,6 @@ static int tab_open(tab_t *t, const uint8_t *blob, size_t n) {
             if (aop == ACT_PICK_PLAYER && ph[3] >= t->n_preds) return -1;
             if (aop == ACT_PICK_OPTION && ph[3] == 0) return -1;
             if (wolfy && exo != EX_NONE && aop != ACT_PICK_PLAYER) return -1;
-            if (!wolfy && aop == ACT_PICK_PLAYER) return -1;
         }
         for (int b = 0; b < nbr; ++b) {
             const uint8_t *br = ph + 16 + 8 * b;

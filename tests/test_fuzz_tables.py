@@ -51,7 +51,7 @@ def random_table(seed: int, family: int) -> T.Table:
             ph.entry_op = T.EN_ASSIGN_ROLES                          # most werewolf predicates need roles
         if kind == T.KIND_ACTION:
             ph.actor_pred = int(rng.integers(0, npred))
-            ph.action_op = int(rng.choice([T.ACT_PICK_PLAYER, T.ACT_PICK_OPTION, T.ACT_MARK] if wolf else [T.ACT_PICK_OPTION, T.ACT_MARK]))
+            ph.action_op = int(rng.choice([T.ACT_PICK_PLAYER, T.ACT_PICK_OPTION, T.ACT_MARK]))
             if rng.random() < 0.75:
                 ph.exit_op = int(rng.choice(exits))
                 if wolf:
