@@ -170,3 +170,79 @@ def test_interpreter_kernels_match_oracle_on_random_tables(family, kernel):
     next(p for p in bad.phases if p.kind in (T.KIND_UI, T.KIND_TIMER)).exit_op = T.EX_DAY_VOTE if family == T.FAMILY_WEREWOLF else T.EX_T_VOTES
     with pytest.raises(GameEngineError):
         Table(_Blob(bad))
+
+
+def test_library_and_oracle_validators_agree_on_mutated_blobs(games):
+    """Random byte mutations of valid tables: ge_table_create (CUDA library, validates on the host) and Oracle B's
+    tab_open must take the same accept / reject decision — a blob only one side accepts could not be parity-tested."""
+    import ctypes
+    from game_engine_b200 import capi
+    from oracle.oracle import Oracle
+    L = capi.lib()
+    rng = np.random.default_rng(99)
+    blobs = [games("werewolf-(mafia)", 8).blob, games("two-truths-and-a-lie", 4).blob, games("werewolf-revote", 32).blob,
+             random_table(5, T.FAMILY_WEREWOLF).pack(), random_table(6, T.FAMILY_TTL).pack()]
+    accepted = rejected = 0
+    for trial in range(600):
+        blob = bytearray(blobs[trial % len(blobs)])
+        for _ in range(int(rng.integers(1, 4))):
+            blob[int(rng.integers(4, len(blob)))] = int(rng.integers(0, 256)) if rng.random() < 0.5 else int(rng.integers(0, 8))
+        if rng.random() < 0.1:
+            blob = blob[: int(rng.integers(8, len(blob)))]
+        buf = ctypes.create_string_buffer(bytes(blob), len(blob))
+        h = ctypes.c_void_p()
+        lib_ok = L.ge_table_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), ctypes.byref(h)) == 0
+        if lib_ok:
+            L.ge_table_destroy(h)
+        try:
+            Oracle(bytes(blob))
+            ora_ok = True
+        except ValueError:
+            ora_ok = False
+        assert lib_ok == ora_ok, "trial %d: library %s, oracle %s\n%s" % (trial, lib_ok, ora_ok, bytes(blob).hex())
+        accepted += lib_ok
+        rejected += not lib_ok
+    assert accepted > 50 and rejected > 50
+
+
+@pytest.mark.gpu
+def test_accepted_mutated_blobs_run_identically(games):
+    """Whatever the validators let through must run the same on the GPU (interpreter kernel) and on Oracle B."""
+    import ctypes
+    from game_engine_b200 import capi
+    from game_engine_b200.batch import SessionBatch, Table
+    from oracle.oracle import Oracle
+    L = capi.lib()
+    rng = np.random.default_rng(123)
+    blobs = [games("werewolf-(mafia)", 8).blob, games("two-truths-and-a-lie", 4).blob, random_table(5, T.FAMILY_WEREWOLF).pack(),
+             random_table(6, T.FAMILY_TTL).pack()]
+    ran = 0
+    for trial in range(400):
+        blob = bytearray(blobs[trial % len(blobs)])
+        for _ in range(int(rng.integers(1, 3))):
+            blob[int(rng.integers(32, len(blob)))] = int(rng.integers(0, 6))
+        blob = bytes(blob)
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        h = ctypes.c_void_p()
+        if L.ge_table_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), ctypes.byref(h)) != 0:
+            continue
+        L.ge_table_destroy(h)
+        if blob in blobs or ran >= 40:
+            continue
+
+        class _B:
+            pass
+        cg = _B()
+        cg.blob, cg.audience_preds = blob, {}
+        cg.record_size = T.record_size(blob[6], blob[8])
+        o = Oracle(blob)
+        n, first, seed = 300, 17, trial
+        b = SessionBatch(Table(cg), n, first_session_id=first, seed=seed, kernel="tps")
+        rec = o.init(n)
+        for k in range(24):
+            b.step(1)
+            o.step(rec, first, seed, 1)
+            assert np.array_equal(b.export_state(), rec), "trial %d step %d blob %s" % (trial, k, blob.hex())
+        b.close()
+        ran += 1
+    assert ran >= 20
