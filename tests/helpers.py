@@ -1,7 +1,6 @@
 """Shared test helpers: replaying packed records through the host adapter and normalising dict states."""
 import copy
 
-import numpy as np
 
 KEEP = ("current_phase_id", "current_phase_name", "player_states", "playerActions", "phase_history", "game_notes")
 

@@ -6,7 +6,6 @@ import gzip
 import json
 import os
 
-import numpy as np
 import pytest
 
 from helpers import first_diff, normalise, replay_records

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import KEEP, first_diff, normalise, oracle_b_records
+from helpers import first_diff, normalise, oracle_b_records
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.json.gz")))
 

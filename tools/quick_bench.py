@@ -10,7 +10,6 @@ import torch  # noqa: E402
 
 from game_engine_b200 import compile_game  # noqa: E402
 from game_engine_b200.batch import Table, SessionBatch  # noqa: E402
-from game_engine_b200 import table as T  # noqa: E402
 
 
 def main():
