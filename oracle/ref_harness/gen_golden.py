@@ -21,6 +21,10 @@ CASES = [
     ("werewolf-(mafia)", 8, 0, 0), ("werewolf-(mafia)", 8, 1, 1), ("werewolf-(mafia)", 8, 7, 123456789012),
     ("werewolf-(mafia)", 8, 20261018, 4242), ("werewolf-(mafia)", 5, 3, 3), ("werewolf-(mafia)", 16, 4, 9),
     ("werewolf-(mafia)", 32, 6, 31),
+    # more player counts (minimum table sizes, odd counts, the 24-player bucket) and seeds
+    ("werewolf-(mafia)", 4, 21, 1000), ("werewolf-(mafia)", 6, 22, 1001), ("werewolf-(mafia)", 7, 23, 1002),
+    ("werewolf-(mafia)", 12, 24, 1003), ("werewolf-(mafia)", 24, 25, 1004),
+    ("two-truths-and-a-lie", 5, 26, 1005), ("two-truths-and-a-lie", 8, 27, 1006), ("two-truths-and-a-lie", 16, 28, 1007),
     # third table: the reference's earlier 13-phase werewolf generation (game_draft/), aliased state schema
     ("werewolf-draft", 8, 11, 77), ("werewolf-draft", 6, 12, 1 << 36), ("werewolf-draft", 12, 13, 5),
 ]
@@ -32,6 +36,9 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else None          # optional: regenerate one game's fixtures
     for game, P, seed, sid in CASES:
         if only and game != only:
+            continue
+        name = "%s_p%d_seed%d_sid%d.json.gz" % (game.replace("(", "").replace(")", ""), P, seed, sid)
+        if os.environ.get("GOLDEN_ONLY_MISSING") and os.path.exists(os.path.join(out_dir, name)):
             continue
         trace = run_session(game, P, seed, sid)
         name = "%s_p%d_seed%d_sid%d.json.gz" % (game.replace("(", "").replace(")", ""), P, seed, sid)

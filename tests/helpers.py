@@ -60,3 +60,13 @@ def first_diff(a, b, path=""):
                 return d
         return None
     return None if a == b else "%s: %r != %r" % (path, a, b)
+
+
+def pick(paths, *needles):
+    """Fixtures whose file name contains one of the needles, in the order given (stable under new fixtures)."""
+    out = []
+    for nd in needles:
+        hit = [p for p in paths if nd in p.rsplit("/", 1)[-1]]
+        assert len(hit) == 1, (nd, hit)
+        out.append(hit[0])
+    return out
