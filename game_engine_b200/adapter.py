@@ -158,6 +158,9 @@ class SessionCodec:
                 }
                 if "team_is_wolf" in self.dsl_name:
                     entry["team_is_wolf"] = assigned and bit(rec.wolf)
+                if cg.session_fields:       # session-level re-vote state, carried by every player (rules session_fields)
+                    entry[cg.session_fields["revote_count"]] = rec.revote & 0x7F
+                    entry[cg.session_fields["tie_pending"]] = bool(rec.revote & 0x80)
                 if self.dsl_name:
                     entry = {self._k(k): v for k, v in entry.items()}
                 if prev_ps is not None:
@@ -224,7 +227,11 @@ class SessionCodec:
             winner = 0
             if cg.table.phases[phase].kind == T.KIND_TERMINAL:
                 winner = 1 if (wolf & alive) == 0 else 2
-            r[4], r[5], r[6], r[7] = winner, kill, protect, 0
+            revote = 0
+            if cg.session_fields:           # every player carries the same value; the lowest id is read
+                g0 = get(0)
+                revote = (int(g0.get(cg.session_fields["revote_count"]) or 0) & 0x7F) | (0x80 if g0.get(cg.session_fields["tie_pending"]) else 0)
+            r[4], r[5], r[6], r[7] = winner, kill, protect, revote
             for i, v in enumerate((alive, can_vote, elig, sub, rev, inv, wolf, secret, lo, hi)):
                 put32(8 + 4 * i, v)
             for p in range(P):
@@ -350,6 +357,8 @@ class SessionCodec:
             elif ex == T.EX_DAY_VOTE:
                 if died:
                     out.append(("CRITICAL", "Player %d (%s) was eliminated by day vote - marked is_alive=false" % (died[0] + 1, role_of(died[0]))))
+                elif a.revote & 0x80:
+                    out.append(("DECISION", "Day vote tied - re-vote %d of %d" % (a.revote & 0x7F, cg.table.max_revotes)))
                 else:
                     out.append(("DECISION", "Day vote produced no elimination"))
             if en == T.EN_ASSIGN_ROLES:

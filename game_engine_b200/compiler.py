@@ -240,6 +240,9 @@ class CompiledGame:
     audience_preds: Dict[str, Tuple[int, int, int, int]] = field(default_factory=dict)
     field_alias: Dict[str, str] = field(default_factory=dict)      # DSL field name -> canonical field name
     dsl: Dict[str, Any] = field(default_factory=dict)
+    # session-level record items that the DSL carries in per-player fields (rules `session_fields:`): the re-vote
+    # counter and the tie flag of tables with max_revotes > 0 ("revote_count" / "tie_pending" -> DSL field name)
+    session_fields: Dict[str, str] = field(default_factory=dict)
 
     @property
     def record_size(self) -> int:
@@ -301,6 +304,16 @@ def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: O
             raise DSLCompileError("rules alias %r is not a field of the DSL's player_states_template" % dsl_name)
         if canon not in fields and canon not in CANONICAL_EXTRA:
             raise DSLCompileError("rules alias %r -> %r: unknown canonical field" % (dsl_name, canon))
+    session_fields = {str(k): str(v) for k, v in (rules.get("session_fields") or {}).items()}
+    for item, dsl_name in session_fields.items():
+        if item not in ("revote_count", "tie_pending"):
+            raise DSLCompileError("rules session_fields: unknown item %r" % item)
+        if dsl_name not in tpl:
+            raise DSLCompileError("rules session_fields %r -> %r: not a field of the DSL's player_states_template" % (item, dsl_name))
+    if fam == T.FAMILY_WEREWOLF and max_revotes > 0 and set(session_fields) != {"revote_count", "tie_pending"}:
+        # without them the dict state cannot say "a tied vote is pending": the drop-in nodes would silently take the
+        # no-tie branch (the record is rebuilt from the dict on every step)
+        raise DSLCompileError("a table with max_revotes > 0 needs rules session_fields for revote_count and tie_pending")
     init_masks = 0
     for name, val in tpl.items():
         fid = fields.get(alias.get(name, name))
@@ -397,5 +410,5 @@ def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: O
         name=game, family=fam, n_players=n_players, table=tab, blob=tab.pack(), phase_ids=ids,
         phase_names=[get(p).get("name", "Phase %d" % p) for p in ids], role_names=role_names,
         teams=(village_team, wolf_team), action_text=action_text, template=tpl, audience_preds=aud, dsl=dsl,
-        field_alias=alias,
+        field_alias=alias, session_fields=session_fields,
     )

@@ -20,7 +20,12 @@ KEEP = ("current_phase_id", "current_phase_name", "player_states", "playerAction
 
 # Games the reference's own loader (agent/tools/utils.py:557-581: games/<gameName>.yaml) finds under another name:
 # its earlier werewolf generation lives in game_draft/, reachable through a relative gameName.
-REFERENCE_GAME_NAME = {"werewolf-draft": "../game_draft/werewolf-(mafia)"}
+REFERENCE_GAME_NAME = {
+    "werewolf-draft": "../game_draft/werewolf-(mafia)",
+    # the repo's extended game (tie -> re-vote, BASELINE config 4), loaded by the reference's loader from this repo
+    "werewolf-revote": os.path.relpath(os.path.join(REPO, "game_engine_b200", "games", "werewolf-revote"),
+                                       os.path.join(shims.REFERENCE_ROOT, "games")),
+}
 
 
 def load_rules(game: str) -> dict:

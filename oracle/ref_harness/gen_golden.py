@@ -27,6 +27,10 @@ CASES = [
     ("two-truths-and-a-lie", 5, 26, 1005), ("two-truths-and-a-lie", 8, 27, 1006), ("two-truths-and-a-lie", 16, 28, 1007),
     # third table: the reference's earlier 13-phase werewolf generation (game_draft/), aliased state schema
     ("werewolf-draft", 8, 11, 77), ("werewolf-draft", 6, 12, 1 << 36), ("werewolf-draft", 12, 13, 5),
+    # BASELINE config 4's table: the repo's extended game (tie -> re-vote phases), run by the reference's own nodes;
+    # sid 3010 uses both re-votes of a day and its third vote is tied again (lowest id among the tied dies)
+    ("werewolf-revote", 8, 42, 2001), ("werewolf-revote", 8, 46, 3010), ("werewolf-revote", 5, 44, 2003),
+    ("werewolf-revote", 16, 45, 7), ("werewolf-revote", 32, 43, 2002),
 ]
 
 

@@ -78,6 +78,10 @@ class StubChatModel:
     def F(self, canon: str) -> str:
         return self.dsl_name.get(canon, canon)
 
+    def _sf(self, item: str) -> str:
+        """DSL per-player field that carries a session-level item (rules `session_fields:`; extended re-vote game)."""
+        return (self.rules.get("session_fields") or {}).get(item, item)
+
     def bind_tools(self, tools, **kw):
         return _Bound(self, frozenset(t.name for t in tools))
 
@@ -148,6 +152,7 @@ class StubChatModel:
                 op = a["op"]
                 ok = (op == "ALWAYS" or (op == "COUNT_EQ0" and cnt(a["a"]) == 0) or (op == "COUNT_GE" and cnt(a["a"]) >= cnt(a["b"]))
                       or (op == "PREV_IN" and prev in a["phases"])
+                      or (op == "TIE_PENDING" and bool(self._ps(ids[0]).get(self._sf("tie_pending"))))
                       or (op == "ALL_VAL_GE" and all((self._ps(i).get(a["field"]) or 0) >= (self.rules["rounds"] if a["value"] == "rounds" else int(a["value"])) for i in ids)))
                 if ok:
                     target, why = nxt[a["key"]]["id"], a["key"]
@@ -215,13 +220,25 @@ class StubChatModel:
         if ex == "DAY_VOTE":
             for i in actors:
                 upd(i, "selected_target_id", choice[i])
-            x = plurality([choice[i] for i in actors])
-            if x:
-                role = self._ps(x)["role"]
-                die(x); upd(x, "role_revealed", True)
-                note("CRITICAL", "Player %d (%s) was eliminated by day vote - marked is_alive=false" % (x, role))
+            votes = [choice[i] for i in actors if choice[i]]
+            x = plurality(votes)
+            R = int(self.rules.get("max_revotes") or 0)
+            used = int(self._ps(ids[0]).get(self._sf("revote_count")) or 0) if R else 0
+            tied = x != 0 and sum(1 for c in set(votes) if votes.count(c) == votes.count(x)) > 1
+            if R and tied and used < R:             # SPEC section 4, EX_DAY_VOTE with max_revotes > 0: nobody dies
+                for i in ids:
+                    upd(i, self._sf("revote_count"), used + 1); upd(i, self._sf("tie_pending"), True)
+                note("DECISION", "Day vote tied - re-vote %d of %d" % (used + 1, R))
             else:
-                note("DECISION", "Day vote produced no elimination")
+                if R:
+                    for i in ids:
+                        upd(i, self._sf("tie_pending"), False)
+                if x:
+                    role = self._ps(x)["role"]
+                    die(x); upd(x, "role_revealed", True)
+                    note("CRITICAL", "Player %d (%s) was eliminated by day vote - marked is_alive=false" % (x, role))
+                else:
+                    note("DECISION", "Day vote produced no elimination")
         if ex == "T_STATEMENTS":
             for i in actors:
                 upd(i, "statements", {str(k + 1): s for k, s in enumerate(TTL_STATEMENTS)}); upd(i, "statements_submitted", True)
@@ -249,6 +266,8 @@ class StubChatModel:
         if en == "NIGHT_RESET":
             for i in ids:
                 upd(i, "night_action_submitted", False); upd(i, "selected_target_id", 0)
+                if self.rules.get("max_revotes"):
+                    upd(i, self._sf("revote_count"), 0); upd(i, self._sf("tie_pending"), False)
         if en == "T_ROUND_START":
             R = int(self.rules["rounds"])
             pending = [i for i in ids if (self._ps(i).get("rounds_as_speaker") or 0) < R]

@@ -42,7 +42,8 @@ def test_gpu_records_expand_to_the_reference_trace(path, kernel, games):
     _assert_traces_equal(g["trace"], replay_records(cg, recs))
 
 
-@pytest.mark.parametrize("path", pick(GOLDEN, "lie_p3_", "lie_p4_seed0_", "lie_p5_", "draft_p6_", "draft_p8_", "mafia_p4_", "mafia_p8_seed1_", "mafia_p16_"),
+@pytest.mark.parametrize("path", pick(GOLDEN, "lie_p3_", "lie_p4_seed0_", "lie_p5_", "draft_p6_", "draft_p8_", "mafia_p4_", "mafia_p8_seed1_", "mafia_p16_",
+                                             "revote_p8_seed42_", "revote_p8_seed46_", "revote_p16_"),
                          ids=lambda p: os.path.basename(p)[:-8])
 def test_step_session_chain(path):
     """L1 adapter: dict in -> dict out, every step rebuilt from the dict alone (no hidden device state)."""
@@ -60,7 +61,7 @@ def test_step_session_chain(path):
     assert first_diff(normalise({**state, **again}), trace[-1]) is None
 
 
-@pytest.mark.parametrize("path", pick(GOLDEN, "lie_p4_seed0_", "draft_p12_", "mafia_p8_seed7_"), ids=lambda p: os.path.basename(p)[:-8])
+@pytest.mark.parametrize("path", pick(GOLDEN, "lie_p4_seed0_", "draft_p12_", "mafia_p8_seed7_", "revote_p8_seed46_"), ids=lambda p: os.path.basename(p)[:-8])
 def test_drop_in_nodes_follow_the_reference_graph(path):
     """BotBehaviorNode -> PhaseNode -> (RefereeNode | ActionExecutor) with the reference's goto targets and
     update keys (reference agent/game_agent_v2.py:609-617, 1043-1052, 1238-1241, 794-803)."""
@@ -92,7 +93,7 @@ def test_drop_in_nodes_follow_the_reference_graph(path):
     _assert_traces_equal(g["trace"], asyncio.run(run()))
 
 
-@pytest.mark.parametrize("path", pick(GOLDEN, "lie_p4_seed1_", "draft_p8_", "mafia_p12_"), ids=lambda p: os.path.basename(p)[:-8])
+@pytest.mark.parametrize("path", pick(GOLDEN, "lie_p4_seed1_", "draft_p8_", "mafia_p12_", "revote_p5_"), ids=lambda p: os.path.basename(p)[:-8])
 def test_v3_merged_node_follows_the_reference(path):
     """BotBehaviorNode -> ActionExecutorV3 (the newer graph, reference agent/game_agent_v3.py:1099-1117): same
     player_states / playerActions / phase ids as the v2 fixtures; history entries carry no timestamp and are only
