@@ -65,6 +65,9 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--e2e-calls", type=int, default=24)
     ap.add_argument("--e2e-subs", type=int, default=4, help="pipelined sub-batches of the end-to-end call")
+    ap.add_argument("--wire", default="dense", choices=["dense", "canonical"],
+                    help="record format of the end-to-end call's host buffers (dense: 32 / 48 bytes per session for werewolf "
+                         "tables up to 8 / 16 players, SPEC section 5b; other tables are canonical either way)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -261,6 +264,20 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------------------- our arm
+def stream_delay(device: int, stream: int, microseconds: int) -> None:
+    """Keeps a CUDA stream busy for about `microseconds` with a one-thread spin kernel from the bench-only helper
+    library (tools/benchaux, built by game_engine_b200/build.py; deliberately not part of the product ABI)."""
+    import ctypes
+    path = os.path.join(ROOT, "tools", "benchaux", "libge_benchaux.so")
+    if not os.path.exists(path):
+        from game_engine_b200 import build as _b
+        _b.build_aux()
+    lib = ctypes.CDLL(path)
+    lib.bx_stream_delay.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint]
+    if lib.bx_stream_delay(int(device), ctypes.c_void_p(stream), int(microseconds)) != 0:
+        raise RuntimeError("bx_stream_delay failed")
+
+
 class _CudaArray:
     """Minimal __cuda_array_interface__ view so torch can wrap the library's device statistics buffer."""
 
@@ -352,7 +369,7 @@ def run_ours(a):
         if pre:
             b.step(pre)
         age[i] = pre
-    from game_engine_b200.batch import step_many, stream_delay
+    from game_engine_b200.batch import step_many
     k_global = 0
     resets = 0
 
@@ -495,12 +512,15 @@ def run_ours(a):
         sub = N // NSUB
         subs = [SessionBatch(tab, sub, first_session_id=sid_base(1 << 20, 0) + j * sub, seed=a.seed, device=local_rank, kernel=a.kernel)
                 for j in range(NSUB)]
-        pin_in, pin_out, pin_st = PinnedBuffer(N * S), PinnedBuffer(N * S), PinnedBuffer(NSUB * 560 * 8)
-        rin = pin_in.array.reshape(NSUB, sub, S)
-        rout = pin_out.array.reshape(NSUB, sub, S)
+        for sb in subs:
+            sb.set_wire(a.wire)
+        W = subs[0].wire_record_size                          # bytes per session on the wire
+        pin_in, pin_out, pin_st = PinnedBuffer(N * W), PinnedBuffer(N * W), PinnedBuffer(NSUB * 560 * 8)
+        rin = pin_in.array.reshape(NSUB, sub, W)
+        rout = pin_out.array.reshape(NSUB, sub, W)
         rst = pin_st.array.view(np.uint64).reshape(NSUB, 560)
         for j, sb in enumerate(subs):
-            sb.export_state(out=rin[j])                       # canonical initial records, produced by the library
+            sb.export_state(out=rin[j])                       # initial records in the wire format, produced by the library
             sb.set_host_fused(True)                           # run-to-completion call: one fused launch per sub-batch
 
         def e2e_stream(n_calls, n_steps, src):
@@ -539,7 +559,8 @@ def run_ours(a):
             dt, e_counted, dt1, s_counted = float(emax[0]), float(esum[1]), float(emax[2]), float(esum[3])
         e2e = {
             "value": e_counted / dt, "unit": UNIT,
-            "h2d_bytes_per_step": N * S, "d2h_bytes_per_step": N * S + NSUB * 560 * 8,
+            "h2d_bytes_per_step": N * W, "d2h_bytes_per_step": N * W + NSUB * 560 * 8,
+            "wire": {"format": a.wire, "record_bytes": W, "canonical_record_bytes": S},
             "call": "%d back-to-back calls, each %d x SessionBatch.run_host_async (ge_run_host_async): pinned host records in -> "
                     "%d steps -> records + stats out for %d sessions in %d pipelined sub-batches; one sync at the end; bytes "
                     "are per call" % (a.e2e_calls, NSUB, cap, N, NSUB),

@@ -58,6 +58,15 @@ class SessionBatch:
         """Bind to an external CUDA stream handle (e.g. torch.cuda.Stream().cuda_stream); 0 = own stream."""
         capi.check(capi.lib().ge_batch_set_stream(self._h, ctypes.c_void_p(stream)))
 
+    def set_wire(self, wire: str) -> None:
+        """Record format of the host-buffer calls: "canonical" (SPEC section 5) or "dense" (section 5b: 32 / 48 bytes
+        for werewolf tables up to 8 / 16 players; other tables keep the canonical record)."""
+        capi.check(capi.lib().ge_batch_set_wire(self._h, capi.WIRE_NAMES[wire]))
+
+    @property
+    def wire_record_size(self) -> int:
+        return int(capi.lib().ge_batch_wire_size(self._h))
+
     def set_kernel(self, kernel: str) -> None:
         capi.check(capi.lib().ge_batch_set_kernel(self._h, capi.KERNEL_NAMES[kernel]))
 
@@ -127,7 +136,7 @@ class SessionBatch:
     # ---- state
     def export_state(self, first: int = 0, count: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
         count = self.n - first if count is None else int(count)
-        S = self.table.record_size
+        S = self.wire_record_size
         if out is None:
             out = np.empty((count, S), dtype=np.uint8)
         assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == count * S
@@ -136,7 +145,7 @@ class SessionBatch:
 
     def import_state(self, records: np.ndarray, first: int = 0) -> None:
         rec = np.ascontiguousarray(records, dtype=np.uint8)
-        S = self.table.record_size
+        S = self.wire_record_size
         assert rec.size % S == 0
         capi.check(capi.lib().ge_import_state(self._h, int(first), rec.size // S, rec.ctypes.data))
 
@@ -151,10 +160,24 @@ class SessionBatch:
     def run_host(self, records_in: Optional[np.ndarray], records_out: Optional[np.ndarray], n_steps: int,
                  stats_out: Optional[np.ndarray] = None) -> None:
         """End-to-end call with host buffers (H2D, n_steps steps, D2H); synchronous."""
-        pin = records_in.ctypes.data if records_in is not None else None
-        pout = records_out.ctypes.data if records_out is not None else None
-        pst = stats_out.ctypes.data if stats_out is not None else None
+        pin, pout, pst = self._host_args(records_in, records_out, stats_out)
         capi.check(capi.lib().ge_run_host(self._h, pin, pout, int(n_steps), pst))
+
+    def _host_args(self, records_in, records_out, stats_out):
+        """Pointers of the host-buffer call.  The library reads / writes n * S bytes behind them, so anything but a
+        C-contiguous uint8 array of exactly that size is refused here."""
+        need = self.n * self.wire_record_size
+        for name, arr in (("records_in", records_in), ("records_out", records_out)):
+            if arr is not None and not (isinstance(arr, np.ndarray) and arr.dtype == np.uint8 and arr.flags.c_contiguous and arr.size == need):
+                raise ValueError("%s must be a C-contiguous uint8 array of %d bytes (%d sessions x %d)" % (name, need, self.n, self.wire_record_size))
+        if records_out is not None and not records_out.flags.writeable:
+            raise ValueError("records_out must be writeable")
+        if stats_out is not None and not (isinstance(stats_out, np.ndarray) and stats_out.dtype == np.uint64 and stats_out.flags.c_contiguous
+                                          and stats_out.size >= capi.STATS_LEN):
+            raise ValueError("stats_out must be a C-contiguous uint64 array of at least %d words" % capi.STATS_LEN)
+        return (records_in.ctypes.data if records_in is not None else None,
+                records_out.ctypes.data if records_out is not None else None,
+                stats_out.ctypes.data if stats_out is not None else None)
 
     def set_host_fused(self, on: bool) -> None:
         """Host-buffer calls apply their n_steps in one fused launch (state in registers) when on."""
@@ -163,9 +186,7 @@ class SessionBatch:
     def run_host_async(self, records_in: Optional[np.ndarray], records_out: Optional[np.ndarray], n_steps: int,
                        stats_out: Optional[np.ndarray] = None) -> None:
         """run_host without the final synchronisation (pinned buffers; call sync() before reading them)."""
-        pin = records_in.ctypes.data if records_in is not None else None
-        pout = records_out.ctypes.data if records_out is not None else None
-        pst = stats_out.ctypes.data if stats_out is not None else None
+        pin, pout, pst = self._host_args(records_in, records_out, stats_out)
         capi.check(capi.lib().ge_run_host_async(self._h, pin, pout, int(n_steps), pst))
 
     def eval_preds(self, preds, first: int = 0, count: Optional[int] = None) -> np.ndarray:
@@ -233,11 +254,6 @@ def step_many(batches, n_rounds: int = 1) -> None:
     """n_rounds round-robin passes: one step of every batch in order (one C call; see ge_step_many)."""
     arr = (ctypes.c_void_p * len(batches))(*[b._h for b in batches])
     capi.check(capi.lib().ge_step_many(arr, len(batches), int(n_rounds)))
-
-
-def stream_delay(device: int, stream: int, microseconds: int) -> None:
-    """Measurement helper: keeps a CUDA stream busy for about `microseconds` (see ge_stream_delay)."""
-    capi.check(capi.lib().ge_stream_delay(int(device), ctypes.c_void_p(stream), int(microseconds)))
 
 
 class PinnedBuffer:

@@ -17,6 +17,11 @@ NVCC_FLAGS = [
 ]
 
 
+# bench-only helper (head-start spin kernel): kept OUT of the product library
+AUX_SRC = os.path.join(os.path.dirname(_HERE), "tools", "benchaux", "ge_benchaux.cu")
+AUX_LIB = os.path.join(os.path.dirname(_HERE), "tools", "benchaux", "libge_benchaux.so")
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -25,11 +30,22 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_aux() -> str:
+    if os.path.exists(AUX_SRC) and (not os.path.exists(AUX_LIB) or os.path.getmtime(AUX_LIB) < os.path.getmtime(AUX_SRC)):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", AUX_LIB, AUX_SRC], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout)
+            raise RuntimeError("nvcc failed on the bench helper (exit %d)" % res.returncode)
+    return AUX_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     # constexpr views of the shipped games' tables (regenerated only when their content changes)
     sys.path.insert(0, os.path.dirname(_HERE))
     from game_engine_b200 import specgen
     specgen.write()
+    build_aux()
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libgame_engine_b200.so")
 STATS_LEN = 560
 GE_OK, GE_ERR_ARG, GE_ERR_CUDA, GE_ERR_UNSUPPORTED, GE_ERR_NOMEM = 0, -1, -2, -3, -4
 KERNEL_AUTO, KERNEL_COOP, KERNEL_TPS, KERNEL_TPS_GENERIC = 0, 1, 2, 3
+WIRE_CANONICAL, WIRE_DENSE = 0, 1
+WIRE_NAMES = {"canonical": WIRE_CANONICAL, "dense": WIRE_DENSE}
 KERNEL_NAMES = {"auto": KERNEL_AUTO, "coop": KERNEL_COOP, "tps": KERNEL_TPS, "tps_generic": KERNEL_TPS_GENERIC}
 
 # every symbol include/game_engine_b200.h declares: (name, restype, argtypes)
@@ -30,6 +32,9 @@ SYMBOLS = [
     ("ge_batch_destroy", None, [_vp]),
     ("ge_batch_set_stream", _int, [_vp, _vp]),
     ("ge_batch_set_kernel", _int, [_vp, _int]),
+    ("ge_table_wire_size", _sz, [_vp, _int]),
+    ("ge_batch_set_wire", _int, [_vp, _int]),
+    ("ge_batch_wire_size", _sz, [_vp]),
     ("ge_batch_set_compaction", _int, [_vp, _int, _int]),
     ("ge_batch_set_regroup", _int, [_vp, _int, _int]),
     ("ge_batch_set_grid", _int, [_vp, _int]),
@@ -59,7 +64,6 @@ SYMBOLS = [
     ("ge_state_device_ptr", _vp, [_vp]),
     ("ge_state_device_bytes", _sz, [_vp]),
     ("ge_launch_count", _u64, [_vp]),
-    ("ge_stream_delay", _int, [_int, _vp, ctypes.c_uint]),
     ("ge_last_error", ctypes.c_char_p, []),
     ("ge_version", ctypes.c_char_p, []),
 ]

@@ -28,6 +28,12 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
             return fail(GE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
     } while (0)
 
+#define SYNC(b)                                                                                    \
+    do {                                                                                           \
+        const int rc_ = sync_and_check(b);                                                         \
+        if (rc_ != GE_OK) return rc_;                                                              \
+    } while (0)
+
 extern "C" const char* ge_last_error(void) { return g_err.c_str(); }
 extern "C" const char* ge_version(void) { return "game_engine_b200 0.1.0 (sm_100a)"; }
 
@@ -79,12 +85,35 @@ struct ge_batch {
     step_fn fn[4];               // by kernel id (COOP, TPS, TPS_GENERIC)
     int grid[4], occ[4];         // persistent grid size / occupancy limit (CTAs per SM) per kernel id
     uint64_t launches;
+    int wire;                     // host-buffer record format (GE_WIRE_*); rec_wire = its record size
+    size_t rec_wire;
+    uint32_t* d_err;              // import validation: [0] rejected records, [1] max(~index) (k_import)
+    uint32_t* h_err;              // pinned copy, read after the next synchronisation
+    cudaEvent_t fence;            // orders a caller-supplied stream against the batch's own (ge_step / ge_run_fused / ge_stats_refresh)
 };
 
-static int restore_order(ge_batch* b);
+static int restore_order(ge_batch* b, bool keep_records);
+// Synchronise the batch's stream, then report what the last import found (the verdict travels back asynchronously,
+// so the asynchronous host-buffer call can stay asynchronous): a batch that was fed malformed records says so at
+// its next synchronising call.  The offending records were replaced by initial records on the device.
+static int sync_and_check(ge_batch* b);
 static int lanes_per_session(const ge_table* t);
 extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixed_shift);
 static int ensure_stage(ge_batch* b, size_t bytes);
+extern "C" size_t ge_table_wire_size(const ge_table* t, int wire);
+
+static int sync_and_check(ge_batch* b) {
+    CU(cudaStreamSynchronize(b->stream));
+    const uint32_t bad = ((volatile uint32_t*)b->h_err)[0];
+    if (bad) {
+        const uint32_t first = ~((volatile uint32_t*)b->h_err)[1];
+        b->h_err[0] = 0; b->h_err[1] = 0;
+        return fail(GE_ERR_ARG, "import: " + std::to_string(bad) + " record(s) failed validation (first at index " + std::to_string(first) +
+                                "): phase / player ids outside the table, mask bits above the player count, or step 0 outside phase 0; "
+                                "they were replaced by initial records");
+    }
+    return GE_OK;
+}
 
 // ------------------------------------------------------------------------------------ table
 static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
@@ -100,6 +129,12 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     t->dev.h = h;
     memcpy(t->dev.phase, blob + sizeof h, (size_t)h.n_phases * sizeof(ge_phase_t));
     memcpy(t->dev.pred, blob + sizeof h + (size_t)h.n_phases * sizeof(ge_phase_t), (size_t)h.n_preds * sizeof(ge_pred_t));
+    // predicates may only name mask fields the family defines (SPEC.md section 2): werewolf 0-12 and 15, TTL 0-4 and 15
+    const uint16_t defined = h.family == FAM_WEREWOLF ? 0x9FFFu : 0x801Fu;
+    for (int i = 0; i < h.n_preds; ++i) {
+        const ge_pred_t& p = t->dev.pred[i];
+        if ((p.pos0 | p.neg0 | p.pos1 | p.neg1) & ~defined) return fail(GE_ERR_ARG, "predicate names an undefined mask field");
+    }
     for (int i = 0; i < h.n_phases; ++i) {
         const ge_phase_t& ph = t->dev.phase[i];
         if (ph.kind > KIND_TERMINAL || ph.n_branches > 4) return fail(GE_ERR_ARG, "bad phase record");
@@ -236,6 +271,12 @@ extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
 extern "C" void ge_table_destroy(ge_table* t) { delete t; }
 extern "C" size_t ge_table_record_size(const ge_table* t) { return t ? t->rec_canon : 0; }
 extern "C" int ge_table_n_players(const ge_table* t) { return t ? t->P : 0; }
+// dense wire records exist for werewolf tables up to 16 players (SPEC.md section 5b); everything else travels canonical
+static bool has_dense(const ge_table* t) { return t->family == FAM_WEREWOLF && t->bucket <= 16; }
+extern "C" size_t ge_table_wire_size(const ge_table* t, int wire) {
+    if (!t || (wire != GE_WIRE_CANONICAL && wire != GE_WIRE_DENSE)) return 0;
+    return (wire == GE_WIRE_DENSE && has_dense(t)) ? (t->bucket == 8 ? 32 : 48) : t->rec_canon;
+}
 
 // ------------------------------------------------------------------------------------ dispatch
 static step_fn pick_fn(const ge_table* t, int kernel) {
@@ -281,7 +322,7 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
     CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
     b->next_override = 1u;        // every session is in phase index 0
     b->epoch++;
-    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch);
+    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch, 0);
     CU(cudaGetLastError());
     b->compacted = false;
     b->since_compact = 0;
@@ -335,6 +376,10 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (e == cudaSuccess) e = cudaMalloc(&b->d_prefix, mask_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cstate, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc(&b->h_hint, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_err, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc(&b->h_err, 2 * sizeof(uint32_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) { b->h_err[0] = 0; b->h_err[1] = 0; }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->fence, cudaEventDisableTiming);
     if (e == cudaSuccess) { b->h_hint[0] = n_sessions; b->h_hint[1] = 0; }
     b->scan_blocks = (int)((b->n_tiles + CS_TILES - 1) / CS_TILES);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_blk, ((size_t)b->scan_blocks + 2) * sizeof(uint32_t));
@@ -349,6 +394,7 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (e != cudaSuccess) {
         cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_presence);
         cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
+        cudaFree(b->d_err); cudaFreeHost(b->h_err); if (b->fence) cudaEventDestroy(b->fence);
         delete b;
         return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_create: ") + cudaGetErrorString(e));
     }
@@ -366,6 +412,7 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
         b->grid[k] = g < 1 ? 1 : (int)g;
     }
     b->kernel = GE_KERNEL_TPS;
+    b->wire = GE_WIRE_CANONICAL; b->rec_wire = t->rec_canon;
     int rc = ge_batch_clear_stats(b);
     if (rc == GE_OK) rc = init_sessions(b, first_session_id, seed);
     // tables with a tie -> re-vote loop de-synchronise their sessions: regroup them by phase (k_regroup_*)
@@ -387,6 +434,7 @@ extern "C" void ge_batch_destroy(ge_batch* b) {
     cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_stage); cudaFree(b->d_presence);
     cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
     cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin);
+    cudaFree(b->d_err); cudaFreeHost(b->h_err); if (b->fence) cudaEventDestroy(b->fence);
     delete b;
 }
 
@@ -398,13 +446,21 @@ extern "C" int ge_batch_set_stream(ge_batch* b, void* cuda_stream) {
     return GE_OK;
 }
 
+extern "C" int ge_batch_set_wire(ge_batch* b, int wire) {
+    if (!b || (wire != GE_WIRE_CANONICAL && wire != GE_WIRE_DENSE)) return fail(GE_ERR_ARG, "bad wire format");
+    b->wire = wire;
+    b->rec_wire = ge_table_wire_size(b->tab, wire);
+    return GE_OK;
+}
+extern "C" size_t ge_batch_wire_size(const ge_batch* b) { return b ? b->rec_wire : 0; }
+
 extern "C" int ge_batch_set_kernel(ge_batch* b, int kernel) {
     if (!b || kernel < GE_KERNEL_AUTO || kernel > GE_KERNEL_TPS_GENERIC) return fail(GE_ERR_ARG, "bad kernel id");
     kernel = kernel == GE_KERNEL_AUTO ? GE_KERNEL_TPS : kernel;
     if (kernel == GE_KERNEL_COOP && b->kernel != GE_KERNEL_COOP) {
         // the lane-per-player kernels walk every slot in session order: undo any compaction first
         CU(cudaSetDevice(b->device));
-        const int rc = restore_order(b);
+        const int rc = restore_order(b, true);
         if (rc) return rc;
     }
     b->kernel = kernel;
@@ -471,7 +527,7 @@ extern "C" int ge_batch_epochs(ge_batch* b, uint64_t* out) {
     if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_batch_epochs");
     CU(cudaSetDevice(b->device));
     CU(cudaMemcpyAsync(out, b->d_cstate + 8, sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 
@@ -494,7 +550,7 @@ extern "C" int ge_batch_active(ge_batch* b, uint64_t* out) {
     if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_batch_active");
     CU(cudaSetDevice(b->device));
     CU(cudaMemcpyAsync(out, b->d_cstate, sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 extern "C" int ge_batch_get_kernel(const ge_batch* b) { return b ? b->kernel : GE_ERR_ARG; }
@@ -587,10 +643,30 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
     return GE_OK;
 }
 
+// A caller-supplied stream is ordered against the batch's own on both sides: it first waits for everything the batch
+// has enqueued (initialisation, imports, compaction bookkeeping), and the batch's stream then waits for the work
+// enqueued on it, so later exports / steps of the batch see the result.  No host synchronisation.
+static int fence_in(ge_batch* b, cudaStream_t other) {
+    if (other == b->stream) return GE_OK;
+    CU(cudaEventRecord(b->fence, b->stream));
+    CU(cudaStreamWaitEvent(other, b->fence, 0));
+    return GE_OK;
+}
+static int fence_out(ge_batch* b, cudaStream_t other) {
+    if (other == b->stream) return GE_OK;
+    CU(cudaEventRecord(b->fence, other));
+    CU(cudaStreamWaitEvent(b->stream, b->fence, 0));
+    return GE_OK;
+}
+
 extern "C" int ge_step(ge_batch* b, int n_steps, void* cuda_stream) {
     if (!b || n_steps < 0) return fail(GE_ERR_ARG, "bad arguments to ge_step");
     CU(cudaSetDevice(b->device));
-    return launch_steps(b, n_steps, 1, cuda_stream ? (cudaStream_t)cuda_stream : b->stream);
+    const cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+    int rc = fence_in(b, st);
+    if (rc == GE_OK) rc = launch_steps(b, n_steps, 1, st);
+    if (rc == GE_OK) rc = fence_out(b, st);
+    return rc;
 }
 
 extern "C" int ge_step_many(ge_batch** batches, int n_batches, int n_rounds) {
@@ -612,13 +688,17 @@ extern "C" int ge_run_fused(ge_batch* b, int n_steps, void* cuda_stream) {
     if (!b || n_steps < 0) return fail(GE_ERR_ARG, "bad arguments to ge_run_fused");
     if (n_steps == 0) return GE_OK;
     CU(cudaSetDevice(b->device));
-    return launch_steps(b, 1, n_steps, cuda_stream ? (cudaStream_t)cuda_stream : b->stream);
+    const cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+    int rc = fence_in(b, st);
+    if (rc == GE_OK) rc = launch_steps(b, 1, n_steps, st);
+    if (rc == GE_OK) rc = fence_out(b, st);
+    return rc;
 }
 
 extern "C" int ge_sync(ge_batch* b) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     CU(cudaSetDevice(b->device));
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 
@@ -631,11 +711,17 @@ static int ensure_stage(ge_batch* b, size_t bytes) {
     return GE_OK;
 }
 
-static int export_async(ge_batch* b, uint64_t first, uint64_t count, void* host_buf) {
-    const size_t S = b->tab->rec_canon;
+static int export_async(ge_batch* b, uint64_t first, uint64_t count, void* host_buf, int wire) {
+    const bool dense = wire == GE_WIRE_DENSE && has_dense(b->tab);
+    const size_t S = dense ? ge_table_wire_size(b->tab, GE_WIRE_DENSE) : b->tab->rec_canon;
     int rc = ensure_stage(b, count * S);
     if (rc) return rc;
-    if (b->compacted)
+    if (dense) {
+        const uint32_t* org = b->compacted ? b->d_origin : nullptr;
+        const int g = glue_grid(b, org ? b->n : count, 256);
+        if (b->tab->bucket == 8) k_export_dense<8><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        else k_export_dense<16><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+    } else if (b->compacted)
         k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, b->d_origin, b->n, first, count, b->d_stage);
     else
         k_export<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage);
@@ -646,19 +732,23 @@ static int export_async(ge_batch* b, uint64_t first, uint64_t count, void* host_
 }
 
 // Undo the slot permutation of compaction: records go back to slot == session index, every slot active.
-static int restore_order(ge_batch* b) {
-    if (b->compacted) {
+// keep_records = false: the caller is about to overwrite every record, only the bookkeeping is reset.
+// The device epoch of auto-reset (cstate[8]) survives: the resident sessions' ids depend on it.
+static int restore_order(ge_batch* b, bool keep_records) {
+    if (b->compacted && keep_records) {
         const size_t S = b->tab->rec_canon;
         int rc = ensure_stage(b, b->n * S);
         if (rc) return rc;
+        InitRec rec;
+        memcpy(rec.w, b->tab->init_words, sizeof rec.w);
         k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, b->d_origin, b->n, 0, b->n, b->d_stage);
-        k_import<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, 0, b->n, b->d_stage);
+        k_import<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, 0, b->n, b->d_stage, nullptr);
         CU(cudaGetLastError());
         b->launches += 2;
-        b->compacted = false;
     }
+    b->compacted = false;
     b->epoch++;
-    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch);
+    k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch, 1);
     CU(cudaGetLastError());
     b->since_compact = 0;
     CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
@@ -666,16 +756,25 @@ static int restore_order(ge_batch* b) {
     return GE_OK;
 }
 
-static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void* host_buf) {
-    const size_t S = b->tab->rec_canon;
-    int rc = restore_order(b);         // imported sessions may be live anywhere
+// Every import path comes through here: the records are range-checked ON THE DEVICE by k_import (record_invalid,
+// ge_glue.cuh) and the verdict is copied to pinned host memory behind it; sync_and_check reports it.
+static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void* host_buf, int wire) {
+    const bool dense = wire == GE_WIRE_DENSE && has_dense(b->tab);
+    const size_t S = dense ? ge_table_wire_size(b->tab, GE_WIRE_DENSE) : b->tab->rec_canon;
+    int rc = restore_order(b, !(first == 0 && count == b->n));         // imported sessions may be live anywhere
     if (rc) return rc;
     rc = ensure_stage(b, count * S);
     if (rc) return rc;
+    InitRec rec;
+    memcpy(rec.w, b->tab->init_words, sizeof rec.w);
     CU(cudaMemcpyAsync(b->d_stage, host_buf, count * S, cudaMemcpyHostToDevice, b->stream));
-    k_import<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage);
+    CU(cudaMemsetAsync(b->d_err, 0, 2 * sizeof(uint32_t), b->stream));
+    if (dense && b->tab->bucket == 8) k_import_dense<8><<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err);
+    else if (dense) k_import_dense<16><<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err);
+    else k_import<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage, b->d_err);
     CU(cudaGetLastError());
     b->launches++;
+    CU(cudaMemcpyAsync(b->h_err, b->d_err, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
     CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
     b->next_override = 0xFFFFFFFFu;   // imported sessions can be in any phase
     return GE_OK;
@@ -685,25 +784,19 @@ extern "C" int ge_export_state(ge_batch* b, uint64_t first, uint64_t count, void
     if (!b || !host_buf || first + count > b->n) return fail(GE_ERR_ARG, "bad arguments to ge_export_state");
     if (count == 0) return GE_OK;
     CU(cudaSetDevice(b->device));
-    int rc = export_async(b, first, count, host_buf);
+    int rc = export_async(b, first, count, host_buf, b->wire);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 
 extern "C" int ge_import_state(ge_batch* b, uint64_t first, uint64_t count, const void* host_buf) {
     if (!b || !host_buf || first + count > b->n) return fail(GE_ERR_ARG, "bad arguments to ge_import_state");
     if (count == 0) return GE_OK;
-    // reject records whose phase index is outside the table: the kernels index the table with it
-    const size_t S = b->tab->rec_canon;
-    const uint8_t* p = static_cast<const uint8_t*>(host_buf);
-    for (uint64_t i = 0; i < count; ++i)
-        if (p[i * S] >= b->tab->dev.h.n_phases || p[i * S + 1] >= b->tab->dev.h.n_phases)
-            return fail(GE_ERR_ARG, "record has a phase index outside the table");
     CU(cudaSetDevice(b->device));
-    int rc = import_async(b, first, count, host_buf);
+    int rc = import_async(b, first, count, host_buf, b->wire);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 
@@ -714,13 +807,13 @@ extern "C" int ge_trace(ge_batch* b, uint64_t first, uint64_t count, int n_steps
     CU(cudaSetDevice(b->device));
     const size_t frame = count * b->tab->rec_canon;
     uint8_t* out = static_cast<uint8_t*>(host_records);
-    int rc = export_async(b, first, count, out);
+    int rc = export_async(b, first, count, out, GE_WIRE_CANONICAL);
     for (int k = 1; rc == GE_OK && k <= n_steps; ++k) {
         rc = launch_steps(b, 1, 1, b->stream);
-        if (rc == GE_OK) rc = export_async(b, first, count, out + (size_t)k * frame);
+        if (rc == GE_OK) rc = export_async(b, first, count, out + (size_t)k * frame, GE_WIRE_CANONICAL);
     }
     if (rc != GE_OK) return rc;
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 
@@ -741,7 +834,7 @@ extern "C" int ge_eval_preds(ge_batch* b, const ge_pred_t* preds, int n_preds, u
     CU(cudaGetLastError());
     b->launches++;
     CU(cudaMemcpyAsync(host_masks, b->d_stage, bytes, cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 
@@ -749,12 +842,14 @@ extern "C" int ge_stats_refresh(ge_batch* b, void* cuda_stream) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     CU(cudaSetDevice(b->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+    int rc = fence_in(b, st);
+    if (rc != GE_OK) return rc;
     // snapshot = accumulator + histograms of the sessions currently resident
     CU(cudaMemcpyAsync(b->d_stats_out, b->d_stats, GE_STATS_LEN * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     k_stats<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->tab->dev, b->d_tiles, (uint32_t)b->tab->rec_dev, b->n, b->d_stats_out);
     CU(cudaGetLastError());
     b->launches++;
-    return GE_OK;
+    return fence_out(b, st);
 }
 
 extern "C" int ge_stats(ge_batch* b, uint64_t* host_hist, size_t n) {
@@ -762,7 +857,7 @@ extern "C" int ge_stats(ge_batch* b, uint64_t* host_hist, size_t n) {
     int rc = ge_stats_refresh(b, nullptr);
     if (rc) return rc;
     CU(cudaMemcpyAsync(host_hist, b->d_stats_out, GE_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 
@@ -772,15 +867,7 @@ extern "C" int ge_counted_steps(ge_batch* b, uint64_t* out) {
     if (!b || !out) return fail(GE_ERR_ARG, "bad arguments to ge_counted_steps");
     CU(cudaSetDevice(b->device));
     CU(cudaMemcpyAsync(out, b->d_stats, sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
-    return GE_OK;
-}
-
-extern "C" int ge_stream_delay(int device, void* cuda_stream, unsigned microseconds) {
-    if (microseconds > 1000000u) return fail(GE_ERR_ARG, "ge_stream_delay: at most one second");
-    CU(cudaSetDevice(device));
-    k_delay<<<1, 1, 0, (cudaStream_t)cuda_stream>>>((unsigned long long)microseconds * 1000ull);
-    CU(cudaGetLastError());
+    SYNC(b);
     return GE_OK;
 }
 
@@ -797,11 +884,11 @@ extern "C" int ge_run_host_async(ge_batch* b, const void* records_in, void* reco
     if (!b || n_steps < 0) return fail(GE_ERR_ARG, "bad arguments to ge_run_host_async");
     CU(cudaSetDevice(b->device));
     int rc;
-    if (records_in && (rc = import_async(b, 0, b->n, records_in)) != GE_OK) return rc;
+    if (records_in && (rc = import_async(b, 0, b->n, records_in, b->wire)) != GE_OK) return rc;
     if (b->host_fused && n_steps > 1) rc = launch_steps(b, 1, n_steps, b->stream);
     else rc = launch_steps(b, n_steps, 1, b->stream);
     if (rc != GE_OK) return rc;
-    if (records_out && (rc = export_async(b, 0, b->n, records_out)) != GE_OK) return rc;
+    if (records_out && (rc = export_async(b, 0, b->n, records_out, b->wire)) != GE_OK) return rc;
     if (host_stats) {
         if ((rc = ge_stats_refresh(b, nullptr)) != GE_OK) return rc;
         CU(cudaMemcpyAsync(host_stats, b->d_stats_out, GE_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, b->stream));
@@ -812,7 +899,7 @@ extern "C" int ge_run_host_async(ge_batch* b, const void* records_in, void* reco
 extern "C" int ge_run_host(ge_batch* b, const void* records_in, void* records_out, int n_steps, uint64_t* host_stats) {
     const int rc = ge_run_host_async(b, records_in, records_out, n_steps, host_stats);
     if (rc != GE_OK) return rc;
-    CU(cudaStreamSynchronize(b->stream));
+    SYNC(b);
     return GE_OK;
 }
 

@@ -39,10 +39,11 @@ struct DevTable {
 static_assert(sizeof(ge_phase_t) == 48 && sizeof(ge_pred_t) == 8 && sizeof(ge_table_header_t) == 32, "table ABI");
 static_assert(sizeof(DevTable) <= 4000, "table must fit the kernel parameter space");
 
-// Per-launch arguments of every step kernel.
-struct StepArgs {
+// Per-launch arguments of every step kernel: the part that belongs to ONE batch (SlotArgs) and the part a ring of
+// batches stepped by one launch shares (StepArgs adds it: seed, steps per launch, Philox round keys).
+struct SlotArgs {
     uint8_t* tiles;
-    uint64_t n_sessions, n_tiles, first_sid, seed;
+    uint64_t n_sessions, n_tiles, first_sid;
     unsigned long long* stats;
     // Phase-presence masks (3 rotating words): launch k READS word k%3 (bit i = some session was in
     // phase index i after launch k-1), ORs the phases its sessions end in into word (k+1)%3 and clears
@@ -50,7 +51,6 @@ struct StepArgs {
     // reset or an import, when the device words are not valid).
     uint32_t* presence;
     uint32_t launch_idx, presence_override;
-    int n_steps;
     // Active-prefix compaction (ge_capi.cu): only slots [0, *n_active) can hold live sessions; `origin`
     // maps a slot to the session's original index (NULL = identity; session id = first_sid + origin);
     // the step kernel publishes which lanes of each tile are still live after the step in live_mask.
@@ -63,19 +63,30 @@ struct StepArgs {
     // thread-per-session kernel also adds, per phase index, the sessions that entered it to rg[0..31] and the
     // number of tiles whose live sessions sit in more than one phase to rg[32].  NULL = not collected.
     uint32_t* rg;
-    // Philox round keys (k0 + r*W0, k1 + r*W1 for r = 0..9), expanded once on the host: as kernel parameters they
-    // are constant-bank operands of the round's XOR, so the key schedule costs no instructions.
-    uint32_t rk[20];
     // Auto-reset (ge_capi.cu, k_autoreset_*): n_active[8] counts the device-side re-initialisations; the session
     // in slot i then has id first_sid + n_active[8] * sid_stride + origin[i].  0 = off.
     uint64_t sid_stride;
 };
+struct StepArgs : SlotArgs {
+    uint64_t seed;
+    int n_steps;
+    // Philox round keys (k0 + r*W0, k1 + r*W1 for r = 0..9), expanded once on the host: as kernel parameters they
+    // are constant-bank operands of the round's XOR, so the key schedule costs no instructions.
+    uint32_t rk[20];
+};
+// A ring of independent batches of the SAME table and seed, stepped once each by ONE launch (k_ring_*): the launch
+// walks the slots in order; nothing orders one slot against another (their sessions are independent).
+constexpr int GE_RING_MAX = 16;
+struct RingArgs {
+    int n;
+    SlotArgs slot[GE_RING_MAX];
+};
 
-__device__ __forceinline__ uint64_t first_sid_of(const StepArgs& A) {
+__device__ __forceinline__ uint64_t first_sid_of(const SlotArgs& A) {
     return A.sid_stride ? A.first_sid + A.n_active[8] * A.sid_stride : A.first_sid;
 }
 
-__device__ __forceinline__ void publish_presence(const StepArgs& A, uint32_t block_present) {
+__device__ __forceinline__ void publish_presence(const SlotArgs& A, uint32_t block_present) {
     // called by all threads after a __syncthreads() that orders the block's shared accumulation
     if (threadIdx.x == 0) {
         if (block_present) atomicOr(&A.presence[(A.launch_idx + 1) % 3], block_present);

@@ -41,18 +41,187 @@ __global__ void k_export(const uint8_t* tiles, uint32_t S_dev, uint32_t S_canon,
     }
 }
 
-__global__ void k_import(uint8_t* tiles, uint32_t S_dev, uint32_t S_canon, uint64_t first, uint64_t count, const uint8_t* in) {
+// Record validation (SPEC.md section 7b), shared by every import path: the step kernels index the table with the
+// phase bytes and shift by player ids, so a record must be range-checked before it reaches them.  0 = well-formed.
+__device__ __forceinline__ int record_invalid(const DevTable& T, const uint8_t* r, uint32_t S_canon) {
+    const int P = T.h.n_players;
+    const uint32_t hi = P >= 32 ? 0u : ~((1u << P) - 1u);
+    const uint32_t step = r[2] | ((uint32_t)r[3] << 8);
+    if (r[0] >= T.h.n_phases || r[1] >= T.h.n_phases) return 1;
+    if (step == 0 && (r[0] != 0 || r[1] != 0)) return 2;
+    if (T.h.family == FAM_WEREWOLF) {
+        if (r[4] > 2 || r[5] > P || r[6] > P) return 3;
+        if ((r[7] & 0x7Fu) > T.h.max_revotes || (T.h.max_revotes == 0 && r[7] != 0)) return 4;
+        for (int f = 0; f < 10; ++f) {
+            const uint32_t m = r[8 + 4 * f] | ((uint32_t)r[9 + 4 * f] << 8) | ((uint32_t)r[10 + 4 * f] << 16) | ((uint32_t)r[11 + 4 * f] << 24);
+            if (m & hi) return 5;
+        }
+        for (uint32_t p = 0; 48 + p < S_canon; ++p)
+            if (r[48 + p] > ((int)p < P ? P : 0)) return 6;
+    } else {
+        if (r[4] > P || r[6] > P || r[7] != 0) return 3;
+        for (uint32_t p = 0; 8 + 4 * p < S_canon; ++p) {
+            if ((int)p < P) { if (r[11 + 4 * p] & 0xE0u) return 5; }
+            else if (r[8 + 4 * p] | r[9 + 4 * p] | r[10 + 4 * p] | r[11 + 4 * p]) return 6;
+        }
+    }
+    return 0;
+}
+
+// canonical AoS records -> tiles.  A record that fails validation is replaced by the table's initial record (always
+// safe to step) and reported: err[0] counts such records, err[1] = max(~index) (so ~err[1] is the first one).
+__global__ void k_import(const __grid_constant__ DevTable T, const __grid_constant__ InitRec init, uint8_t* tiles, uint32_t S_dev, uint32_t S_canon,
+                         uint64_t first, uint64_t count, const uint8_t* in, uint32_t* err) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n16 = S_dev / 16;
     for (uint64_t j = t; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = first + j;
         uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
         const uint32_t sl = (uint32_t)(i & 31);
+        const uint8_t* r = in + j * S_canon;
+        const bool bad = err != nullptr && record_invalid(T, r, S_canon) != 0;
+        if (bad) { atomicAdd(&err[0], 1u); atomicMax(&err[1], ~(uint32_t)(j > 0xFFFFFFFEull ? 0xFFFFFFFEull : j)); }
         for (uint32_t k = 0; k < S_dev / 8; ++k) {
             uint2 v = make_uint2(0, 0);
-            if (k < S_canon / 8) v = *reinterpret_cast<const uint2*>(in + j * S_canon + 8 * k);
+            if (bad) v = make_uint2(init.w[2 * k], init.w[2 * k + 1]);
+            else if (k < S_canon / 8) v = *reinterpret_cast<const uint2*>(r + 8 * k);
             *reinterpret_cast<uint2*>(base + rt_tile_off(8 * k, sl, n16)) = v;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------ dense wire format
+// Werewolf tables with P <= 16 players: the ten lane masks of the canonical record carry P8 bits each but occupy
+// 32, so at the host boundary (PCIe) a record can travel in 32 bytes (P8 = 8) or 48 bytes (P8 = 16) instead of
+// 56 / 64 (SPEC.md section 5b).  Words (little-endian u32):
+//   P8 = 8 : 0-1 header (as canonical) | 2 alive,can_vote,eligible,submitted (u8 each) | 3 revealed,investigated,wolf,secret
+//            | 4 role_lo,role_hi,0,0 | 5-6 selected_target_id[0..7] | 7 zero
+//   P8 = 16: 0-1 header | 2 alive,can_vote (u16 each) | 3 eligible,submitted | 4 revealed,investigated | 5 wolf,secret
+//            | 6 role_lo,role_hi | 7 zero | 8-11 selected_target_id[0..15]
+// The conversion happens in the import / export kernels; the session store in HBM keeps the canonical columns.
+template <int P8> struct DenseW { static constexpr int WORDS = P8 == 8 ? 8 : 12; static constexpr int CW = 12 + P8 / 4; };
+
+template <int P8>
+__device__ __forceinline__ void dense_pack(const uint32_t (&w)[12 + P8 / 4], uint32_t (&d)[DenseW<P8>::WORDS]) {
+    d[0] = w[0]; d[1] = w[1];
+    if (P8 == 8) {
+        d[2] = (w[2] & 0xFFu) | ((w[3] & 0xFFu) << 8) | ((w[4] & 0xFFu) << 16) | ((w[5] & 0xFFu) << 24);
+        d[3] = (w[6] & 0xFFu) | ((w[7] & 0xFFu) << 8) | ((w[8] & 0xFFu) << 16) | ((w[9] & 0xFFu) << 24);
+        d[4] = (w[10] & 0xFFu) | ((w[11] & 0xFFu) << 8);
+        d[5] = w[12]; d[6] = w[13]; d[7] = 0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) d[2 + k] = (w[2 + 2 * k] & 0xFFFFu) | ((w[3 + 2 * k] & 0xFFFFu) << 16);
+        d[7] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[8 + k] = w[12 + k];
+    }
+}
+// returns non-zero when the padding of the dense record is not zero (then the record is malformed)
+template <int P8>
+__device__ __forceinline__ uint32_t dense_unpack(const uint32_t (&d)[DenseW<P8>::WORDS], uint32_t (&w)[12 + P8 / 4]) {
+    w[0] = d[0]; w[1] = d[1];
+    if (P8 == 8) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { w[2 + k] = (d[2] >> (8 * k)) & 0xFFu; w[6 + k] = (d[3] >> (8 * k)) & 0xFFu; }
+        w[10] = d[4] & 0xFFu; w[11] = (d[4] >> 8) & 0xFFu;
+        w[12] = d[5]; w[13] = d[6];
+        return (d[4] >> 16) | d[7];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { w[2 + 2 * k] = d[2 + k] & 0xFFFFu; w[3 + 2 * k] = d[2 + k] >> 16; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[12 + k] = d[8 + k];
+        return d[7];
+    }
+}
+
+// record_invalid on the canonical WORDS of a werewolf record (same rules; the two are held to each other by the tests)
+template <int P8>
+__device__ __forceinline__ int words_invalid_w(const DevTable& T, const uint32_t (&w)[12 + P8 / 4]) {
+    const int P = T.h.n_players;
+    const uint32_t hi = P >= 32 ? 0u : ~((1u << P) - 1u);
+    const uint32_t ph = w[0] & 0xFFu, pv = (w[0] >> 8) & 0xFFu, step = w[0] >> 16;
+    if (ph >= T.h.n_phases || pv >= T.h.n_phases) return 1;
+    if (step == 0 && (ph != 0 || pv != 0)) return 2;
+    if ((w[1] & 0xFFu) > 2u || ((w[1] >> 8) & 0xFFu) > (uint32_t)P || ((w[1] >> 16) & 0xFFu) > (uint32_t)P) return 3;
+    const uint32_t rv = w[1] >> 24;
+    if ((rv & 0x7Fu) > T.h.max_revotes || (T.h.max_revotes == 0 && rv != 0)) return 4;
+    uint32_t any = 0;
+#pragma unroll
+    for (int f = 0; f < 10; ++f) any |= w[2 + f];
+    if (any & hi) return 5;
+#pragma unroll
+    for (int p = 0; p < P8; ++p)
+        if (((w[12 + (p >> 2)] >> (8 * (p & 3))) & 0xFFu) > (uint32_t)(p < P ? P : 0)) return 6;
+    return 0;
+}
+
+// canonical words of one slot of the tiled store (werewolf) and back
+template <int P8>
+__device__ __forceinline__ void tile_load_words(const uint8_t* tiles, uint64_t slot, uint32_t (&w)[12 + P8 / 4]) {
+    constexpr int S = 48 + P8;
+    const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S);
+    const uint32_t sl = (uint32_t)(slot & 31);
+#pragma unroll
+    for (int c = 0; c < S / 16; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(base + c * 512 + sl * 16);
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+    if (S % 16) {
+        const uint2 v = *reinterpret_cast<const uint2*>(base + (S / 16) * 512 + sl * 8);
+        w[4 * (S / 16)] = v.x; w[4 * (S / 16) + 1] = v.y;
+    }
+}
+template <int P8>
+__device__ __forceinline__ void tile_store_words(uint8_t* tiles, uint64_t slot, const uint32_t (&w)[12 + P8 / 4]) {
+    constexpr int S = 48 + P8;
+    uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S);
+    const uint32_t sl = (uint32_t)(slot & 31);
+#pragma unroll
+    for (int c = 0; c < S / 16; ++c)
+        *reinterpret_cast<uint4*>(base + c * 512 + sl * 16) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    if (S % 16)
+        *reinterpret_cast<uint2*>(base + (S / 16) * 512 + sl * 8) = make_uint2(w[4 * (S / 16)], w[4 * (S / 16) + 1]);
+}
+
+// dense AoS records -> tiles (validated like k_import).  One thread per session, 128-bit accesses on both sides.
+template <int P8>
+__global__ void __launch_bounds__(256)
+k_import_dense(const __grid_constant__ DevTable T, const __grid_constant__ InitRec init, uint8_t* tiles, uint64_t first, uint64_t count,
+               const uint8_t* in, uint32_t* err) {
+    constexpr int DW = DenseW<P8>::WORDS;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t d[DW], w[12 + P8 / 4];
+        const uint4* src = reinterpret_cast<const uint4*>(in + j * (4 * DW));
+#pragma unroll
+        for (int k = 0; k < DW / 4; ++k) { const uint4 v = src[k]; d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w; }
+        const uint32_t pad = dense_unpack<P8>(d, w);
+        if (pad != 0 || words_invalid_w<P8>(T, w) != 0) {
+            atomicAdd(&err[0], 1u);
+            atomicMax(&err[1], ~(uint32_t)(j > 0xFFFFFFFEull ? 0xFFFFFFFEull : j));
+#pragma unroll
+            for (int k = 0; k < 12 + P8 / 4; ++k) w[k] = init.w[k];
+        }
+        tile_store_words<P8>(tiles, first + j, w);
+    }
+}
+
+// tiles -> dense AoS records; origin != NULL: slots are permuted (compaction), records leave in original order
+template <int P8>
+__global__ void __launch_bounds__(256)
+k_export_dense(const uint8_t* tiles, const uint32_t* __restrict__ origin, uint64_t n, uint64_t first, uint64_t count, uint8_t* out) {
+    constexpr int DW = DenseW<P8>::WORDS;
+    const uint64_t lo = origin ? 0 : first, hi = origin ? n : first + count;
+    for (uint64_t slot = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < hi; slot += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = origin ? origin[slot] : slot;
+        if (o < first || o >= first + count) continue;
+        uint32_t d[DW], w[12 + P8 / 4];
+        tile_load_words<P8>(tiles, slot, w);
+        dense_pack<P8>(w, d);
+        uint4* dst = reinterpret_cast<uint4*>(out + (o - first) * (4 * DW));
+#pragma unroll
+        for (int k = 0; k < DW / 4; ++k) dst[k] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
     }
 }
 
@@ -148,9 +317,11 @@ __global__ void k_iota(uint32_t* origin, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) origin[i] = (uint32_t)i;
 }
 
-__global__ void k_cstate_reset(unsigned long long* cstate, unsigned long long n, unsigned long long epoch) {
+__global__ void k_cstate_reset(unsigned long long* cstate, unsigned long long n, unsigned long long epoch, int keep_device_epoch) {
     // [7] = host epoch tag, [8] = number of device-side re-initialisations (auto-reset) since the last host one
-    if (threadIdx.x < 16) cstate[threadIdx.x] = threadIdx.x == 0 ? n : threadIdx.x == 7 ? epoch : 0ull;
+    // (kept when only the slot order is restored: the resident sessions' ids depend on it)
+    if (threadIdx.x < 16 && !(keep_device_epoch && threadIdx.x == 8))
+        cstate[threadIdx.x] = threadIdx.x == 0 ? n : threadIdx.x == 7 ? epoch : 0ull;
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t* total) {
@@ -432,13 +603,4 @@ __global__ void k_eval_preds(const __grid_constant__ DevTable T, const __grid_co
             out[(o - first) * PL.n + j] = res;
         }
     }
-}
-
-// Measurement helper: occupies `cuda_stream` for about `microseconds` (one thread spinning on %globaltimer).  A
-// benchmark enqueues it in front of its first timing event so that the host can queue the timed launches while
-// the device is still busy — the timed region then measures the device, not the host's launch rate from a cold queue.
-__global__ void k_delay(unsigned long long ns) {
-    unsigned long long t0, t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
 }

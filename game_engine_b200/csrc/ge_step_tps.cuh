@@ -552,17 +552,29 @@ __device__ __forceinline__ uint32_t need_of(const DevTable& T, uint32_t present)
     return need;
 }
 
+// Shared-memory working set of one CTA of the werewolf thread-per-session kernels.
+template <int P8>
+struct WSmem {
+    uint32_t visits[32];
+    uint32_t present, live, mixed;
+    uint32_t fields[16][TPS_THREADS];
+    uint8_t lut[P8 > 16 ? P8 : 1][TPS_THREADS];
+};
+
+// One pass of this CTA's share of ONE batch: every non-terminal session of the batch's active prefix advances by
+// A.n_steps... C carries what a ring of batches shares (steps per launch, Philox round keys), A the batch.
 // Spec = void: interpret the run-time table T.  Spec = a generated ge::spec struct: the same table known at
 // build time (the host only selects this instantiation when the blobs are byte-identical).
-template <int P8, class Spec = void>
-__global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
-k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
+// Called by all threads of the block; contains block-wide barriers.
+template <int P8, class Spec>
+__device__ __forceinline__ void w_tps_pass(const DevTable& T, const StepArgs& C, const SlotArgs& A, WSmem<P8>& sm) {
     constexpr int S = 48 + P8;
     constexpr int NT16 = P8 / 16;          // full 16-byte target columns
     constexpr bool THALF = (P8 % 16) != 0; // trailing 8-byte column
-    __shared__ uint32_t s_visits[32];
-    __shared__ uint32_t s_present, s_live, s_mixed;
-    __shared__ uint32_t s_fields[16][TPS_THREADS];
+    uint32_t (&s_visits)[32] = sm.visits;
+    uint32_t& s_present = sm.present;
+    uint32_t& s_live = sm.live;
+    uint32_t& s_mixed = sm.mixed;
     if (threadIdx.x < 32) s_visits[threadIdx.x] = 0;
     if (threadIdx.x == 0) { s_present = 0; s_live = 0; s_mixed = 0; }
     __syncthreads();
@@ -571,13 +583,12 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     // which column groups can any session of this batch need?  (bit0 C1, bit1 C2, bit2 player bytes, bit3 session id)
     const uint32_t present_in = A.presence_override ? A.presence_override : A.presence[A.launch_idx % 3];
-    const uint32_t need = A.n_steps > 1 ? 15u : need_of(T, present_in);
+    const uint32_t need = C.n_steps > 1 ? 15u : need_of(T, present_in);
     const uint64_t n_act = *A.n_active;                 // slots beyond it hold only terminal sessions
     const uint64_t sid0 = first_sid_of(A);
     const uint32_t n_tiles_act = (uint32_t)((n_act + 31) >> 5);
     const bool use_origin = A.origin != nullptr && (need & 8);
-    __shared__ uint8_t s_lut[P8 > 16 ? P8 : 1][TPS_THREADS];
-    const FieldTable F{s_fields, (int)threadIdx.x, &s_lut[0][P8 > 16 ? threadIdx.x : 0]};
+    const FieldTable F{sm.fields, (int)threadIdx.x, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]};
     uint32_t present_out = 0, live_cnt = 0, mixed = 0;
     VisitAcc visits;
 
@@ -683,13 +694,13 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
             bool live = in_range;
             const uint64_t sid = sid0 + org;
             uint32_t dirty = 0;
-            for (int it = 0; it < A.n_steps; ++it) {
+            for (int it = 0; it < C.n_steps; ++it) {
                 int np = -1;
                 if (live) {
                     if constexpr (std::is_void<Spec>::value)
-                        np = w_step<P8>(T, s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
+                        np = w_step<P8>(T, s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty);
                     else
-                        np = w_step_spec<P8, Spec>(s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), A, dirty);
+                        np = w_step_spec<P8, Spec>(s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty);
                     if (np < 0) live = false;
                 }
                 mixed += visits.add(s_visits, np, lane) > 1;
@@ -723,6 +734,27 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     if (A.count_live && A.rg != nullptr) {             // inputs of the phase regrouping check (k_regroup_plan)
         if (threadIdx.x < 32 && s_visits[threadIdx.x]) atomicAdd(&A.rg[threadIdx.x], s_visits[threadIdx.x]);
         if (threadIdx.x == 0 && s_mixed) atomicAdd(&A.rg[32], s_mixed);
+    }
+}
+
+template <int P8, class Spec = void>
+__global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
+k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
+    __shared__ WSmem<P8> sm;
+    w_tps_pass<P8, Spec>(T, A, A, sm);
+}
+
+// The ring launch: one step of EVERY batch of a ring (same table, same seed) in one launch.  A batch of 2^20 8-player
+// sessions is ~10 us of work, so launched alone a step kernel spends its life in ramp-up and tail (0.43 of the
+// roofline on one stream); the ring used to hide that by running 8 small launches side by side on 8 streams.  Here
+// each CTA simply walks the slots in order: one ramp and one tail per RING pass, full-occupancy grid, one stream.
+template <int P8, class Spec = void>
+__global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
+k_ring_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs C, const __grid_constant__ RingArgs R) {
+    __shared__ WSmem<P8> sm;
+    for (int i = 0; i < R.n; ++i) {
+        w_tps_pass<P8, Spec>(T, C, R.slot[i], sm);
+        __syncthreads();                               // the epilogue's readers are done before the counters are cleared
     }
 }
 

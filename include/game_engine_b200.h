@@ -31,6 +31,10 @@ extern "C" {
 #define GE_ERR_UNSUPPORTED (-3)   /* table uses a family / player count the kernels do not cover */
 #define GE_ERR_NOMEM (-4)
 
+/* record formats at the host boundary (ge_batch_set_wire) */
+#define GE_WIRE_CANONICAL 0       /* SPEC.md section 5: S = 48 + P8 (werewolf), roundup8(8 + 4P) (TTL) */
+#define GE_WIRE_DENSE 1           /* SPEC.md section 5b: werewolf tables up to 16 players, masks as u8 / u16: 32 / 48 bytes */
+
 /* kernel mappings (ge_batch_set_kernel) */
 #define GE_KERNEL_AUTO 0
 #define GE_KERNEL_COOP 1          /* one lane per player, warp ballots / match_any (32/P sessions per warp) */
@@ -126,9 +130,19 @@ int ge_batch_epochs(ge_batch *b, uint64_t *out);
 int ge_batch_active_hint(ge_batch *b, uint64_t *out);
 int ge_batch_get_kernel(const ge_batch *b);
 
+/* Record format of the host-buffer calls of this batch (ge_export_state, ge_import_state, ge_run_host[_async]):
+ * canonical (default) or dense.  The dense format carries the same fields in 32 bytes (<= 8 players) or 48 bytes
+ * (<= 16 players) instead of 56 / 64 — the conversion runs inside the import / export kernels, so 1.75x / 1.33x fewer
+ * bytes cross PCIe per session.  Tables it does not cover (more than 16 players, TTL) keep the canonical record:
+ * ge_table_wire_size / ge_batch_wire_size give the size in force.  ge_trace always writes canonical records. */
+size_t ge_table_wire_size(const ge_table *t, int wire);
+int ge_batch_set_wire(ge_batch *b, int wire);
+size_t ge_batch_wire_size(const ge_batch *b);
+
 /* Apply n_steps session-phase-steps to every non-terminal session: n_steps launches of the step
  * kernel on `cuda_stream` (NULL = the batch's own stream), each reading and writing the state once.
- * Asynchronous.  Replaces one graph run BotBehaviorNode -> PhaseNode -> RefereeNode per step
+ * Asynchronous.  A caller-supplied stream is fenced against the batch's own stream with events on both sides (it
+ * waits for the batch's pending work; the batch's later work waits for it).  Replaces one graph run BotBehaviorNode -> PhaseNode -> RefereeNode per step
  * (reference agent/game_agent_v2.py:468-617, 987-1241, 619-803) including the tool applications
  * _execute_update_player_actions / _execute_update_player_state (agent/tools/backend_tools.py:285-344,
  * 204-225). */
@@ -146,6 +160,12 @@ int ge_sync(ge_batch *b);
  * (reference agent/game_agent_v2.py:97-117).  Synchronous. */
 int ge_export_state(ge_batch *b, uint64_t first, uint64_t count, void *host_buf);
 int ge_import_state(ge_batch *b, uint64_t first, uint64_t count, const void *host_buf);
+/* Every import path (ge_import_state, ge_run_host, ge_run_host_async) range-checks its records ON THE DEVICE
+ * (SPEC.md section 7b: phase / prev inside the table, step 0 only in phase 0, winner / player ids <= P, re-vote
+ * counter <= max_revotes, no mask or flag bits above the player count, padding zero).  A record that fails is
+ * replaced by the table's initial record (always safe to step) and the call — or, for the asynchronous call, the
+ * next synchronising call on the batch (ge_sync, ge_export_state, ge_stats, ...) — returns GE_ERR_ARG naming the
+ * first offending index. */
 
 /* Step log for replay: applies n_steps single-step launches to the whole batch and writes the canonical records
  * of sessions [first, first+count) after each of them: host_records holds (n_steps + 1) frames of count * S
@@ -190,10 +210,6 @@ void *ge_state_device_ptr(ge_batch *b);
 size_t ge_state_device_bytes(const ge_batch *b);
 /* number of kernel launches (step + glue kernels) issued by this batch since creation */
 uint64_t ge_launch_count(const ge_batch *b);
-
-/* Measurement helper: keeps `cuda_stream` of `device` busy for about `microseconds` (<= 1 s) with a one-thread spin
- * kernel, so that a benchmark can queue its timed launches behind it (see bench.py). */
-int ge_stream_delay(int device, void *cuda_stream, unsigned microseconds);
 
 const char *ge_last_error(void);
 const char *ge_version(void);

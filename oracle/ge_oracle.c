@@ -87,6 +87,12 @@ static int tab_open(tab_t *t, const uint8_t *blob, size_t n) {
             if (wolfy ? (br[0] == BR_ALL_VAL_GE || br[2] > 2) : br[0] == BR_TIE_PENDING) return -1;
         }
     }
+    /* predicates may only name mask fields the family defines (SPEC.md section 2) */
+    for (int i = 0; i < t->n_preds; ++i) {
+        const uint8_t *pr = blob + 32 + 48 * t->n_phases + 8 * i;
+        const unsigned used = rd16(pr) | rd16(pr + 2) | rd16(pr + 4) | rd16(pr + 6);
+        if (used & ~(t->family == FAM_WEREWOLF ? 0x9FFFu : 0x801Fu)) return -1;
+    }
     if (wolfy_counts_bad(t)) return -1;
     return 0;
 }
@@ -392,7 +398,7 @@ static int step_session(const tab_t *t, sess_t *s, uint64_t seed, uint64_t sid, 
     }
     if (tag) s->winner = tag;
 
-    s->prev = X; s->phase = Y; s->step = step0 + 1;
+    s->prev = X; s->phase = Y; s->step = (step0 + 1) & 0xFFFF;      /* 16-bit counter (SPEC section 7) */
     if (visits) visits[Y]++;
     return 1;
 }
@@ -541,6 +547,40 @@ int ge_cpu_eval_preds(const uint8_t *blob, size_t nb, const uint8_t *records, ui
         }
     }
     return 0;
+}
+
+/* Record well-formedness (SPEC.md section 7b): the rules the CUDA library applies to every imported record.
+ * ok[i] = 1 when record i may be stepped.  Returns the number of malformed records, or -1 for a bad table. */
+long ge_cpu_validate_records(const uint8_t *blob, size_t nb, const uint8_t *records, uint64_t n_sessions, uint8_t *ok) {
+    tab_t t;
+    if (tab_open(&t, blob, nb)) return -1;
+    const size_t S = rec_size(&t);
+    long bad = 0;
+    for (uint64_t i = 0; i < n_sessions; ++i) {
+        const uint8_t *r = records + i * S;
+        int good = 1;
+        const unsigned step = rd16(r + 2);
+        if (r[0] >= t.n_phases || r[1] >= t.n_phases) good = 0;             /* the table is indexed with both */
+        if (step == 0 && (r[0] != 0 || r[1] != 0)) good = 0;                /* a session that has not started is in phase 0 */
+        if (t.family == FAM_WEREWOLF) {
+            if (r[4] > 2 || r[5] > t.P || r[6] > t.P) good = 0;             /* winner tag, kill / protect ids */
+            if ((r[7] & 0x7F) > t.max_revotes || (t.max_revotes == 0 && r[7] != 0)) good = 0;
+            for (int f = 0; f < 10; ++f)                                    /* no mask bit above the player count */
+                for (int p = t.P; p < 32; ++p)
+                    if ((rd32(r + 8 + 4 * f) >> p) & 1u) good = 0;
+            for (size_t p = 0; 48 + p < S; ++p)                             /* targets are player ids; padding is zero */
+                if (r[48 + p] > ((int)p < t.P ? t.P : 0)) good = 0;
+        } else {
+            if (r[4] > t.P || r[6] > t.P || r[7] != 0) good = 0;            /* speaker, winner, reserved byte */
+            for (size_t p = 0; 8 + 4 * p < S; ++p) {
+                if ((int)p < t.P) { if (r[11 + 4 * p] & 0xE0) good = 0; }   /* five flag bits */
+                else if (r[8 + 4 * p] || r[9 + 4 * p] || r[10 + 4 * p] || r[11 + 4 * p]) good = 0;
+            }
+        }
+        if (ok) ok[i] = (uint8_t)good;
+        bad += !good;
+    }
+    return bad;
 }
 
 int ge_cpu_max_threads(void) {

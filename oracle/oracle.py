@@ -38,6 +38,8 @@ class Oracle:
         L.ge_cpu_stats_final.argtypes = [u8p, sz, u8p, u64, u8p]
         L.ge_cpu_peek_choices.argtypes = [u8p, sz, u8p, u64, u64, u8p]
         L.ge_cpu_philox.argtypes = [u8p, u8p, u8p]
+        L.ge_cpu_validate_records.argtypes = [u8p, sz, u8p, u64, u8p]
+        L.ge_cpu_validate_records.restype = ctypes.c_long
         L.ge_cpu_eval_preds.argtypes = [u8p, sz, u8p, u64, u8p, ctypes.c_int, u8p]
         self.blob = bytes(blob)
         self._blob_buf = ctypes.create_string_buffer(self.blob, len(self.blob))
@@ -77,6 +79,14 @@ class Oracle:
         out = np.zeros((rec.shape[0], arr.shape[0]), dtype=np.uint32)
         self.lib.ge_cpu_eval_preds(self._bp, len(self.blob), rec.ctypes.data, rec.shape[0], arr.ctypes.data, arr.shape[0], out.ctypes.data)
         return out
+
+    def validate_records(self, rec: np.ndarray) -> np.ndarray:
+        """ok[i] = True when record i is well-formed (SPEC.md section 7b), the rule set of the library's import paths."""
+        rec = np.ascontiguousarray(rec, dtype=np.uint8).reshape(-1, self.record_size)
+        ok = np.zeros(rec.shape[0], dtype=np.uint8)
+        if self.lib.ge_cpu_validate_records(self._bp, len(self.blob), rec.ctypes.data, rec.shape[0], ok.ctypes.data) < 0:
+            raise RuntimeError("ge_cpu_validate_records failed")
+        return ok.astype(bool)
 
     def philox(self, key, ctr):
         k = np.asarray(key, dtype=np.uint32)

@@ -53,6 +53,6 @@ def test_cuda_arm_prints_one_contract_line():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 65536 * 56 and e["d2h_bytes_per_step"] >= 65536 * 56
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 65536 * 32 and e["d2h_bytes_per_step"] >= 65536 * 32 and e["wire"]["record_bytes"] == 32
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
