@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--ring", type=int, default=8, help="batches in the ring (footprint must exceed L2)")
     ap.add_argument("--cap", type=int, default=0, help="steps before a batch is re-initialised (0 = by player count)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tps", "tps_generic", "coop"])
+    ap.add_argument("--launch", default="streams", choices=["streams", "ring"],
+                    help="streams: one step launch per batch, the ring's batches spread over --streams CUDA streams; "
+                         "ring: ONE launch per pass over the ring on one stream (ge_step_ring, full-occupancy grid)")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the ring's independent batches are spread over")
     ap.add_argument("--ctas-per-sm", type=int, default=3,
                     help="persistent grid of a step launch = SMs x this (0 = occupancy limit); small grids let the launches "
@@ -337,7 +340,8 @@ def run_ours(a):
     tab = Table(cg)
     # the ring's batches are independent sessions: batch i runs on stream i % NS so that one batch's launch
     # ramp / tail and near-empty late-game launches overlap with another batch's work
-    NS = max(1, min(a.streams, R))
+    merged = a.launch == "ring" and a.kernel != "coop"
+    NS = 1 if merged else max(1, min(a.streams, R))
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     stream = streams[0]
     torch.cuda.set_stream(stream)
@@ -349,7 +353,7 @@ def run_ours(a):
     ring = [SessionBatch(tab, N, first_session_id=sid_base(0, i), seed=a.seed, device=local_rank, kernel=a.kernel) for i in range(R)]
     for i, b in enumerate(ring):
         b.set_stream(streams[i % NS].cuda_stream)
-        b.set_grid(a.ctas_per_sm)
+        b.set_grid(0 if merged else a.ctas_per_sm)
         if a.regroup:
             b.set_regroup(*[int(x) for x in a.regroup.split(",")])
         if a.compaction:
@@ -369,9 +373,17 @@ def run_ours(a):
         if pre:
             b.step(pre)
         age[i] = pre
-    from game_engine_b200.batch import step_many
+    from game_engine_b200.batch import step_many, step_ring
     k_global = 0
     resets = 0
+
+    def step_each(batches):
+        """one step of each batch of the list: a launch per batch, or (--launch ring) one launch for the list"""
+        if merged and batches:
+            step_ring(batches, 1)
+        else:
+            for b in batches:
+                b.step(1)
 
     def run_steps(n):
         """n launches, round-robin over the ring starting at slot k_global % R; a batch that has been stepped
@@ -390,13 +402,11 @@ def run_ours(a):
                 run += 1
             run = max(run, 1)
             head = min(run, (R - i) % R)              # finish the current round first
-            for j in range(head):
-                ring[(i + j) % R].step(1)
+            step_each([ring[(i + j) % R] for j in range(head)])
             full, tail = divmod(run - head, R)
             if full:
-                step_many(ring, full)
-            for j in range(tail):
-                ring[j].step(1)
+                (step_ring if merged else step_many)(ring, full)
+            step_each(ring[:tail])
             for j in range(run):
                 age[(i + j) % R] += 1
             k_global += run
@@ -590,7 +600,8 @@ def run_ours(a):
         "dtype": "u32", "data": "synthetic",
         "config": {
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
-            "kernel": kern, "streams": NS, "ctas_per_sm": a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
+            "kernel": kern, "launch": "one ring launch per pass (ge_step_ring)" if merged else "one launch per batch", "streams": NS,
+            "ctas_per_sm": "occupancy limit" if merged else a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
             "steps_before_reinit": "when every game of the batch is over (device-side auto-reset, checked every 8 steps)" if auto else cap,
             "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
             "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,

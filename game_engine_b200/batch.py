@@ -256,6 +256,13 @@ def step_many(batches, n_rounds: int = 1) -> None:
     capi.check(capi.lib().ge_step_many(arr, len(batches), int(n_rounds)))
 
 
+def step_ring(batches, n_rounds: int = 1) -> None:
+    """n_rounds passes over a ring of batches, ONE launch per pass (ge_step_ring): same results as step_many for
+    batches that share table, device, seed, kernel and stream."""
+    arr = (ctypes.c_void_p * len(batches))(*[b._h for b in batches])
+    capi.check(capi.lib().ge_step_ring(arr, len(batches), int(n_rounds)))
+
+
 class PinnedBuffer:
     """Page-locked host memory from the library (cudaHostAlloc) exposed as a NumPy array."""
 

@@ -45,6 +45,7 @@ SYMBOLS = [
     ("ge_batch_get_kernel", _int, [_vp]),
     ("ge_step", _int, [_vp, _int, _vp]),
     ("ge_step_many", _int, [ctypes.POINTER(_vp), _int, _int]),
+    ("ge_step_ring", _int, [ctypes.POINTER(_vp), _int, _int]),
     ("ge_run_fused", _int, [_vp, _int, _vp]),
     ("ge_sync", _int, [_vp]),
     ("ge_export_state", _int, [_vp, _u64, _u64, _vp]),

@@ -44,9 +44,11 @@ struct ge_table {
     size_t rec_canon, rec_dev;   // canonical / device record bytes
     uint32_t init_words[40];     // initial device record
     void (*spec_fn)(const DevTable, const StepArgs);   // build-time specialised step kernel for this exact table, or NULL
+    void (*spec_ring_fn)(const DevTable, const StepArgs, const RingArgs);   // its ring-launch twin
 };
 
 typedef void (*step_fn)(const DevTable, const StepArgs);
+typedef void (*ring_fn)(const DevTable, const StepArgs, const RingArgs);
 
 struct ge_batch {
     ge_table* tab;
@@ -69,7 +71,8 @@ struct ge_batch {
     unsigned long long* d_cstate; // [0] n_active  [1] n_live  [2] pairs to swap  [3] live already in front  [4] old tiles
     int compact_every, since_compact;
     bool host_fused;              // ge_run_host[_async]: apply n_steps in one fused launch
-    unsigned long long* h_hint;   // pinned {n_active, epoch}: refreshed by an async copy after every compaction
+    unsigned long long* h_hint;   // pinned, device-mapped {n_active, epoch}: stored by the compaction / regroup kernels
+    unsigned long long* d_hint;   // the same words as the device sees them
     unsigned long long epoch;     // bumped by every (re)initialisation; stale hints are ignored
     bool compacted;               // origin may differ from identity
     // phase regrouping (see k_regroup_*): counting sort of the active prefix by phase, through a scratch store
@@ -83,6 +86,7 @@ struct ge_batch {
     uint32_t next_override;       // presence override for the next launch (0 = read the device word)
     int kernel;
     step_fn fn[4];               // by kernel id (COOP, TPS, TPS_GENERIC)
+    ring_fn rfn[4];              // ring-launch twins (thread-per-session kernels only)
     int grid[4], occ[4];         // persistent grid size / occupancy limit (CTAs per SM) per kernel id
     uint64_t launches;
     int wire;                     // host-buffer record format (GE_WIRE_*); rec_wire = its record size
@@ -248,12 +252,18 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
 }
 
 // build-time specialised kernels (ge_spec_gen.cuh), matched by byte-identical table blobs
-struct SpecEntry { const unsigned char* blob; size_t len; step_fn fn; };
+struct SpecEntry { const unsigned char* blob; size_t len; step_fn fn; ring_fn rfn; };
 template <int FAM, int BUCKET, class S> struct SpecKernel;
-template <int BUCKET, class S> struct SpecKernel<FAM_WEREWOLF, BUCKET, S> { static step_fn fn() { return (step_fn)k_step_w_tps<BUCKET, S>; } };
-template <int BUCKET, class S> struct SpecKernel<FAM_TTL, BUCKET, S> { static step_fn fn() { return (step_fn)k_step_t_tps<BUCKET, S>; } };
-#define GE_SPEC_ENTRY(S, FAM, BUCKET) {spec::S##_blob, sizeof(spec::S##_blob), SpecKernel<FAM, BUCKET, spec::S>::fn()},
-static const SpecEntry g_specs[] = { GE_SPEC_LIST(GE_SPEC_ENTRY) {nullptr, 0, nullptr} };
+template <int BUCKET, class S> struct SpecKernel<FAM_WEREWOLF, BUCKET, S> {
+    static step_fn fn() { return (step_fn)k_step_w_tps<BUCKET, S>; }
+    static ring_fn rfn() { return (ring_fn)k_ring_w_tps<BUCKET, S>; }
+};
+template <int BUCKET, class S> struct SpecKernel<FAM_TTL, BUCKET, S> {
+    static step_fn fn() { return (step_fn)k_step_t_tps<BUCKET, S>; }
+    static ring_fn rfn() { return (ring_fn)k_ring_t_tps<BUCKET, S>; }
+};
+#define GE_SPEC_ENTRY(S, FAM, BUCKET) {spec::S##_blob, sizeof(spec::S##_blob), SpecKernel<FAM, BUCKET, spec::S>::fn(), SpecKernel<FAM, BUCKET, spec::S>::rfn()},
+static const SpecEntry g_specs[] = { GE_SPEC_LIST(GE_SPEC_ENTRY) {nullptr, 0, nullptr, nullptr} };
 
 extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
     if (!out) return fail(GE_ERR_ARG, "out is NULL");
@@ -262,9 +272,10 @@ extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
     const int rc = validate_and_build(blob, n, t);
     if (rc != GE_OK) { delete t; return rc; }
     t->spec_fn = nullptr;
+    t->spec_ring_fn = nullptr;
     const size_t used = sizeof(ge_table_header_t) + (size_t)t->dev.h.n_phases * sizeof(ge_phase_t) + (size_t)t->dev.h.n_preds * sizeof(ge_pred_t);
     for (const SpecEntry* e = g_specs; e->blob; ++e)
-        if (e->len == used && memcmp(e->blob, blob, used) == 0) t->spec_fn = e->fn;
+        if (e->len == used && memcmp(e->blob, blob, used) == 0) { t->spec_fn = e->fn; t->spec_ring_fn = e->rfn; }
     *out = t;
     return GE_OK;
 }
@@ -293,6 +304,25 @@ static step_fn pick_fn(const ge_table* t, int kernel) {
         case 8: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<8> : (step_fn)k_step_t_tps<8>;
         case 16: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<16> : (step_fn)k_step_t_tps<16>;
         case 32: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<32> : (step_fn)k_step_t_tps<32>;
+        }
+    }
+    return nullptr;
+}
+
+static ring_fn pick_ring_fn(const ge_table* t) {
+    if (t->family == FAM_WEREWOLF) {
+        switch (t->bucket) {
+        case 8: return (ring_fn)k_ring_w_tps<8>;
+        case 16: return (ring_fn)k_ring_w_tps<16>;
+        case 24: return (ring_fn)k_ring_w_tps<24>;
+        case 32: return (ring_fn)k_ring_w_tps<32>;
+        }
+    } else {
+        switch (t->bucket) {
+        case 4: return (ring_fn)k_ring_t_tps<4>;
+        case 8: return (ring_fn)k_ring_t_tps<8>;
+        case 16: return (ring_fn)k_ring_t_tps<16>;
+        case 32: return (ring_fn)k_ring_t_tps<32>;
         }
     }
     return nullptr;
@@ -400,6 +430,7 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     }
     for (int k = GE_KERNEL_COOP; k <= GE_KERNEL_TPS_GENERIC; ++k) {
         b->fn[k] = k == GE_KERNEL_TPS_GENERIC ? pick_fn(t, GE_KERNEL_TPS) : (k == GE_KERNEL_TPS && t->spec_fn) ? t->spec_fn : pick_fn(t, k);
+        b->rfn[k] = k == GE_KERNEL_COOP ? nullptr : (k == GE_KERNEL_TPS && t->spec_ring_fn) ? t->spec_ring_fn : pick_ring_fn(t);
         if (!b->fn[k]) { ge_batch_destroy(b); return fail(GE_ERR_UNSUPPORTED, "no kernel for this table"); }
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)b->fn[k], 128, 0);
@@ -555,24 +586,35 @@ extern "C" int ge_batch_active(ge_batch* b, uint64_t* out) {
 }
 extern "C" int ge_batch_get_kernel(const ge_batch* b) { return b ? b->kernel : GE_ERR_ARG; }
 
-// scan -> rank -> swap -> commit on the live masks of the step that just ran (all asynchronous, no host sync)
-static int enqueue_compaction(ge_batch* b, cudaStream_t st) {
-    if (!b->compacted) {
-        k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
-        b->compacted = true;
-        b->launches++;
+// scan -> rank -> swap -> commit on the live masks of the step that just ran, for a list of batches of one table in
+// ONE launch pair (all asynchronous, no host sync, no copies: the kernels store the host's progress hint themselves)
+static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st) {
+    CompactArgs ca;
+    memset(&ca, 0, sizeof ca);
+    ca.n = n;
+    ca.S = (uint32_t)list[0]->tab->rec_dev;
+    ca.dead_shift = (uint32_t)list[0]->dead_shift;
+    int max_scan = 1;
+    uint64_t max_tiles = 1;
+    for (int i = 0; i < n; ++i) {
+        ge_batch* b = list[i];
+        if (!b->compacted) {
+            k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
+            b->compacted = true;
+            b->launches++;
+        }
+        ca.s[i] = CompactSlot{b->d_tiles, b->d_origin, b->d_live_mask, b->d_prefix, b->d_blk, b->d_cstate, b->d_hint};
+        if (b->scan_blocks > max_scan) max_scan = b->scan_blocks;
+        if (b->n_tiles > max_tiles) max_tiles = b->n_tiles;
+        b->since_compact = 0;
     }
-    k_compact_scan<<<b->scan_blocks, 1024, 0, st>>>(b->d_live_mask, b->d_prefix, b->d_blk, b->d_cstate, (uint32_t)b->dead_shift);
-    uint64_t sg = (b->n_tiles * 16 + 127) / 128;
-    if (sg > (uint64_t)b->sm_count * 8) sg = (uint64_t)b->sm_count * 8;
-    k_compact_swap<<<(int)(sg < 1 ? 1 : sg), 128, 0, st>>>(
-        b->d_tiles, (uint32_t)b->tab->rec_dev, b->d_origin, b->d_live_mask, b->d_prefix, b->d_blk, b->d_cstate);
+    list[0]->launches += 2;                           // one launch pair for the whole list
+    k_compact_scan<<<dim3(max_scan, n), 1024, 0, st>>>(ca);
+    uint64_t sg = (max_tiles * 16 + 127) / 128;
+    const uint64_t cap = (uint64_t)list[0]->sm_count * 8 / (n > 4 ? 4 : n);       // the list shares the machine
+    if (sg > cap) sg = cap;
+    k_compact_swap<<<dim3((unsigned)(sg < 1 ? 1 : sg), n), 128, 0, st>>>(ca);
     CU(cudaGetLastError());
-    b->launches += 2;
-    b->since_compact = 0;
-    // non-blocking progress hint for the host: {n_active, epoch} (cstate[0], cstate[7] are not adjacent: two copies)
-    CU(cudaMemcpyAsync(&b->h_hint[0], b->d_cstate, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&b->h_hint[1], b->d_cstate + 7, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     return GE_OK;
 }
 
@@ -583,29 +625,41 @@ static int enqueue_regroup(ge_batch* b, cudaStream_t st) {
     uint64_t g = (b->n + 1023) / 1024;
     if (g > (uint64_t)b->sm_count * 2) g = (uint64_t)b->sm_count * 2;
     k_regroup_scatter<<<(int)g, 1024, 0, st>>>(b->d_tiles, S, b->d_origin, b->d_rg, b->tab->dev.nonterm, b->d_rg_tiles, b->d_rg_origin);
-    k_regroup_copyback<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->d_tiles, S, b->d_origin, b->d_rg, b->d_rg_tiles, b->d_rg_origin);
+    k_regroup_copyback<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->d_tiles, S, b->d_origin, b->d_rg, b->d_rg_tiles, b->d_rg_origin, b->d_cstate, b->d_hint);
     CU(cudaGetLastError());
     b->launches += 3;
     b->since_compact = 0;
-    CU(cudaMemcpyAsync(&b->h_hint[0], b->d_cstate, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&b->h_hint[1], b->d_cstate + 7, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     return GE_OK;
+}
+
+static void fill_common(const ge_batch* b, StepArgs& a, int steps_per_launch) {
+    a.seed = b->seed; a.n_steps = steps_per_launch;
+    for (int r = 0; r < 10; ++r) {
+        a.rk[2 * r] = (uint32_t)b->seed + (uint32_t)r * 0x9E3779B9u;
+        a.rk[2 * r + 1] = (uint32_t)(b->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+}
+
+// the per-batch arguments of the batch's NEXT step launch (advances its launch index)
+static void fill_slot(ge_batch* b, SlotArgs& a, bool count_live, bool regroup) {
+    a.tiles = b->d_tiles; a.n_sessions = b->n; a.n_tiles = b->n_tiles; a.first_sid = b->first_sid;
+    a.stats = b->d_stats; a.presence = b->d_presence;
+    a.n_active = b->d_cstate; a.live_mask = b->d_live_mask; a.live_count = b->d_cstate + 5;
+    a.sid_stride = b->sid_stride;
+    a.rg = regroup ? b->d_rg : nullptr;
+    a.count_live = count_live ? 1u : 0u;
+    a.launch_idx = b->launch_idx++;
+    a.presence_override = b->next_override;
+    b->next_override = 0;
+    a.origin = b->compacted ? b->d_origin : nullptr;
 }
 
 static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaStream_t st) {
     const step_fn fn = b->fn[b->kernel];
     StepArgs a;
-    a.tiles = b->d_tiles; a.n_sessions = b->n; a.n_tiles = b->n_tiles; a.first_sid = b->first_sid; a.seed = b->seed;
-    a.stats = b->d_stats; a.presence = b->d_presence; a.n_steps = steps_per_launch;
-    a.n_active = b->d_cstate; a.live_mask = b->d_live_mask; a.live_count = b->d_cstate + 5;
-    a.sid_stride = b->sid_stride;
-    for (int r = 0; r < 10; ++r) {
-        a.rk[2 * r] = (uint32_t)b->seed + (uint32_t)r * 0x9E3779B9u;
-        a.rk[2 * r + 1] = (uint32_t)(b->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
-    }
+    fill_common(b, a, steps_per_launch);
     // phase regrouping replaces the swap compaction (it also moves finished games behind the live ones)
     const bool regroup = b->regroup_every > 0 && b->kernel != GE_KERNEL_COOP && steps_per_launch == 1;
-    a.rg = regroup ? b->d_rg : nullptr;
     for (int i = 0; i < n_launches; ++i) {
         if (regroup && !b->compacted) {              // the origin map must exist before the first regrouping
             k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
@@ -614,11 +668,7 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
         }
         const bool regroup_after = regroup && b->since_compact + 1 >= b->regroup_every;
         const bool compact_after = !regroup && b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
-        a.count_live = (compact_after || regroup_after) ? 1u : 0u;
-        a.launch_idx = b->launch_idx++;
-        a.presence_override = b->next_override;
-        b->next_override = 0;
-        a.origin = b->compacted ? b->d_origin : nullptr;
+        fill_slot(b, a, compact_after || regroup_after, regroup);
         fn<<<b->grid[b->kernel], 128, 0, st>>>(b->tab->dev, a);
         b->launches++;
         b->since_compact++;
@@ -626,7 +676,7 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
             const int rc = enqueue_regroup(b, st);
             if (rc != GE_OK) return rc;
         } else if (compact_after) {
-            const int rc = enqueue_compaction(b, st);
+            const int rc = enqueue_compaction(&b, 1, st);
             if (rc != GE_OK) return rc;
         }
         if ((regroup_after || compact_after) && b->sid_stride != 0) {      // every game over? start the next epoch on the device
@@ -637,6 +687,62 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
             k_autoreset_commit<<<1, 32, 0, st>>>(b->d_cstate, b->d_presence, regroup ? b->d_rg : nullptr, b->launch_idx, b->n);
             CU(cudaGetLastError());
             b->launches += 2;
+        }
+    }
+    CU(cudaGetLastError());
+    return GE_OK;
+}
+
+// One step of every batch of a ring in ONE launch (k_ring_*), n_rounds times, all on the FIRST batch's stream.
+// The batches must share table, device, seed, kernel (thread-per-session) and stream, and use neither phase
+// regrouping nor auto-reset; compaction checks that fall due are batched into one launch pair per round.
+extern "C" int ge_step_ring(ge_batch** batches, int n_batches, int n_rounds) {
+    if (!batches || n_batches < 1 || n_batches > GE_RING_MAX || n_rounds < 0) return fail(GE_ERR_ARG, "bad arguments to ge_step_ring (1..16 batches)");
+    ge_batch* b0 = batches[0];
+    if (!b0) return fail(GE_ERR_ARG, "NULL batch in ge_step_ring");
+    for (int i = 0; i < n_batches; ++i) {
+        const ge_batch* b = batches[i];
+        if (!b) return fail(GE_ERR_ARG, "NULL batch in ge_step_ring");
+        if (b->tab != b0->tab || b->device != b0->device || b->seed != b0->seed || b->kernel != b0->kernel || b->stream != b0->stream)
+            return fail(GE_ERR_ARG, "ge_step_ring: the batches must share table, device, seed, kernel and stream (ge_batch_set_stream)");
+        if (b->kernel == GE_KERNEL_COOP || b->regroup_every > 0 || b->sid_stride != 0)
+            return fail(GE_ERR_UNSUPPORTED, "ge_step_ring covers the thread-per-session kernels without phase regrouping / auto-reset");
+        for (int j = 0; j < i; ++j)
+            if (batches[j] == b) return fail(GE_ERR_ARG, "ge_step_ring: a batch appears twice");
+    }
+    CU(cudaSetDevice(b0->device));
+    const ring_fn fn = b0->rfn[b0->kernel];
+    if (!fn) return fail(GE_ERR_UNSUPPORTED, "no ring kernel for this table");
+    StepArgs c;
+    memset(&c, 0, sizeof c);
+    fill_common(b0, c, 1);
+    // every CTA walks all the slots, so the grid is sized for the largest batch at the kernel's occupancy limit
+    uint64_t warps = 0;
+    for (int i = 0; i < n_batches; ++i) if (batches[i]->n_tiles > warps) warps = batches[i]->n_tiles;
+    uint64_t g = (warps + 3) / 4;
+    uint64_t cap = (uint64_t)b0->sm_count * b0->occ[b0->kernel];
+    if (const char* e = getenv("GE_RING_CTAS_PER_SM")) { const int v = atoi(e); if (v > 0 && v < b0->occ[b0->kernel]) cap = (uint64_t)b0->sm_count * v; }
+    if (g > cap) g = cap;
+    for (int r = 0; r < n_rounds; ++r) {
+        RingArgs ra;
+        ra.n = n_batches;
+        ra.rot_div = (uint32_t)b0->sm_count;
+        ge_batch* due[GE_RING_MAX];
+        int n_due = 0;
+        // the ring is checked as a whole, on the first batch's cadence: one launch pair for all its batches
+        const bool ring_due = b0->compact_every > 0 && b0->since_compact + 1 >= b0->compact_every;
+        for (int i = 0; i < n_batches; ++i) {
+            ge_batch* b = batches[i];
+            const bool compact_after = ring_due && b->compact_every > 0;
+            fill_slot(b, ra.slot[i], compact_after, false);
+            b->since_compact++;
+            if (compact_after) due[n_due++] = b;
+        }
+        fn<<<(unsigned)(g < 1 ? 1 : g), 128, 0, b0->stream>>>(b0->tab->dev, c, ra);
+        b0->launches++;                               // ONE launch for the whole ring
+        if (n_due) {
+            const int rc = enqueue_compaction(due, n_due, b0->stream);
+            if (rc != GE_OK) return rc;
         }
     }
     CU(cudaGetLastError());

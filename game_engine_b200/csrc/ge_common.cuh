@@ -79,8 +79,15 @@ struct StepArgs : SlotArgs {
 constexpr int GE_RING_MAX = 16;
 struct RingArgs {
     int n;
+    // CTA b starts at slot (b + b / rot_div) % n (rot_div = SM count): the CTAs resident on one SM then work on
+    // DIFFERENT batches at any moment, so a batch in a bandwidth-bound phase (header-only steps) shares the SM with
+    // one in an issue-bound phase (votes) — the overlap that separate launches on separate streams used to give.
+    uint32_t rot_div;
     SlotArgs slot[GE_RING_MAX];
 };
+__device__ __forceinline__ int ring_first_slot(const RingArgs& R) {
+    return (int)((blockIdx.x + blockIdx.x / R.rot_div) % (uint32_t)R.n);
+}
 
 __device__ __forceinline__ uint64_t first_sid_of(const SlotArgs& A) {
     return A.sid_stride ? A.first_sid + A.n_active[8] * A.sid_stride : A.first_sid;

@@ -343,13 +343,38 @@ __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s
     return s_warp[warp] + incl - v;
 }
 
-// grid = ceil(max tiles / 1024) blocks of 1024 threads.  loc[t] = live sessions in tiles of the same block
+// The compaction kernels take a LIST of batches (blockIdx.y selects one): a ring stepped by one launch is also
+// checked by one launch pair, and a single batch is a list of one.  `hint` is the batch's pinned host word pair
+// {n_active, host epoch} (mapped into the device address space): the swap kernel stores the new values there
+// directly, so the host's non-blocking progress hint costs no copy operations on the stream.
+struct CompactSlot {
+    uint8_t* tiles;
+    uint32_t* origin;
+    uint32_t* live_mask;
+    uint32_t* loc;
+    uint32_t* blk;
+    unsigned long long* cstate;
+    unsigned long long* hint;
+};
+struct CompactArgs {
+    int n;
+    uint32_t S, dead_shift;
+    CompactSlot s[GE_RING_MAX];
+};
+
+// grid = (ceil(max tiles / 1024), batches) blocks of 1024 threads.  loc[t] = live sessions in tiles of the same block
 // before t, blk[b] = live sessions in blocks before b (filled in by the last block to finish).
 __global__ void __launch_bounds__(1024)
-k_compact_scan(const uint32_t* __restrict__ live_mask, uint32_t* loc, uint32_t* blk, unsigned long long* cstate, uint32_t dead_shift) {
+k_compact_scan(const __grid_constant__ CompactArgs CA) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_last;
+    const CompactSlot& Q = CA.s[blockIdx.y];
+    const uint32_t* __restrict__ live_mask = Q.live_mask;
+    uint32_t* loc = Q.loc;
+    uint32_t* blk = Q.blk;
+    unsigned long long* cstate = Q.cstate;
+    const uint32_t dead_shift = CA.dead_shift;
     const uint64_t n_act = cstate[0];
     const uint64_t live_now = cstate[5];
     const uint64_t nt = (n_act + 31) >> 5;
@@ -393,10 +418,24 @@ k_compact_scan(const uint32_t* __restrict__ live_mask, uint32_t* loc, uint32_t* 
 // Pair i swaps the i-th terminal session of the front region [0, n_live) with the i-th live session of the
 // back region [n_live, old prefix).  Both are located by binary search over the two-level prefix
 // P(t) = blk[t / 1024] + loc[t] (terminals before tile t = 32t - P(t)).  One thread per pair.
-__global__ void k_compact_swap(uint8_t* tiles, uint32_t S, uint32_t* origin, const uint32_t* __restrict__ live_mask,
-                               const uint32_t* __restrict__ loc, const uint32_t* __restrict__ blk, unsigned long long* cstate) {
+__global__ void k_compact_swap(const __grid_constant__ CompactArgs CA) {
+    const CompactSlot& Q = CA.s[blockIdx.y];
+    uint8_t* tiles = Q.tiles;
+    const uint32_t S = CA.S;
+    uint32_t* origin = Q.origin;
+    const uint32_t* __restrict__ live_mask = Q.live_mask;
+    const uint32_t* __restrict__ loc = Q.loc;
+    const uint32_t* __restrict__ blk = Q.blk;
+    unsigned long long* cstate = Q.cstate;
     const uint64_t n_live = cstate[1], pairs = cstate[2], in_front = cstate[3], nt = cstate[4];
-    if (blockIdx.x == 0 && threadIdx.x == 0) cstate[5] = 0;      // the next counted step starts from zero
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cstate[5] = 0;                                           // the next counted step starts from zero
+        if (Q.hint) {                                            // progress hint for the host: value first, then its epoch tag
+            ((volatile unsigned long long*)Q.hint)[0] = cstate[0];
+            __threadfence_system();
+            ((volatile unsigned long long*)Q.hint)[1] = cstate[7];
+        }
+    }
     if (pairs == 0) return;
     const uint32_t n16 = S / 16;
     const bool half = (S % 16) != 0;
@@ -537,7 +576,13 @@ k_regroup_scatter(const uint8_t* __restrict__ tiles, uint32_t S, const uint32_t*
 }
 
 __global__ void k_regroup_copyback(uint8_t* __restrict__ tiles, uint32_t S, uint32_t* __restrict__ origin, const uint32_t* __restrict__ rg,
-                                   const uint8_t* __restrict__ in_tiles, const uint32_t* __restrict__ in_origin) {
+                                   const uint8_t* __restrict__ in_tiles, const uint32_t* __restrict__ in_origin,
+                                   const unsigned long long* cstate, unsigned long long* hint) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && hint) {           // progress hint for the host (see k_compact_swap)
+        ((volatile unsigned long long*)hint)[0] = cstate[0];
+        __threadfence_system();
+        ((volatile unsigned long long*)hint)[1] = cstate[7];
+    }
     const uint32_t old = rg[RG_OLD];
     const uint32_t n16 = S / 16;
     const bool half = (S % 16) != 0;

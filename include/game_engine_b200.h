@@ -151,6 +151,13 @@ int ge_step(ge_batch *b, int n_steps, void *cuda_stream);
  * its own (bound) stream.  One call instead of n_rounds * n_batches keeps the host out of the way when the
  * launches are short. */
 int ge_step_many(ge_batch **batches, int n_batches, int n_rounds);
+/* The same round-robin as ONE launch per round: a ring kernel whose CTAs walk the batches in order, on the first
+ * batch's stream, with the compaction checks that fall due batched into one launch pair.  A 2^20-session batch is only
+ * ~10 us of work, so separate launches live in their ramp-up and tail unless many streams overlap them; the ring
+ * launch pays one ramp and one tail per round.  Up to 16 batches that share table, device, seed, kernel (thread per
+ * session) and stream (ge_batch_set_stream), without phase regrouping or auto-reset.  Results are identical to
+ * ge_step_many's. */
+int ge_step_ring(ge_batch **batches, int n_batches, int n_rounds);
 /* Same semantics with the state kept in registers for up to n_steps steps (one launch). */
 int ge_run_fused(ge_batch *b, int n_steps, void *cuda_stream);
 int ge_sync(ge_batch *b);

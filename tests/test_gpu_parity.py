@@ -347,3 +347,43 @@ def test_autoreset_runs_epochs_on_the_device(games, oracle_for, game, P, every, 
     b.step(20)
     o.step(rec, 5, seed, 20)
     np.testing.assert_array_equal(b.export_state(), rec)
+
+
+@pytest.mark.parametrize("game,P,kernel", [(WEREWOLF, 8, "tps"), (WEREWOLF, 8, "tps_generic"), (WEREWOLF, 32, "tps"), (TTL, 4, "tps"),
+                                           (DRAFT, 6, "tps"), (WEREWOLF, 16, "tps")])
+def test_ring_launch_equals_separate_launches(games, oracle_for, game, P, kernel):
+    """ge_step_ring (one launch per pass over a ring of batches, compaction checks batched) == the oracle, with the
+    ring's batches at different depths of their games and of different sizes."""
+    from game_engine_b200.batch import SessionBatch, Table, step_ring
+    from game_engine_b200.capi import GameEngineError
+    cg = games(game, P)
+    o = oracle_for(cg)
+    t = Table(cg)
+    sizes = [3000, 777, 4096, 33, 1500]
+    firsts = [0, 10000, 20000, 30000, 40000]
+    seed = 77
+    ring = [SessionBatch(t, n, first_session_id=f, seed=seed, kernel=kernel) for n, f in zip(sizes, firsts)]
+    st = ring[0].state_device_ptr() and 0
+    import torch
+    stream = torch.cuda.Stream()
+    for i, b in enumerate(ring):
+        b.set_stream(stream.cuda_stream)
+        b.set_compaction(3, 2) if cg.family == 1 else None
+        b.step(4 * i)                                  # staggered ages
+    total = 0
+    for rounds in (1, 7, 30, 25):
+        step_ring(ring, rounds)
+        total += rounds
+        for i, b in enumerate(ring):
+            rec = o.init(sizes[i])
+            ost = o.new_stats()
+            o.step(rec, firsts[i], seed, 4 * i + total, ost)
+            o.stats_final(rec, ost)
+            np.testing.assert_array_equal(b.export_state(), rec)
+            np.testing.assert_array_equal(b.stats(), ost)
+    # a sub-list is a ring too; mismatched seeds are refused
+    step_ring(ring[1:3], 2)
+    other = SessionBatch(t, 64, first_session_id=0, seed=seed + 1, kernel=kernel)
+    other.set_stream(stream.cuda_stream)
+    with pytest.raises(GameEngineError):
+        step_ring([ring[0], other], 1)

@@ -24,7 +24,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from game_engine_b200 import compile_game  # noqa: E402
-from game_engine_b200.batch import SessionBatch, Table, step_many  # noqa: E402
+from game_engine_b200.batch import SessionBatch, Table, step_many, step_ring  # noqa: E402
 
 
 def main():
@@ -39,7 +39,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=60)
     ap.add_argument("--cap", type=int, default=0)
     ap.add_argument("--kernel", default="auto")
-    ap.add_argument("--persistent", type=int, default=-1, help="ring stepping mode, when the library offers one (-1 = default)")
+    ap.add_argument("--launch", default="streams", choices=["streams", "ring"], help="one launch per batch on --streams streams, or one ring launch per pass")
     a = ap.parse_args()
     from bench import game_cap
     dev = torch.device("cuda", 0)
@@ -48,12 +48,13 @@ def main():
     cap = a.cap or game_cap(cg.family, a.players, cg.table.max_revotes)
     tab = Table(cg)
     R, N = a.ring, a.sessions
-    NS = max(1, min(a.streams, R))
+    merged = a.launch == "ring"
+    NS = 1 if merged else max(1, min(a.streams, R))
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     ring = [SessionBatch(tab, N, first_session_id=i * N, seed=1, kernel=a.kernel) for i in range(R)]
     for i, b in enumerate(ring):
         b.set_stream(streams[i % NS].cuda_stream)
-        b.set_grid(a.ctas_per_sm)
+        b.set_grid(0 if merged else a.ctas_per_sm)
     age, epoch = [0] * R, [0] * R
     for i, b in enumerate(ring):
         pre = (i * cap) // R
@@ -68,7 +69,7 @@ def main():
                     epoch[i] += 1
                     b.reset(first_session_id=(epoch[i] * R + i) * N)
                     age[i] = 0
-            step_many(ring, 1)
+            (step_ring if merged else step_many)(ring, 1)
             for i in range(R):
                 age[i] += 1
 
@@ -94,7 +95,7 @@ def main():
     counted = sum(b.counted_steps() for b in ring) - c0
     launches = sum(b.launch_count() for b in ring) - l0
     S = cg.record_size
-    print(json.dumps({"game": a.game, "players": a.players, "sessions_per_batch": N, "ring": R, "streams": NS,
+    print(json.dumps({"game": a.game, "players": a.players, "sessions_per_batch": N, "ring": R, "launch": a.launch, "streams": NS,
                       "ctas_per_sm": a.ctas_per_sm, "passes": a.steps, "region_ms": ms, "counted_steps": counted,
                       "launches": launches, "steps_per_s": counted / (ms * 1e-3), "record_bytes": S,
                       "algorithmic_bytes": counted * 2 * S}), flush=True)
