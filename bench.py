@@ -39,23 +39,54 @@ def game_cap(family: int, players: int, max_revotes: int = 0) -> int:
     return 9 * players - 16 + 2 * max_revotes * (players - 2) if family == 1 else 2 + 8 * players
 
 
+# BASELINE.json configs[1..4] ("config 2..5" in BASELINE.md section 4).  `total` sessions are sharded over the ranks; each
+# rank keeps a ring of R independent replicas of its shard (different session ids) so that its inputs come from HBM.
+CONFIGS = {
+    2: dict(game="werewolf-(mafia)", players=8, total=None, sessions=1 << 20, ring=8, streams=8, ctas_per_sm=3),
+    3: dict(game="werewolf-(mafia)", players=16, total=1 << 24, ring=4, streams=4, ctas_per_sm=3),
+    4: dict(game="werewolf-revote", players=32, total=1 << 26, ring=1, streams=1, ctas_per_sm=0),
+    5: dict(game="two-truths-and-a-lie", players=4, total=1 << 28, ring=2, streams=2, ctas_per_sm=0),
+}
+
+
+def apply_config(a, world: int):
+    """--config N presets game / players / sessions per batch / ring / streams (explicit flags still win)."""
+    c = CONFIGS[a.config]
+    given = {k for k in ("game", "players", "sessions", "ring", "streams", "ctas_per_sm") if getattr(a, k) is not None}
+    for k in ("game", "players", "ring", "streams", "ctas_per_sm"):
+        if k not in given:
+            setattr(a, k, c[k])
+    if "sessions" not in given:
+        if c["total"] is None:
+            a.sessions = c["sessions"]                       # config 2: 2^20 sessions per batch on every GPU (weak scaling)
+        else:
+            # the shard of this rank; the ring holds R independent replicas of it so that the resident data set stays
+            # larger than L2 (2^24 sessions x 64 B over 8 GPUs is 134 MB per GPU: one replica would sit in the 126 MB L2)
+            a.sessions = max(1 << 16, c["total"] // max(1, world))
+    return a
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.md section 4 configuration: 2 = werewolf 8 players, 2^20 sessions per batch per GPU (the headline, "
+                         "default); 3 = werewolf 16 players, 2^24 sessions sharded over the GPUs; 4 = werewolf-revote 32 players, "
+                         "2^26 sessions sharded; 5 = two-truths-and-a-lie, 2^28 sessions sharded")
     ap.add_argument("--steps", type=int, default=2500, help="timed steps; one step = one pass over the ring (one launch per batch)")
     ap.add_argument("--warmup", type=int, default=25)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--game", default="werewolf-(mafia)")
-    ap.add_argument("--players", type=int, default=8)
-    ap.add_argument("--sessions", type=int, default=1 << 20, help="sessions per batch (per GPU)")
-    ap.add_argument("--ring", type=int, default=8, help="batches in the ring (footprint must exceed L2)")
+    ap.add_argument("--game", default=None)
+    ap.add_argument("--players", type=int, default=None)
+    ap.add_argument("--sessions", type=int, default=None, help="sessions per batch (per GPU)")
+    ap.add_argument("--ring", type=int, default=None, help="batches in the ring (footprint must exceed L2)")
     ap.add_argument("--cap", type=int, default=0, help="steps before a batch is re-initialised (0 = by player count)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tps", "tps_generic", "coop"])
     ap.add_argument("--launch", default="streams", choices=["streams", "ring"],
                     help="streams: one step launch per batch, the ring's batches spread over --streams CUDA streams; "
                          "ring: ONE launch per pass over the ring on one stream (ge_step_ring, full-occupancy grid)")
-    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the ring's independent batches are spread over")
-    ap.add_argument("--ctas-per-sm", type=int, default=3,
+    ap.add_argument("--streams", type=int, default=None, help="CUDA streams the ring's independent batches are spread over")
+    ap.add_argument("--ctas-per-sm", type=int, default=None,
                     help="persistent grid of a step launch = SMs x this (0 = occupancy limit); small grids let the launches "
                          "of the ring's other batches be resident at the same time")
     ap.add_argument("--autoreset", action="store_true",
@@ -74,7 +105,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    return apply_config(a, int(os.environ.get("WORLD_SIZE", "1")))
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -144,13 +176,33 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload_key: str):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, or None."""
+L2_BYTES = 126 << 20
+
+
+def ncu_traffic(game: str, players: int, kernel: str, sessions: int, ring: int, record_bytes: int):
+    """Physical DRAM traffic per counted step of this workload from the committed ncu captures (profiles/traffic.json,
+    written by tools/phys_traffic.py), or None.  An entry is used only for the same table, player count and kernel,
+    and only when its resident data set and ours are on the same side of the L2 capacity (bytes per step do not
+    depend on the batch size once the ring is several times larger than L2 — cfg 5: 42.4 B at 2^24 and 42.5 B at
+    2^27 sessions per batch — but a ring that fits in L2 moves almost nothing: 6.6 B at 4 x 2^19 x 64 B)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload_key)
+            t = json.load(f)
     except Exception:
         return None
+    exact = t.get("%s_p%d_%s_n%d" % (game, players, kernel, sessions))
+    if exact:
+        return exact
+    mine = ring * sessions * record_bytes
+    best = None
+    for k, e in t.items():
+        if not k.startswith("%s_p%d_%s_n" % (game, players, kernel)):
+            continue
+        theirs = e.get("resident_bytes", 0)
+        if mine > 2 * L2_BYTES and theirs > 2 * L2_BYTES:
+            if best is None or abs(theirs - mine) < abs(best.get("resident_bytes", 0) - mine):
+                best = dict(e, source=e["source"] + " [measured at %d sessions per batch]" % e.get("sessions_per_batch", 0))
+    return best
 
 
 def build_oracle_native():
@@ -185,17 +237,24 @@ def cpu_oracle_rate(cg, n_sessions: int, cap: int, seed: int, threads: int, nati
 
 
 def cpu_baseline(cg, cap: int, seed: int, target_seconds: float):
+    """Oracle B on whole games of the same workload: best of 5 on all host threads, plus a single-thread figure
+    (BASELINE.md section 4); the five runs together take about `target_seconds`."""
     native = build_oracle_native()
     from oracle.oracle import Oracle
     threads = host_threads(Oracle(cg.blob, native=native))
-    steps, dt = cpu_oracle_rate(cg, 1 << 13, cap, seed, threads, native)          # calibration
+    steps, dt = cpu_oracle_rate(cg, 1 << 13, cap, seed, threads, native)          # calibration (also warms the thread pool)
     per_session = dt / (1 << 13)
-    n = int(max(1 << 13, min(1 << 22, target_seconds / max(per_session, 1e-9))))
-    steps, dt = cpu_oracle_rate(cg, n, cap, seed, threads, native)
+    n = int(max(1 << 13, min(1 << 22, target_seconds / 6.0 / max(per_session, 1e-9))))
+    runs = [cpu_oracle_rate(cg, n, cap, seed, threads, native) for _ in range(5)]
+    steps, dt = min(runs, key=lambda r: r[1])
+    n1 = max(1 << 10, n // max(1, threads))
+    s1, d1 = min((cpu_oracle_rate(cg, n1, cap, seed, 1, native) for _ in range(3)), key=lambda r: r[1])
     return {
         "value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": "%d sessions x %d steps (whole games) of the same workload, Oracle B (oracle/ge_oracle.c, gcc -O3%s, OpenMP), %.1f s"
-                  % (n, cap, " -march=native" if native else "", dt),
+        "sample": "%d sessions x %d steps (whole games) of the same workload, Oracle B (oracle/ge_oracle.c, gcc -O3%s, OpenMP), best of 5 "
+                  "(%.2f s; all five: %s)" % (n, cap, " -march=native" if native else "", dt, " ".join("%.2f" % r[1] for r in runs)),
+        "single_thread": {"value": s1 / d1, "unit": UNIT, "sample": "%d sessions, best of 3, %.2f s" % (n1, d1)},
+        "ns_per_step": 1e9 * dt / max(1, steps),
     }
 
 
@@ -519,13 +578,14 @@ def run_ours(a):
         # The public host-buffer call on the same 2^20 sessions, split into NSUB sub-batches driven with
         # run_host_async so that H2D, the steps and D2H of different sub-batches overlap (two copy engines + SMs).
         NSUB = max(1, a.e2e_subs)
-        sub = N // NSUB
+        NE = min(N, 1 << 20)                                  # sessions per end-to-end call (bounded: 2 x NE x W bytes of pinned memory)
+        sub = NE // NSUB
         subs = [SessionBatch(tab, sub, first_session_id=sid_base(1 << 20, 0) + j * sub, seed=a.seed, device=local_rank, kernel=a.kernel)
                 for j in range(NSUB)]
         for sb in subs:
             sb.set_wire(a.wire)
         W = subs[0].wire_record_size                          # bytes per session on the wire
-        pin_in, pin_out, pin_st = PinnedBuffer(N * W), PinnedBuffer(N * W), PinnedBuffer(NSUB * 560 * 8)
+        pin_in, pin_out, pin_st = PinnedBuffer(NE * W), PinnedBuffer(NE * W), PinnedBuffer(NSUB * 560 * 8)
         rin = pin_in.array.reshape(NSUB, sub, W)
         rout = pin_out.array.reshape(NSUB, sub, W)
         rst = pin_st.array.view(np.uint64).reshape(NSUB, 560)
@@ -569,11 +629,11 @@ def run_ours(a):
             dt, e_counted, dt1, s_counted = float(emax[0]), float(esum[1]), float(emax[2]), float(esum[3])
         e2e = {
             "value": e_counted / dt, "unit": UNIT,
-            "h2d_bytes_per_step": N * W, "d2h_bytes_per_step": N * W + NSUB * 560 * 8,
+            "h2d_bytes_per_step": NE * W, "d2h_bytes_per_step": NE * W + NSUB * 560 * 8,
             "wire": {"format": a.wire, "record_bytes": W, "canonical_record_bytes": S},
             "call": "%d back-to-back calls, each %d x SessionBatch.run_host_async (ge_run_host_async): pinned host records in -> "
                     "%d steps -> records + stats out for %d sessions in %d pipelined sub-batches; one sync at the end; bytes "
-                    "are per call" % (a.e2e_calls, NSUB, cap, N, NSUB),
+                    "are per call" % (a.e2e_calls, NSUB, cap, NE, NSUB),
             "calls": a.e2e_calls, "ms_per_call": dt / a.e2e_calls * 1e3, "single_call_latency_ms": lat_ms,
             "single_step_round_trip": {"value": s_counted / dt1, "unit": UNIT, "ms_per_call": dt1 / a.e2e_calls * 1e3,
                                        "note": "n_steps=1 per call: every step crosses PCIe twice"},
@@ -589,31 +649,46 @@ def run_ours(a):
 
     peak, peak_src = hbm_peak()
     B = 2 * S
-    achieved = counted_all / world * B / (ms_max * 1e-3) / 1e9          # per GPU
+    per_gpu = counted_all / world / (ms_max * 1e-3)                       # counted steps per second per GPU
+    achieved = per_gpu * B / 1e9
     kern = ring[0].kernel
-    wl_key = "%s_p%d_%s" % (a.game, a.players, kern)
-    traffic = ncu_traffic(wl_key)
-    launches_per_s = a.steps * R / (ms_max * 1e-3)                        # step-kernel launches per second per GPU
+    step_launches = a.steps * (1 if merged else R)                        # step-kernel launches per GPU in the timed region
+    # physical DRAM traffic: bytes per counted step from the committed ncu capture of THIS workload (same table, players,
+    # kernel and batch size; anything else is refused), times the live step rate
+    tr = ncu_traffic(a.game, a.players, kern, N, R, S)
+    nec = tab.necessary_bytes_per_step(stats)                             # visit-weighted columns that must move (ge_table_phase_io)
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": (tr["bytes_per_step"] * counted_all / world / step_launches) if tr else None, "peak_source": peak_src,
+            "frac_of_nominal_8000": achieved / 8000.0,         # BASELINE.md section 2 asks for the nominal figure too
+            "algorithmic_bytes_per_step": B, "kernel": "k_%s_%s_%s" % ("ring" if merged else "step", "w" if cg.family == 1 else "t", "tps" if kern.startswith("tps") else kern),
+            "steps_per_launch": counted_all / world / step_launches, "launches_per_step": 1 if merged else R,
+            "necessary_bytes_per_step": nec, "necessary_gbs": per_gpu * nec / 1e9, "frac_necessary": per_gpu * nec / 1e9 / peak,
+            "note": "achieved = counted steps x 2S (SURVEY 8d: the whole record read and written every step); necessary = the columns "
+                    "each phase must move (ge_table_phase_io) weighted by the visit histogram; dram_physical = what crossed the "
+                    "DRAM pins (ncu, reads AND writes, caches not flushed between kernels)"}
+    if tr:
+        roof["dram_physical"] = {"bytes_per_step": tr["bytes_per_step"], "read_bytes_per_step": tr["read_bytes_per_step"],
+                                 "write_bytes_per_step": tr["write_bytes_per_step"], "gbs": per_gpu * tr["bytes_per_step"] / 1e9,
+                                 "frac_of_measured_peak": per_gpu * tr["bytes_per_step"] / 1e9 / peak,
+                                 "frac_of_nominal_8000": per_gpu * tr["bytes_per_step"] / 1e9 / 8000.0,
+                                 "issue_frac": per_gpu * tr["warp_instructions_per_step"] / (148 * 4 * 1.965e9),
+                                 "source": tr["source"]}
+    else:
+        roof["dram_physical"] = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
         "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
+            "baseline_config": a.config,
             "kernel": kern, "launch": "one ring launch per pass (ge_step_ring)" if merged else "one launch per batch", "streams": NS,
             "ctas_per_sm": "occupancy limit" if merged else a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
             "steps_before_reinit": "when every game of the batch is over (device-side auto-reset, checked every 8 steps)" if auto else cap,
             "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
             "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,
         },
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "frac_of_nominal_8000": achieved / 8000.0,         # BASELINE.md section 2 asks for the nominal figure too
-                     # what actually crosses the DRAM pins: ncu bytes per launch x the live launch rate (column skipping
-                     # and compaction keep it below the algorithmic bytes)
-                     "dram_gbs_from_traffic": (traffic * launches_per_s / 1e9) if traffic else None,
-                     "algorithmic_bytes_per_step": B, "kernel": "k_step_%s_%s" % ("w" if cg.family == 1 else "t", kern),
-                     "steps_per_launch": counted_all / world / (a.steps * R), "launches_per_step": R},
+        "roofline": roof,
         "e2e": e2e,
         "fused": fused,
         "gpu_launches": launches_all,

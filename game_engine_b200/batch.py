@@ -28,6 +28,28 @@ class Table:
         self.record_size = int(L.ge_table_record_size(self._h))
         assert self.record_size == game.record_size
 
+    def phase_io(self):
+        """[(read_bytes, write_bytes)] per phase index: what a step starting there must move per session."""
+        out = []
+        for i in range(len(self.game.phase_ids)):
+            r, w = ctypes.c_uint32(), ctypes.c_uint32()
+            capi.check(capi.lib().ge_table_phase_io(self._h, i, ctypes.byref(r), ctypes.byref(w)))
+            out.append((int(r.value), int(w.value)))
+        return out
+
+    def necessary_bytes_per_step(self, stats) -> float:
+        """Visit-weighted necessary DRAM bytes per session-phase-step (stats = the u64[560] statistics: words
+        260.. are visits per phase index; a visit to a non-terminal phase is followed by one step that starts there)."""
+        io = self.phase_io()
+        num = den = 0.0
+        for i, (r, w) in enumerate(io):
+            if r + w == 0:
+                continue
+            v = float(stats[260 + i])
+            num += v * (r + w)
+            den += v
+        return num / den if den else 0.0
+
     def close(self) -> None:
         if self._h:
             capi.lib().ge_table_destroy(self._h)
@@ -66,6 +88,26 @@ class SessionBatch:
     @property
     def wire_record_size(self) -> int:
         return int(capi.lib().ge_batch_wire_size(self._h))
+
+    @property
+    def human_stride(self) -> int:
+        return int(capi.lib().ge_table_human_stride(self.table._h))
+
+    def set_human_seats(self, masks: Optional[np.ndarray]) -> None:
+        """Seats played by people: uint32[n], bit p-1 = player p (None = all bots).  SPEC.md D3h."""
+        if masks is None:
+            capi.check(capi.lib().ge_batch_set_human_seats(self._h, None))
+            return
+        m = np.ascontiguousarray(masks, dtype=np.uint32)
+        assert m.size == self.n
+        capi.check(capi.lib().ge_batch_set_human_seats(self._h, m.ctypes.data))
+
+    def set_human_choices(self, choices: np.ndarray) -> None:
+        """Inputs of the human seats for the NEXT step: uint8[n, human_stride], 0xFF = has not acted."""
+        c = np.ascontiguousarray(choices, dtype=np.uint8)
+        assert c.size == self.n * self.human_stride
+        self._hc_keepalive = c                      # the copy is asynchronous
+        capi.check(capi.lib().ge_batch_set_human_choices(self._h, c.ctypes.data))
 
     def set_kernel(self, kernel: str) -> None:
         capi.check(capi.lib().ge_batch_set_kernel(self._h, capi.KERNEL_NAMES[kernel]))

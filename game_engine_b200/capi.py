@@ -26,6 +26,7 @@ SYMBOLS = [
     ("ge_table_destroy", None, [_vp]),
     ("ge_table_record_size", _sz, [_vp]),
     ("ge_table_n_players", _int, [_vp]),
+    ("ge_table_phase_io", _int, [_vp, _int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
     ("ge_batch_create", _int, [_vp, _int, _u64, _u64, _u64, ctypes.POINTER(_vp)]),
     ("ge_batch_reset", _int, [_vp, _u64, _u64]),
     ("ge_batch_clear_stats", _int, [_vp]),
@@ -43,6 +44,9 @@ SYMBOLS = [
     ("ge_batch_active", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_active_hint", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_get_kernel", _int, [_vp]),
+    ("ge_batch_set_human_seats", _int, [_vp, _vp]),
+    ("ge_batch_set_human_choices", _int, [_vp, _vp]),
+    ("ge_table_human_stride", _sz, [_vp]),
     ("ge_step", _int, [_vp, _int, _vp]),
     ("ge_step_many", _int, [ctypes.POINTER(_vp), _int, _int]),
     ("ge_step_ring", _int, [ctypes.POINTER(_vp), _int, _int]),

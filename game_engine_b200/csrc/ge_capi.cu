@@ -42,6 +42,7 @@ struct ge_table {
     DevTable dev;
     int family, P, bucket;       // bucket: werewolf P8 (8/16/24/32), TTL PB (4/8/16/32)
     size_t rec_canon, rec_dev;   // canonical / device record bytes
+    uint16_t io_read[GE_MAX_PHASES], io_write[GE_MAX_PHASES];   // bytes a step that starts in phase i must read / write (ge_table_phase_io)
     uint32_t init_words[40];     // initial device record
     void (*spec_fn)(const DevTable, const StepArgs);   // build-time specialised step kernel for this exact table, or NULL
     void (*spec_ring_fn)(const DevTable, const StepArgs, const RingArgs);   // its ring-launch twin
@@ -89,6 +90,9 @@ struct ge_batch {
     ring_fn rfn[4];              // ring-launch twins (thread-per-session kernels only)
     int grid[4], occ[4];         // persistent grid size / occupancy limit (CTAs per SM) per kernel id
     uint64_t launches;
+    uint32_t* d_hmask;            // human seats per session (NULL = all bots) and their inputs for the next step
+    uint8_t* d_hchoice;
+    bool hchoice_set;             // inputs are pending: the next step launch consumes them
     int wire;                     // host-buffer record format (GE_WIRE_*); rec_wire = its record size
     size_t rec_wire;
     uint32_t* d_err;              // import validation: [0] rejected records, [1] max(~index) (k_import)
@@ -97,6 +101,7 @@ struct ge_batch {
 };
 
 static int restore_order(ge_batch* b, bool keep_records);
+static size_t human_stride(const ge_table* t);
 // Synchronise the batch's stream, then report what the last import found (the verdict travels back asynchronously,
 // so the asynchronous host-buffer call can stay asynchronous): a batch that was fed malformed records says so at
 // its next synchronising call.  The offending records were replaced by initial records on the device.
@@ -221,6 +226,37 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
         }
         t->dev.need[i] = need;
     }
+    // NECESSARY bytes per session of a step that starts in phase i (ge_table_phase_io): the columns `need` proves it
+    // must read, and the columns its effects can change.  Column 0 (header, is_alive, can_vote) moves both ways on
+    // every step.  This is what an ideal implementation of the same column layout moves; the §8(d) "algorithmic"
+    // figure 2·S assumes every byte of the record moves on every step.
+    for (int i = 0; i < h.n_phases; ++i) {
+        const ge_phase_t& ph = t->dev.phase[i];
+        if (ph.kind == KIND_TERMINAL) { t->io_read[i] = t->io_write[i] = 0; continue; }
+        const uint8_t need = t->dev.need[i];
+        bool en_assign = false, en_reset = false, en_any = false;
+        for (int b = 0; b < ph.n_branches; ++b) {
+            const int en = t->dev.phase[ph.br[b].next].entry_op;
+            en_assign |= en == EN_ASSIGN_ROLES; en_reset |= en == EN_NIGHT_RESET; en_any |= en != EN_NONE;
+        }
+        if (h.family == FAM_WEREWOLF) {
+            const int P8 = ((h.n_players + 7) / 8) * 8;
+            int rd = 16 + ((need & 1) ? 16 : 0) + ((need & 2) ? 16 : 0) + ((need & 4) ? P8 : 0);
+            int wr = 16;
+            const bool records = ph.kind == KIND_ACTION && ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE;
+            if (records || en_assign || en_reset) wr += 16;                        // submitted / revealed / eligible live in C1
+            if (en_assign) wr += 16;                                               // roles and team: C2
+            if (en_reset || (records && (ph.exit_op == EX_DAY_VOTE || h.n_players <= 8))) wr += P8;
+            else if (records) wr += ph.exit_op == EX_VOTE_KILL ? h.n_wolves : 1;   // one target byte per actor, stored directly
+            t->io_read[i] = (uint16_t)rd; t->io_write[i] = (uint16_t)wr;
+        } else {
+            const int bucket = h.n_players <= 4 ? 4 : h.n_players <= 8 ? 8 : h.n_players <= 16 ? 16 : 32;
+            const int S = 8 + 4 * bucket;
+            const bool touches = (ph.kind == KIND_ACTION && ph.exit_op != EX_NONE) || en_any;
+            t->io_read[i] = (uint16_t)((need & 4) ? S : 16);
+            t->io_write[i] = (uint16_t)(touches ? S : 16);
+        }
+    }
     if (t->dev.phase[0].id != 0) return fail(GE_ERR_ARG, "phase index 0 must be DSL phase 0");
     t->dev.nonterm = 0;
     for (int i = 0; i < h.n_phases; ++i)
@@ -282,6 +318,12 @@ extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
 extern "C" void ge_table_destroy(ge_table* t) { delete t; }
 extern "C" size_t ge_table_record_size(const ge_table* t) { return t ? t->rec_canon : 0; }
 extern "C" int ge_table_n_players(const ge_table* t) { return t ? t->P : 0; }
+extern "C" int ge_table_phase_io(const ge_table* t, int phase_index, uint32_t* read_bytes, uint32_t* write_bytes) {
+    if (!t || phase_index < 0 || phase_index >= t->dev.h.n_phases) return fail(GE_ERR_ARG, "bad arguments to ge_table_phase_io");
+    if (read_bytes) *read_bytes = t->io_read[phase_index];
+    if (write_bytes) *write_bytes = t->io_write[phase_index];
+    return GE_OK;
+}
 // dense wire records exist for werewolf tables up to 16 players (SPEC.md section 5b); everything else travels canonical
 static bool has_dense(const ge_table* t) { return t->family == FAM_WEREWOLF && t->bucket <= 16; }
 extern "C" size_t ge_table_wire_size(const ge_table* t, int wire) {
@@ -466,6 +508,7 @@ extern "C" void ge_batch_destroy(ge_batch* b) {
     cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
     cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin);
     cudaFree(b->d_err); cudaFreeHost(b->h_err); if (b->fence) cudaEventDestroy(b->fence);
+    cudaFree(b->d_hmask); cudaFree(b->d_hchoice);
     delete b;
 }
 
@@ -485,9 +528,53 @@ extern "C" int ge_batch_set_wire(ge_batch* b, int wire) {
 }
 extern "C" size_t ge_batch_wire_size(const ge_batch* b) { return b ? b->rec_wire : 0; }
 
+// Human seats (SPEC.md section 1, D3h).  host_masks[i] = seats of session i played by people (bit p-1 = player p);
+// NULL returns the batch to all bots.  Synchronous copy.
+extern "C" int ge_batch_set_human_seats(ge_batch* b, const uint32_t* host_masks) {
+    if (!b) return fail(GE_ERR_ARG, "batch is NULL");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    if (!host_masks) {
+        cudaFree(b->d_hmask); cudaFree(b->d_hchoice);
+        b->d_hmask = nullptr; b->d_hchoice = nullptr; b->hchoice_set = false;
+        return GE_OK;
+    }
+    if (b->kernel == GE_KERNEL_COOP) return fail(GE_ERR_UNSUPPORTED, "human seats are served by the thread-per-session kernels");
+    const uint32_t hi = b->tab->P >= 32 ? 0u : ~((1u << b->tab->P) - 1u);
+    for (uint64_t i = 0; i < b->n; ++i)
+        if (host_masks[i] & hi) return fail(GE_ERR_ARG, "human seat above the player count");
+    if (!b->d_hmask) {
+        cudaError_t e = cudaMalloc(&b->d_hmask, b->n * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_hchoice, b->n * human_stride(b->tab));
+        if (e == cudaSuccess) e = cudaMemset(b->d_hchoice, HUMAN_NONE, b->n * human_stride(b->tab));
+        if (e != cudaSuccess) {
+            cudaFree(b->d_hmask); cudaFree(b->d_hchoice);
+            b->d_hmask = nullptr; b->d_hchoice = nullptr;
+            return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_set_human_seats: ") + cudaGetErrorString(e));
+        }
+    }
+    CU(cudaMemcpy(b->d_hmask, host_masks, b->n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return GE_OK;
+}
+
+// Inputs of the human seats for the NEXT step launch: host_choices[i * stride + p] = what seat p+1 of session i chose
+// (a player id for PICK_PLAYER, 1..n for PICK_OPTION, anything for MARK; 0xFF = has not acted), stride =
+// ge_table_human_stride.  The next step launch consumes them; a session whose acting human seats are not all
+// answered stays in its phase (its history still grows by one entry).  Asynchronous on the batch's stream.
+extern "C" int ge_batch_set_human_choices(ge_batch* b, const uint8_t* host_choices) {
+    if (!b || !host_choices) return fail(GE_ERR_ARG, "bad arguments to ge_batch_set_human_choices");
+    if (!b->d_hmask) return fail(GE_ERR_ARG, "ge_batch_set_human_choices: the batch has no human seats (ge_batch_set_human_seats)");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(b->d_hchoice, host_choices, b->n * human_stride(b->tab), cudaMemcpyHostToDevice, b->stream));
+    b->hchoice_set = true;
+    return GE_OK;
+}
+extern "C" size_t ge_table_human_stride(const ge_table* t) { return t ? human_stride(t) : 0; }
+
 extern "C" int ge_batch_set_kernel(ge_batch* b, int kernel) {
     if (!b || kernel < GE_KERNEL_AUTO || kernel > GE_KERNEL_TPS_GENERIC) return fail(GE_ERR_ARG, "bad kernel id");
     kernel = kernel == GE_KERNEL_AUTO ? GE_KERNEL_TPS : kernel;
+    if (kernel == GE_KERNEL_COOP && b->d_hmask) return fail(GE_ERR_UNSUPPORTED, "human seats are served by the thread-per-session kernels");
     if (kernel == GE_KERNEL_COOP && b->kernel != GE_KERNEL_COOP) {
         // the lane-per-player kernels walk every slot in session order: undo any compaction first
         CU(cudaSetDevice(b->device));
@@ -632,6 +719,18 @@ static int enqueue_regroup(ge_batch* b, cudaStream_t st) {
     return GE_OK;
 }
 
+// bytes per session of the human-input rows: one byte per seat, rounded up to 8
+static size_t human_stride(const ge_table* t) { return (size_t)((t->P + 7) / 8) * 8; }
+
+// the inputs of the human seats are for ONE step: once a launch has consumed them they are cleared to "has not acted"
+static int consume_human_inputs(ge_batch* b, cudaStream_t st) {
+    if (b->hchoice_set) {
+        CU(cudaMemsetAsync(b->d_hchoice, HUMAN_NONE, b->n * human_stride(b->tab), st));
+        b->hchoice_set = false;
+    }
+    return GE_OK;
+}
+
 static void fill_common(const ge_batch* b, StepArgs& a, int steps_per_launch) {
     a.seed = b->seed; a.n_steps = steps_per_launch;
     for (int r = 0; r < 10; ++r) {
@@ -652,9 +751,12 @@ static void fill_slot(ge_batch* b, SlotArgs& a, bool count_live, bool regroup) {
     a.presence_override = b->next_override;
     b->next_override = 0;
     a.origin = b->compacted ? b->d_origin : nullptr;
+    a.human_mask = b->d_hmask; a.human_choice = b->d_hchoice; a.human_stride = (uint32_t)human_stride(b->tab);
 }
 
 static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaStream_t st) {
+    if (b->d_hmask && (b->kernel == GE_KERNEL_COOP || steps_per_launch > 1))
+        return fail(GE_ERR_UNSUPPORTED, "human seats are served by single-step launches of the thread-per-session kernels");
     const step_fn fn = b->fn[b->kernel];
     StepArgs a;
     fill_common(b, a, steps_per_launch);
@@ -672,6 +774,7 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
         fn<<<b->grid[b->kernel], 128, 0, st>>>(b->tab->dev, a);
         b->launches++;
         b->since_compact++;
+        if (b->hchoice_set) { const int rc = consume_human_inputs(b, st); if (rc != GE_OK) return rc; }
         if (regroup_after) {
             const int rc = enqueue_regroup(b, st);
             if (rc != GE_OK) return rc;
@@ -740,6 +843,8 @@ extern "C" int ge_step_ring(ge_batch** batches, int n_batches, int n_rounds) {
         }
         fn<<<(unsigned)(g < 1 ? 1 : g), 128, 0, b0->stream>>>(b0->tab->dev, c, ra);
         b0->launches++;                               // ONE launch for the whole ring
+        for (int i = 0; i < n_batches; ++i)
+            if (batches[i]->hchoice_set) { const int rc = consume_human_inputs(batches[i], b0->stream); if (rc != GE_OK) return rc; }
         if (n_due) {
             const int rc = enqueue_compaction(due, n_due, b0->stream);
             if (rc != GE_OK) return rc;

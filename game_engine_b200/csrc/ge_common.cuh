@@ -63,6 +63,11 @@ struct SlotArgs {
     // thread-per-session kernel also adds, per phase index, the sessions that entered it to rg[0..31] and the
     // number of tiles whose live sessions sit in more than one phase to rg[32].  NULL = not collected.
     uint32_t* rg;
+    // Human seats (SPEC.md section 1, D3h): human_mask[i] = seats of session i (original index) played by people,
+    // human_choice[i * stride + p] = the input of seat p+1 for THIS step (0xFF = has not acted).  NULL = all bots.
+    const uint32_t* human_mask;
+    const uint8_t* human_choice;
+    uint32_t human_stride;
     // Auto-reset (ge_capi.cu, k_autoreset_*): n_active[8] counts the device-side re-initialisations; the session
     // in slot i then has id first_sid + n_active[8] * sid_stride + origin[i].  0 = off.
     uint64_t sid_stride;
@@ -140,6 +145,24 @@ __device__ __forceinline__ int kth_set_bit(uint32_t m, uint32_t k) {
     { const uint32_t c = __popc(m & 0x3u); if (k >= c) { k -= c; pos += 2; m >>= 2; } }
     { const uint32_t c = m & 1u; if (k >= c) pos += 1; }
     return pos;
+}
+
+// What a step needs to know about the people at the table: which seats are human and where their inputs are.
+struct HumanIn {
+    uint32_t mask;
+    const uint8_t* choice;      // this session's row of SlotArgs::human_choice (valid when mask != 0)
+};
+enum { HUMAN_NONE = 0xFF };
+// The input of human seat p for an action (op, arg), or -1 when the step must wait for it (missing or not valid).
+// legal = the seat's legal target set for PICK_PLAYER (already without itself when the action excludes it).
+__device__ __forceinline__ int human_choice_of(const HumanIn& H, int p, int op, int arg, uint32_t legal) {
+    const uint32_t c = H.choice[p];
+    if (op == ACT_PICK_PLAYER) {
+        if (legal == 0) return 0;                                  // nobody to pick: same as a bot, never waits
+        return (c >= 1 && c <= 32 && ((legal >> (c - 1)) & 1u)) ? (int)c : -1;
+    }
+    if (op == ACT_PICK_OPTION) return (c >= 1 && c <= (uint32_t)arg) ? (int)c : -1;
+    return c != HUMAN_NONE ? 1 : -1;                               // MARK
 }
 
 __device__ __forceinline__ uint32_t all_mask(int P) { return P >= 32 ? 0xFFFFFFFFu : ((1u << P) - 1u); }

@@ -226,7 +226,7 @@ struct CtView {
 // phase index entered; `dirty` collects which column groups changed.
 template <int P8, class V>
 __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
-                                           const StepArgs& A, uint32_t& dirty) {
+                                           const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     // planes of the bit-sliced vote counters: enough for P votes; a build-time table whose phase is the wolves'
     // vote needs only enough for n_wolves votes
     constexpr int NPL_FULL = P8 <= 8 ? 4 : P8 <= 16 ? 5 : 6;
@@ -289,7 +289,23 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
         uint32_t chosen = 0, first_choice = 0;
         uint32_t nib = 0;                       // P8 <= 8: nibble-packed vote counters (one candidate per nibble)
         bool nib_used = false;
-        if (aop == ACT_PICK_PLAYER && !K.direct && (uint32_t)__popc(actors) * 3u > (uint32_t)P8) {
+        // ---- human seats among the actors (SPEC D3h): the step waits — history grows, nothing else changes — until
+        // every one of them has a valid input; bots draw on the step that completes the phase
+        const uint32_t hact = actors & H.mask;
+        if (hact) {
+            uint32_t rem_h = hact;
+            bool waiting = false;
+            while (rem_h) {
+                const int p = __ffs(rem_h) - 1;
+                rem_h &= rem_h - 1;
+                if (human_choice_of(H, p, aop, v.action_arg(), legal0 & ~(excl & (1u << p))) < 0) waiting = true;
+            }
+            if (waiting) {
+                s.h0 = (uint32_t)X | ((uint32_t)X << 8) | ((step0 + 1u) << 16);
+                return X;
+            }
+        }
+        if (aop == ACT_PICK_PLAYER && !K.direct && hact == 0 && (uint32_t)__popc(actors) * 3u > (uint32_t)P8) {
             // ---- many actors (day vote): one statically unrolled pass over the players.  Philox words, target
             // bytes and ranks are static; the pick is a lookup in a nibble LUT of the legal players' positions.
             const uint32_t n0 = __popc(legal0);
@@ -356,9 +372,16 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
             const bool is_first = rem == actors;
             rem &= rem - 1;
             const int blk = p >> 2;
+            uint32_t choice;
+            if ((hact >> p) & 1u) {                   // a person's input instead of a draw (validated above)
+                choice = (uint32_t)human_choice_of(H, p, aop, v.action_arg(), legal0 & ~(excl & (1u << p)));
+                if (aop == ACT_PICK_PLAYER && choice) { chosen |= 1u << (choice - 1u); if (tallying) tally.add(1u << (choice - 1u)); }
+                if (is_first) first_choice = choice;
+                if (record) { if (K.direct) pl_store<P8>(K, p, choice); else set_byte(s.tw, p, choice); }
+                continue;
+            }
             if (blk != cur_blk) { r4 = philox4x32_10(sid_lo, sid_hi, step0, (uint32_t)blk, A.rk); cur_blk = blk; }
             const uint32_t r = word_of(r4, p & 3);
-            uint32_t choice;
             if (aop == ACT_PICK_PLAYER) {
                 const uint32_t legal = legal0 & ~(excl & (1u << p));
                 const uint32_t n = __popc(legal);
@@ -467,32 +490,32 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
 // Generic entry: interpret the run-time table.  Returns the phase entered or -1 for a terminal session.
 template <int P8>
 __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
-                                      const StepArgs& A, uint32_t& dirty) {
+                                      const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     const int X = s.h0 & 0xFF;
     if (T.phase[X].kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
-    return w_step_body<P8>(RtView(T, X), X, s, F, K, sid_lo, sid_hi, A, dirty);
+    return w_step_body<P8>(RtView(T, X), X, s, F, K, sid_lo, sid_hi, A, dirty, H);
 }
 
 // Specialised entry: a warp-uniform switch over the phases of a build-time table.
 template <int P8, class Spec, int X>
 __device__ __forceinline__ int w_step_spec_case(WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
-                                                const StepArgs& A, uint32_t& dirty) {
+                                                const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
-    return w_step_body<P8>(CtView<Spec, X>{}, X, s, F, K, sid_lo, sid_hi, A, dirty);
+    return w_step_body<P8>(CtView<Spec, X>{}, X, s, F, K, sid_lo, sid_hi, A, dirty, H);
 }
 
 template <int P8, class Spec, int X = 0>
 __device__ __forceinline__ int w_step_spec(WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
-                                           const StepArgs& A, uint32_t& dirty) {
+                                           const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     if constexpr (X >= Spec::n_phases) {
         return -1;
     } else {
-        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X>(s, F, K, sid_lo, sid_hi, A, dirty);
-        return w_step_spec<P8, Spec, X + 1>(s, F, K, sid_lo, sid_hi, A, dirty);
+        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X>(s, F, K, sid_lo, sid_hi, A, dirty, H);
+        return w_step_spec<P8, Spec, X + 1>(s, F, K, sid_lo, sid_hi, A, dirty, H);
     }
 }
 
@@ -710,13 +733,18 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             bool live = in_range;
             const uint64_t sid = sid0 + org;
             uint32_t dirty = 0;
+            HumanIn H{0u, nullptr};
+            if (A.human_mask != nullptr && (need & 8) && in_range) {        // action phases only (they need the session id too)
+                H.mask = A.human_mask[org];
+                H.choice = A.human_choice + (uint64_t)org * A.human_stride;
+            }
             for (int it = 0; it < C.n_steps; ++it) {
                 int np = -1;
                 if (live) {
                     if constexpr (std::is_void<Spec>::value)
-                        np = w_step<P8>(T, s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty);
+                        np = w_step<P8>(T, s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
                     else
-                        np = w_step_spec<P8, Spec>(s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty);
+                        np = w_step_spec<P8, Spec>(s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
                     if (np < 0) live = false;
                 }
                 mixed += visits.add(s_visits, np, lane) > 1;
@@ -851,7 +879,7 @@ __device__ __forceinline__ uint32_t t_pred(const V& v, FieldFn field, int pi, ui
 // table; CtView<Spec, X>: a build-time table, every accessor a constant).  Returns the phase entered.
 template <int PB, class V>
 __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi,
-                                           const StepArgs& A, uint32_t& dirty) {
+                                           const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     const int P = v.n_players();
     const uint32_t ALL = all_mask(P);
     const uint32_t step0 = s.h0 >> 16;
@@ -901,6 +929,20 @@ __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s
         const int aop = v.action_op(), exo = v.exit_op();
         const uint32_t legal0 = aop == ACT_PICK_PLAYER ? t_pred(v, field, v.action_arg(), ALL) : 0u;
         uint32_t first_choice = 0; bool have_first = false;
+        const uint32_t hact = actors & H.mask;           // human seats among the actors (SPEC D3h)
+        if (hact) {
+            uint32_t rem_h = hact;
+            bool waiting = false;
+            while (rem_h) {
+                const int p = __ffs(rem_h) - 1;
+                rem_h &= rem_h - 1;
+                if (human_choice_of(H, p, aop, v.action_arg(), (v.action_flags() & 1) ? legal0 & ~(1u << p) : legal0) < 0) waiting = true;
+            }
+            if (waiting) {
+                s.h0 = (uint32_t)X | ((uint32_t)X << 8) | ((step0 + 1u) << 16);
+                return X;
+            }
+        }
 #pragma unroll
         for (int b = 0; b < PB / 4; ++b) {
             const uint32_t ab = (actors >> (4 * b)) & 0xFu;
@@ -912,7 +954,9 @@ __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s
                     const int p = 4 * b + j;
                     if ((ab >> j) & 1u) {
                         uint32_t choice;
-                        if (aop == ACT_PICK_PLAYER) {
+                        if ((hact >> p) & 1u) {
+                            choice = (uint32_t)human_choice_of(H, p, aop, v.action_arg(), (v.action_flags() & 1) ? legal0 & ~(1u << p) : legal0);
+                        } else if (aop == ACT_PICK_PLAYER) {
                             const uint32_t legal = (v.action_flags() & 1) ? legal0 & ~(1u << p) : legal0;
                             const uint32_t n = __popc(legal);
                             choice = n ? 1u + (uint32_t)kth_set_bit<PB>(legal, __umulhi(word_of(r4, j), n)) : 0u;
@@ -986,16 +1030,16 @@ __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s
 
 template <int PB>
 __device__ __forceinline__ int t_step(const DevTable& T, TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi,
-                                      const StepArgs& A, uint32_t& dirty) {
+                                      const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     const int X = s.h0 & 0xFF;
     if (T.phase[X].kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
-    return t_step_body<PB>(RtView(T, X), X, s, sid_lo, sid_hi, A, dirty);
+    return t_step_body<PB>(RtView(T, X), X, s, sid_lo, sid_hi, A, dirty, H);
 }
 
 template <int PB, class Spec, int X = 0>
-__device__ __forceinline__ int t_step_spec(TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi, const StepArgs& A, uint32_t& dirty) {
+__device__ __forceinline__ int t_step_spec(TState<PB>& s, uint32_t sid_lo, uint32_t sid_hi, const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     if constexpr (X >= Spec::n_phases) {
         return -1;
     } else {
@@ -1003,9 +1047,9 @@ __device__ __forceinline__ int t_step_spec(TState<PB>& s, uint32_t sid_lo, uint3
             if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
             dirty |= DIRTY_C0;
             if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
-            return t_step_body<PB>(CtView<Spec, X>{}, X, s, sid_lo, sid_hi, A, dirty);
+            return t_step_body<PB>(CtView<Spec, X>{}, X, s, sid_lo, sid_hi, A, dirty, H);
         }
-        return t_step_spec<PB, Spec, X + 1>(s, sid_lo, sid_hi, A, dirty);
+        return t_step_spec<PB, Spec, X + 1>(s, sid_lo, sid_hi, A, dirty, H);
     }
 }
 
@@ -1026,7 +1070,7 @@ __device__ __forceinline__ void t_tps_tiles(const DevTable& T, const StepArgs& C
     const uint32_t present_in = bc.present_in;
     const uint32_t need = C.n_steps > 1 ? 15u : need_of(T, present_in);
     const bool full = (need & 4u) != 0;
-    const bool use_origin = A.origin != nullptr && (need & 8u);
+    const bool use_origin = A.origin != nullptr && ((need & 8u) || A.human_mask != nullptr);
     const uint64_t n_act = bc.n_act;
     const uint64_t sid0 = bc.sid0;
     const uint64_t n_tiles_act = (n_act + 31) >> 5;
@@ -1126,13 +1170,18 @@ __device__ __forceinline__ void t_tps_tiles(const DevTable& T, const StepArgs& C
         bool live = in_range;
         const uint64_t sid = sid0 + org;
         uint32_t dirty = 0;
+        HumanIn H{0u, nullptr};
+        if (A.human_mask != nullptr && in_range) {
+            H.mask = A.human_mask[org];
+            H.choice = A.human_choice + org * A.human_stride;
+        }
         for (int it = 0; it < C.n_steps; ++it) {
             int np = -1;
             if (live) {
                 if constexpr (std::is_void<Spec>::value)
-                    np = t_step<PB>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty);
+                    np = t_step<PB>(T, s, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
                 else
-                    np = t_step_spec<PB, Spec>(s, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty);
+                    np = t_step_spec<PB, Spec>(s, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
                 if (np < 0) live = false;
             }
             visits.add(s_visits, np, lane);

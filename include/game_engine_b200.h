@@ -78,6 +78,11 @@ void ge_table_destroy(ge_table *t);
 /* canonical packed record size S in bytes (SPEC.md section 5) */
 size_t ge_table_record_size(const ge_table *t);
 int ge_table_n_players(const ge_table *t);
+/* Bytes per session that a step STARTING in phase `phase_index` must read and may write, given the column layout of
+ * the session store (column 0 = header + is_alive + can_vote always moves; the other column groups only when a
+ * predicate or effect of the phase touches them).  Weighted by the visit histogram of the statistics this gives the
+ * necessary DRAM traffic per session-phase-step, the honest lower bound next to the 2*S "algorithmic" figure. */
+int ge_table_phase_io(const ge_table *t, int phase_index, uint32_t *read_bytes, uint32_t *write_bytes);
 
 /* Allocate n_sessions sessions on `device` and initialise them from the DSL template.
  * Session i has id first_session_id + i.  Replaces initialize_player_states_from_dsl
@@ -138,6 +143,20 @@ int ge_batch_get_kernel(const ge_batch *b);
 size_t ge_table_wire_size(const ge_table *t, int wire);
 int ge_batch_set_wire(ge_batch *b, int wire);
 size_t ge_batch_wire_size(const ge_batch *b);
+
+/* Human seats (SPEC.md section 1, D3h).  Replaces: the reference excluding the human player from the bots' actions
+ * (agent/prompt/bot_behavior_system_prompt.txt:3,58-61), logging the person's action in the router
+ * (agent/tools/utils.py:310-358, called agent/game_agent_v2.py:324-332) and PhaseNode staying at the phase — while
+ * still appending to phase_history — until every target player has acted (game_agent_v2.py:1144-1170,1206-1215).
+ * host_masks[i]: seats of session i played by people (bit p-1 = player p); NULL = all bots again.
+ * host_choices[i * ge_table_human_stride(t) + p]: the input of seat p+1 for the NEXT step launch (a player id for
+ * PICK_PLAYER, 1..n for PICK_OPTION, anything for MARK; 0xFF = has not acted); the launch consumes them.  A session
+ * whose acting human seats are not all answered with a valid input STAYS: step + 1, prev = phase, nothing else
+ * changes, bots do not draw (they act on the step that completes the phase).  Thread-per-session kernels,
+ * single-step launches (ge_step, ge_step_many, ge_step_ring, ge_run_host with the fused mode off). */
+int ge_batch_set_human_seats(ge_batch *b, const uint32_t *host_masks);
+int ge_batch_set_human_choices(ge_batch *b, const uint8_t *host_choices);
+size_t ge_table_human_stride(const ge_table *t);
 
 /* Apply n_steps session-phase-steps to every non-terminal session: n_steps launches of the step
  * kernel on `cuda_stream` (NULL = the batch's own stream), each reading and writing the state once.

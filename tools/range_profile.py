@@ -35,8 +35,8 @@ def main():
     ap.add_argument("--ring", type=int, default=8)
     ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--ctas-per-sm", type=int, default=3)
-    ap.add_argument("--steps", type=int, default=56, help="profiled passes over the ring")
-    ap.add_argument("--warmup", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=0, help="profiled passes over the ring (0 = the longest possible game: every batch goes through one whole cycle)")
+    ap.add_argument("--warmup", type=int, default=-1, help="passes before the profiled region (-1 = one whole cycle)")
     ap.add_argument("--cap", type=int, default=0)
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--launch", default="streams", choices=["streams", "ring"], help="one launch per batch on --streams streams, or one ring launch per pass")
@@ -46,6 +46,8 @@ def main():
     torch.cuda.set_device(0)
     cg = compile_game(a.game, a.players)
     cap = a.cap or game_cap(cg.family, a.players, cg.table.max_revotes)
+    a.steps = a.steps or cap
+    a.warmup = cap if a.warmup < 0 else a.warmup
     tab = Table(cg)
     R, N = a.ring, a.sessions
     merged = a.launch == "ring"
