@@ -351,6 +351,25 @@ static step_fn pick_fn(const ge_table* t, int kernel) {
     return nullptr;
 }
 
+static step_fn pick_human_fn(const ge_table* t) {
+    if (t->family == FAM_WEREWOLF) {
+        switch (t->bucket) {
+        case 8: return (step_fn)k_step_w_tps_h<8>;
+        case 16: return (step_fn)k_step_w_tps_h<16>;
+        case 24: return (step_fn)k_step_w_tps_h<24>;
+        case 32: return (step_fn)k_step_w_tps_h<32>;
+        }
+    } else {
+        switch (t->bucket) {
+        case 4: return (step_fn)k_step_t_tps_h<4>;
+        case 8: return (step_fn)k_step_t_tps_h<8>;
+        case 16: return (step_fn)k_step_t_tps_h<16>;
+        case 32: return (step_fn)k_step_t_tps_h<32>;
+        }
+    }
+    return nullptr;
+}
+
 static ring_fn pick_ring_fn(const ge_table* t) {
     if (t->family == FAM_WEREWOLF) {
         switch (t->bucket) {
@@ -757,7 +776,8 @@ static void fill_slot(ge_batch* b, SlotArgs& a, bool count_live, bool regroup) {
 static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaStream_t st) {
     if (b->d_hmask && (b->kernel == GE_KERNEL_COOP || steps_per_launch > 1))
         return fail(GE_ERR_UNSUPPORTED, "human seats are served by single-step launches of the thread-per-session kernels");
-    const step_fn fn = b->fn[b->kernel];
+    // a batch with people at the table runs the run-time-table kernel that carries the human-seat path
+    const step_fn fn = b->d_hmask ? pick_human_fn(b->tab) : b->fn[b->kernel];
     StepArgs a;
     fill_common(b, a, steps_per_launch);
     // phase regrouping replaces the swap compaction (it also moves finished games behind the live ones)
@@ -808,8 +828,8 @@ extern "C" int ge_step_ring(ge_batch** batches, int n_batches, int n_rounds) {
         if (!b) return fail(GE_ERR_ARG, "NULL batch in ge_step_ring");
         if (b->tab != b0->tab || b->device != b0->device || b->seed != b0->seed || b->kernel != b0->kernel || b->stream != b0->stream)
             return fail(GE_ERR_ARG, "ge_step_ring: the batches must share table, device, seed, kernel and stream (ge_batch_set_stream)");
-        if (b->kernel == GE_KERNEL_COOP || b->regroup_every > 0 || b->sid_stride != 0)
-            return fail(GE_ERR_UNSUPPORTED, "ge_step_ring covers the thread-per-session kernels without phase regrouping / auto-reset");
+        if (b->kernel == GE_KERNEL_COOP || b->regroup_every > 0 || b->sid_stride != 0 || b->d_hmask)
+            return fail(GE_ERR_UNSUPPORTED, "ge_step_ring covers the thread-per-session kernels without phase regrouping / auto-reset / human seats");
         for (int j = 0; j < i; ++j)
             if (batches[j] == b) return fail(GE_ERR_ARG, "ge_step_ring: a batch appears twice");
     }
@@ -843,8 +863,6 @@ extern "C" int ge_step_ring(ge_batch** batches, int n_batches, int n_rounds) {
         }
         fn<<<(unsigned)(g < 1 ? 1 : g), 128, 0, b0->stream>>>(b0->tab->dev, c, ra);
         b0->launches++;                               // ONE launch for the whole ring
-        for (int i = 0; i < n_batches; ++i)
-            if (batches[i]->hchoice_set) { const int rc = consume_human_inputs(batches[i], b0->stream); if (rc != GE_OK) return rc; }
         if (n_due) {
             const int rc = enqueue_compaction(due, n_due, b0->stream);
             if (rc != GE_OK) return rc;

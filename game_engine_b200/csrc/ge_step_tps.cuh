@@ -610,7 +610,9 @@ struct WSmem {
 // drift from batch to batch independently.
 // Spec = void: interpret the run-time table T.  Spec = a generated ge::spec struct: the same table known at
 // build time (the host only selects this instantiation when the blobs are byte-identical).
-template <int P8, class Spec>
+// HUM: the batch has human seats (SPEC D3h); only the run-time-table instantiations k_step_*_tps_h carry that path, so
+// the all-bot kernels are exactly what they were.
+template <int P8, class Spec, bool HUM = false>
 __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C, const SlotArgs& A, BlockCounters& bc,
                                             uint32_t (*s_fields)[TPS_THREADS], uint8_t* s_lut_col) {
     constexpr int S = 48 + P8;
@@ -734,9 +736,11 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             const uint64_t sid = sid0 + org;
             uint32_t dirty = 0;
             HumanIn H{0u, nullptr};
-            if (A.human_mask != nullptr && (need & 8) && in_range) {        // action phases only (they need the session id too)
-                H.mask = A.human_mask[org];
-                H.choice = A.human_choice + (uint64_t)org * A.human_stride;
+            if constexpr (HUM) {
+                if (A.human_mask != nullptr && (need & 8) && in_range) {    // action phases only (they need the session id too)
+                    H.mask = A.human_mask[org];
+                    H.choice = A.human_choice + (uint64_t)org * A.human_stride;
+                }
             }
             for (int it = 0; it < C.n_steps; ++it) {
                 int np = -1;
@@ -791,6 +795,18 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
     w_tps_tiles<P8, Spec>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
+    __syncthreads();
+    w_tps_publish(A, sm.c[0]);
+}
+
+// the run-time-table kernel with the human-seat path (batches that have people at the table)
+template <int P8>
+__global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
+k_step_w_tps_h(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
+    __shared__ WSmem<P8, 1> sm;
+    counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
+    __syncthreads();
+    w_tps_tiles<P8, void, true>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
     __syncthreads();
     w_tps_publish(A, sm.c[0]);
 }
@@ -1057,7 +1073,7 @@ __device__ __forceinline__ int t_step_spec(TState<PB>& s, uint32_t sid_lo, uint3
 // step needs the player words at all (DevTable::need bit 2): launches whose sessions are all in header-only
 // phases move one column in and out instead of the whole record.
 // This CTA's share of one TTL batch (see w_tps_tiles: no block-wide barrier inside).
-template <int PB, class Spec>
+template <int PB, class Spec, bool HUM = false>
 __device__ __forceinline__ void t_tps_tiles(const DevTable& T, const StepArgs& C, const SlotArgs& A, BlockCounters& bc) {
     constexpr int S = 8 + 4 * PB;           // device record (PB even => S % 8 == 0)
     constexpr int NW = S / 4;
@@ -1070,7 +1086,7 @@ __device__ __forceinline__ void t_tps_tiles(const DevTable& T, const StepArgs& C
     const uint32_t present_in = bc.present_in;
     const uint32_t need = C.n_steps > 1 ? 15u : need_of(T, present_in);
     const bool full = (need & 4u) != 0;
-    const bool use_origin = A.origin != nullptr && ((need & 8u) || A.human_mask != nullptr);
+    const bool use_origin = A.origin != nullptr && ((need & 8u) || (HUM && A.human_mask != nullptr));
     const uint64_t n_act = bc.n_act;
     const uint64_t sid0 = bc.sid0;
     const uint64_t n_tiles_act = (n_act + 31) >> 5;
@@ -1171,9 +1187,11 @@ __device__ __forceinline__ void t_tps_tiles(const DevTable& T, const StepArgs& C
         const uint64_t sid = sid0 + org;
         uint32_t dirty = 0;
         HumanIn H{0u, nullptr};
-        if (A.human_mask != nullptr && in_range) {
-            H.mask = A.human_mask[org];
-            H.choice = A.human_choice + org * A.human_stride;
+        if constexpr (HUM) {
+            if (A.human_mask != nullptr && in_range) {
+                H.mask = A.human_mask[org];
+                H.choice = A.human_choice + org * A.human_stride;
+            }
         }
         for (int it = 0; it < C.n_steps; ++it) {
             int np = -1;
@@ -1220,6 +1238,17 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     counters_init(bc, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
     t_tps_tiles<PB, Spec>(T, A, A, bc[0]);
+    __syncthreads();
+    t_tps_publish(A, bc[0]);
+}
+
+template <int PB>
+__global__ void __launch_bounds__(128)
+k_step_t_tps_h(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
+    __shared__ BlockCounters bc[1];
+    counters_init(bc, 1, [&](int) -> const SlotArgs& { return A; });
+    __syncthreads();
+    t_tps_tiles<PB, void, true>(T, A, A, bc[0]);
     __syncthreads();
     t_tps_publish(A, bc[0]);
 }

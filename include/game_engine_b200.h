@@ -153,7 +153,8 @@ size_t ge_batch_wire_size(const ge_batch *b);
  * PICK_PLAYER, 1..n for PICK_OPTION, anything for MARK; 0xFF = has not acted); the launch consumes them.  A session
  * whose acting human seats are not all answered with a valid input STAYS: step + 1, prev = phase, nothing else
  * changes, bots do not draw (they act on the step that completes the phase).  Thread-per-session kernels,
- * single-step launches (ge_step, ge_step_many, ge_step_ring, ge_run_host with the fused mode off). */
+ * single-step launches (ge_step, ge_step_many, ge_run_host with the fused mode off); such a batch runs the
+ * run-time-table kernel. */
 int ge_batch_set_human_seats(ge_batch *b, const uint32_t *host_masks);
 int ge_batch_set_human_choices(ge_batch *b, const uint8_t *host_choices);
 size_t ge_table_human_stride(const ge_table *t);

@@ -260,8 +260,11 @@ static int plurality(int P, const uint8_t *is_actor, const uint8_t *choice, int 
     return best;
 }
 
-/* one step of one session; returns 1 if the step counted. visits may be NULL. */
-static int step_session(const tab_t *t, sess_t *s, uint64_t seed, uint64_t sid, uint64_t *visits) {
+/* one step of one session; returns 1 if the step counted. visits may be NULL.
+ * hmask / hchoice: human seats (SPEC D3h) and their inputs for this step (0xFF = has not acted); hmask 0 = all bots.
+ * Restates: human player excluded from bot actions (prompt/bot_behavior_system_prompt.txt:3,58-61), PhaseNode staying
+ * — and still appending history — until the target players have acted (agent/game_agent_v2.py:1144-1170,1206-1215). */
+static int step_session(const tab_t *t, sess_t *s, uint64_t seed, uint64_t sid, uint64_t *visits, uint32_t hmask, const uint8_t *hchoice) {
     const int P = t->P, X = s->phase;
     const uint8_t *ph = tab_phase(t, X);
     if (ph[1] == KIND_TERMINAL) return 0;
@@ -280,9 +283,36 @@ static int step_session(const tab_t *t, sess_t *s, uint64_t seed, uint64_t sid, 
         for (int p = 0; p < P; ++p) actor[p] = (uint8_t)pred_holds(t, s, ph[8], p);
         if (ph[2] == ACT_PICK_PLAYER)
             for (int q = 0; q < P; ++q) legal_ok[q] = (uint8_t)pred_holds(t, s, ph[3], q);
+        /* people first: is every acting human seat answered with something it may choose? */
+        int human_val[MAXP];
+        int waiting = 0;
+        for (int p = 0; p < P; ++p) {
+            human_val[p] = -1;
+            if (!actor[p] || !((hmask >> p) & 1u)) continue;
+            const int c = hchoice[p];
+            if (ph[2] == ACT_PICK_PLAYER) {
+                int n = 0, ok = 0;
+                for (int q = 0; q < P; ++q) {
+                    if ((ph[4] & 1) && q == p) continue;
+                    if (legal_ok[q]) { ++n; if (c == q + 1) ok = 1; }
+                }
+                human_val[p] = n == 0 ? 0 : ok ? c : -1;
+            } else if (ph[2] == ACT_PICK_OPTION) {
+                human_val[p] = (c >= 1 && c <= ph[3]) ? c : -1;
+            } else {
+                human_val[p] = c != 0xFF ? 1 : -1;
+            }
+            if (human_val[p] < 0) waiting = 1;
+        }
+        if (waiting) {                        /* the step stays: history grows, nothing else changes */
+            s->prev = X; s->step = (step0 + 1) & 0xFFFF;
+            if (visits) visits[X]++;
+            return 1;
+        }
         for (int p = 0; p < P; ++p) {
             if (!actor[p]) continue;
             if (first_actor < 0) first_actor = p;
+            if ((hmask >> p) & 1u) { choice[p] = (uint8_t)human_val[p]; continue; }
             uint32_t r = draw(seed, sid, (uint32_t)step0, 0, p);
             if (ph[2] == ACT_PICK_PLAYER) {
                 int legal[MAXP], n = 0;
@@ -432,11 +462,16 @@ int ge_cpu_init(const uint8_t *blob, size_t nb, uint8_t *records, uint64_t n_ses
 }
 
 /* stats (u64[GE_STATS_LEN], may be NULL): [0] += counted steps, [260+i] += visits of phase index i */
-int ge_cpu_step(const uint8_t *blob, size_t nb, uint8_t *records, uint64_t n_sessions, uint64_t first_sid,
-                uint64_t seed, int n_steps, uint64_t *stats, int n_threads) {
+/* hmask[i] / hchoice[i * hstride + p]: human seats of session i and their inputs for the FIRST of the n_steps steps
+ * (consumed by it, like the library's ge_batch_set_human_choices); both NULL = all bots. */
+int ge_cpu_step_h(const uint8_t *blob, size_t nb, uint8_t *records, uint64_t n_sessions, uint64_t first_sid,
+                  uint64_t seed, int n_steps, uint64_t *stats, int n_threads,
+                  const uint32_t *hmask, const uint8_t *hchoice, size_t hstride) {
     tab_t t;
     if (tab_open(&t, blob, nb)) return -1;
     const size_t S = rec_size(&t);
+    uint8_t none[MAXP];
+    memset(none, 0xFF, sizeof none);
     uint64_t counted = 0, visits[32] = {0};
 #ifdef _OPENMP
     if (n_threads > 0) omp_set_num_threads(n_threads);
@@ -448,7 +483,9 @@ int ge_cpu_step(const uint8_t *blob, size_t nb, uint8_t *records, uint64_t n_ses
             sess_t s;
             if (tab_phase(&t, records[(size_t)i * S])[1] == KIND_TERMINAL) continue;   /* frozen (SPEC D16) */
             unpack(&t, records + (size_t)i * S, &s);
-            for (int k = 0; k < n_steps; ++k) my_counted += (uint64_t)step_session(&t, &s, seed, first_sid + (uint64_t)i, my_visits);
+            for (int k = 0; k < n_steps; ++k)
+                my_counted += (uint64_t)step_session(&t, &s, seed, first_sid + (uint64_t)i, my_visits, hmask ? hmask[i] : 0u,
+                                                     (hchoice && k == 0) ? hchoice + (size_t)i * hstride : none);
             pack(&t, &s, records + (size_t)i * S);
         }
 #pragma omp critical
@@ -460,12 +497,19 @@ int ge_cpu_step(const uint8_t *blob, size_t nb, uint8_t *records, uint64_t n_ses
         sess_t s;
         if (tab_phase(&t, records[i * S])[1] == KIND_TERMINAL) continue;
         unpack(&t, records + i * S, &s);
-        for (int k = 0; k < n_steps; ++k) counted += (uint64_t)step_session(&t, &s, seed, first_sid + i, visits);
+        for (int k = 0; k < n_steps; ++k)
+            counted += (uint64_t)step_session(&t, &s, seed, first_sid + i, visits, hmask ? hmask[i] : 0u,
+                                              (hchoice && k == 0) ? hchoice + (size_t)i * hstride : none);
         pack(&t, &s, records + i * S);
     }
 #endif
     if (stats) { stats[0] += counted; for (int j = 0; j < 32; ++j) stats[260 + j] += visits[j]; }
     return 0;
+}
+
+int ge_cpu_step(const uint8_t *blob, size_t nb, uint8_t *records, uint64_t n_sessions, uint64_t first_sid,
+                uint64_t seed, int n_steps, uint64_t *stats, int n_threads) {
+    return ge_cpu_step_h(blob, nb, records, n_sessions, first_sid, seed, n_steps, stats, n_threads, NULL, NULL, 0);
 }
 
 /* final-state statistics: overwrites stats[1..259] and stats[292..547] (SPEC section 6) */

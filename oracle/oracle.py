@@ -35,6 +35,7 @@ class Oracle:
         L.ge_cpu_record_size.restype = sz
         L.ge_cpu_init.argtypes = [u8p, sz, u8p, u64]
         L.ge_cpu_step.argtypes = [u8p, sz, u8p, u64, u64, u64, ctypes.c_int, u8p, ctypes.c_int]
+        L.ge_cpu_step_h.argtypes = [u8p, sz, u8p, u64, u64, u64, ctypes.c_int, u8p, ctypes.c_int, u8p, u8p, sz]
         L.ge_cpu_stats_final.argtypes = [u8p, sz, u8p, u64, u8p]
         L.ge_cpu_peek_choices.argtypes = [u8p, sz, u8p, u64, u64, u8p]
         L.ge_cpu_philox.argtypes = [u8p, u8p, u8p]
@@ -64,6 +65,22 @@ class Oracle:
         rc = self.lib.ge_cpu_step(self._bp, len(self.blob), rec.ctypes.data, rec.shape[0], first_sid, seed, n_steps, sp, threads)
         if rc != 0:
             raise RuntimeError("ge_cpu_step failed")
+
+    def step_humans(self, rec: np.ndarray, first_sid: int, seed: int, masks: np.ndarray, choices: np.ndarray | None,
+                    n_steps: int = 1, stats: np.ndarray | None = None) -> None:
+        """step() with human seats (SPEC D3h): masks uint32[n]; choices uint8[n, stride] (0xFF = has not acted) apply
+        to the first of the n_steps steps; choices None = nobody has acted."""
+        assert rec.dtype == np.uint8 and rec.flags.c_contiguous and rec.shape[1] == self.record_size
+        m = np.ascontiguousarray(masks, dtype=np.uint32)
+        assert m.size == rec.shape[0]
+        if choices is None:
+            choices = np.full((rec.shape[0], 32), 0xFF, dtype=np.uint8)
+        c = np.ascontiguousarray(choices, dtype=np.uint8).reshape(rec.shape[0], -1)
+        sp = stats.ctypes.data if stats is not None else None
+        rc = self.lib.ge_cpu_step_h(self._bp, len(self.blob), rec.ctypes.data, rec.shape[0], first_sid, seed, n_steps, sp, 0,
+                                    m.ctypes.data, c.ctypes.data, c.shape[1])
+        if rc != 0:
+            raise RuntimeError("ge_cpu_step_h failed")
 
     def stats_final(self, rec: np.ndarray, stats: np.ndarray) -> None:
         self.lib.ge_cpu_stats_final(self._bp, len(self.blob), rec.ctypes.data, rec.shape[0], stats.ctypes.data)
