@@ -14,6 +14,7 @@ converts representations and writes the step's results in the reference's string
 from __future__ import annotations
 
 import datetime as _dt
+import re as _re
 import time as _time
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -29,6 +30,52 @@ NOTE_EMOJI = {
 }
 NO_TARGET_TEXT = "had no legal target"
 TTL_STATEMENTS = ("I once met a celebrity.", "I can speak four languages.", "I've never broken a bone.")
+
+
+HUMAN_NONE = 0xFF
+_CONTROL_MESSAGES = ("continue", "start game", "start game.")
+
+
+def last_human_text(messages) -> Optional[str]:
+    """Content of the last message when it is a HumanMessage (langchain object, or the dict form {"type": "human"} /
+    {"role": "user"}), else None — the test the reference's router applies (agent/tools/utils.py:330-331)."""
+    if not messages:
+        return None
+    m = messages[-1]
+    if isinstance(m, dict):
+        kind = str(m.get("type") or m.get("role") or "").lower()
+        return str(m.get("content", "")) if kind in ("human", "user") else None
+    if type(m).__name__ == "HumanMessage":
+        return str(getattr(m, "content", ""))
+    return None
+
+
+def is_action_message(text: Optional[str]) -> bool:
+    """The reference logs a human message as a game action unless it is chat or a generic control message
+    (agent/tools/utils.py:334-337)."""
+    if text is None:
+        return False
+    c = str(text).lower().strip()
+    return "in game chat:" not in c and "to bot" not in c and c not in _CONTROL_MESSAGES
+
+
+def parse_choice(text: str, names: List[str]) -> Optional[int]:
+    """The number a person's action message chooses: the UI's `Player 1 voted "<option>" in voting <id>`
+    (reference src/app/page.tsx:302-305; the option is a player label, a player name or an option number), or free
+    text naming `Player N` / `statement N` / `option N` / a bare number.  None when nothing can be read."""
+    t = str(text)
+    m = _re.search(r'voted\s+"([^"]*)"', t)
+    if m:
+        t = m.group(1)
+    else:                                       # "Player 1: protect Player 4" — the leading label is the speaker, not the choice
+        m2 = _re.match(r"^\s*Player\s+\d+\b\s*[:,\-]?\s*(\S.*)$", t, _re.IGNORECASE | _re.DOTALL)
+        if m2:
+            t = m2.group(1)
+    for i, nm in enumerate(names):
+        if nm and not _re.fullmatch(r"Player \d+", nm) and nm.lower() in t.lower():
+            return i + 1
+    m = _re.search(r"(?:Player|statement|option)\s*#?\s*(\d+)", t, _re.IGNORECASE) or _re.search(r"\b(\d+)\b", t)
+    return int(m.group(1)) if m else None
 
 
 def format_note(note_type: str, content: str) -> str:
@@ -254,9 +301,10 @@ class SessionCodec:
 
     # ------------------------------------------------------------------ one step's worth of reference-format updates
     def step_update(self, state: Dict[str, Any], before: np.ndarray, after: np.ndarray,
-                    now_ms: Optional[int] = None, now_iso: Optional[str] = None) -> Dict[str, Any]:
+                    now_ms: Optional[int] = None, now_iso: Optional[str] = None, human_mask: int = 0) -> Dict[str, Any]:
         """The union of the update dicts of BotBehaviorNode + PhaseNode + RefereeNode for the step that took the
-        session from record `before` to record `after` (both canonical)."""
+        session from record `before` to record `after` (both canonical).  `human_mask`: seats played by people — their
+        actions are logged by the router, not here, and a step that waited for one of them only grows the history."""
         cg, P = self.cg, self.P
         b, a = Record(cg, before), Record(cg, after)
         now_ms = int(_time.time() * 1000) if now_ms is None else now_ms
@@ -271,9 +319,13 @@ class SessionCodec:
                     "current_phase_name": cg.phase_names[a.phase], "phase_history": history, "game_notes": notes}
         X, Y = b.phase, a.phase
         phX = cg.table.phases[X]
+        if self.stayed(before, after, human_mask):         # PhaseNode appends to the history even when it stays (:1206-1215)
+            history.append({"phase_id": cg.phase_ids[Y], "phase_name": cg.phase_names[Y], "timestamp": now_iso})
+            return {"player_states": ps_old, "playerActions": actions, "current_phase_id": cg.phase_ids[Y],
+                    "current_phase_name": cg.phase_names[Y], "phase_history": history, "game_notes": notes}
         # ---- BotBehaviorNode part: the actions the bots took in phase X
         if b.step > 0 and phX.kind == T.KIND_ACTION:
-            actors = b.eval_pred(cg.table.preds[phX.actor_pred])
+            actors = b.eval_pred(cg.table.preds[phX.actor_pred]) & ~human_mask
             for p in _bits(actors, P):
                 if cg.family == T.FAMILY_WEREWOLF:
                     choice = a.target[p]
@@ -300,6 +352,124 @@ class SessionCodec:
         name = cg.phase_names[Y] if b.step > 0 else state.get("current_phase_name", "")
         return {"player_states": new_ps, "playerActions": actions, "current_phase_id": cg.phase_ids[Y],
                 "current_phase_name": name, "phase_history": history, "game_notes": notes}
+
+    # ------------------------------------------------------------------ people at the table (SPEC.md D3h)
+    def log_human_action(self, state: Dict[str, Any], text: str, player_id: str = "1", now_ms: Optional[int] = None) -> Dict[str, Any]:
+        """What the reference's router does with a person's action message before the bots run
+        (process_human_action_if_needed, agent/tools/utils.py:310-358, called game_agent_v2.py:324-332): the raw text,
+        truncated to 200 characters, is appended to playerActions[player_id] — under the name of PHASE 0, because the
+        router passes camelCase keys the state does not have (`currentPhaseId`, game_agent_v2.py:327-328).  Returns the
+        new playerActions; for graphs that replace InitialRouterNode as well."""
+        actions = {pid: {"name": v.get("name"), "actions": dict(v.get("actions", {}))} for pid, v in (state.get("playerActions") or {}).items()}
+        if not is_action_message(text):
+            return actions
+        name = "Player %s" % player_id          # the router also looks under `playerStates`, which the state does not have
+        for p in (state.get("roomSession") or {}).get("players", []):
+            if str(p.get("gamePlayerId", "")) == str(player_id):
+                name = p.get("name", name)
+        slot = actions.setdefault(str(player_id), {"name": name, "actions": {}})
+        ids = [int(v["id"]) for v in slot["actions"].values() if isinstance(v, dict) and str(v.get("id", "")).isdigit()]
+        aid = str(max(ids, default=0) + 1)
+        slot["name"] = name
+        slot["actions"][aid] = {"action": str(text)[:200], "timestamp": int(_time.time() * 1000) if now_ms is None else now_ms,
+                                "phase": self.cg.phase_names[0], "id": aid}
+        return actions
+
+    def human_inputs(self, state: Dict[str, Any], human_seats=(1,)) -> Tuple[int, np.ndarray]:
+        """(human_mask, inputs row) of this graph run: every human seat's input is what the last human message
+        chooses, when that message is an action (the reference has one person, player 1, whose message arrives in
+        the run that logs it); 0xFF otherwise."""
+        P = self.P
+        mask = 0
+        row = np.full(((P + 7) // 8) * 8, HUMAN_NONE, dtype=np.uint8)
+        ps = state.get("player_states") or {}
+        names = [ps.get(str(p + 1), {}).get("name", "") for p in range(P)]
+        text = last_human_text(state.get("messages"))
+        phase = self.cg.table.phases[self.cg.index_of(state.get("current_phase_id", 0))]
+        for seat in human_seats:
+            if not (1 <= int(seat) <= P):
+                continue
+            mask |= 1 << (int(seat) - 1)
+            if is_action_message(text):
+                # a MARK action ("submit your statements") is answered by any action message; the others by the number it names
+                c = 1 if phase.action_op == T.ACT_MARK else parse_choice(text, names)
+                if c is not None and 0 <= c < HUMAN_NONE:
+                    row[int(seat) - 1] = c
+        return mask, row
+
+    def stayed(self, before: np.ndarray, after: np.ndarray, human_mask: int) -> bool:
+        """True when the step b -> a was a wait for a person (SPEC D3h): same phase, history one longer, nothing else."""
+        if not human_mask:
+            return False
+        b, a = Record(self.cg, before), Record(self.cg, after)
+        phX = self.cg.table.phases[b.phase]
+        if b.step == 0 or a.step != b.step + 1 or a.phase != b.phase or a.prev != b.phase or phX.kind != T.KIND_ACTION:
+            return False
+        if not (b.eval_pred(self.cg.table.preds[phX.actor_pred]) & human_mask):
+            return False
+        return bool(np.array_equal(before[4:], after[4:]))
+
+    # ------------------------------------------------------------------ the step as the reference's tool calls
+    def tool_calls_for(self, state: Dict[str, Any], before: np.ndarray, after: np.ndarray, human_mask: int = 0) -> Dict[str, List[dict]]:
+        """The step b -> a as the tool-call lists the reference's three hot-path nodes apply, in the order they apply
+        them (agent/tools/backend_tools.py:10-157; applied in list order, game_agent_v2.py:589-605, 1124-1143, 762-786):
+
+            {"BotBehaviorNode": [update_player_actions...], "PhaseNode": [set_next_phase], "RefereeNode": [update_player_state..., add_game_note...]}
+
+        Feeding these lists to the reference's own nodes through a pass-through chat model reproduces, through the
+        reference's `_execute_*` code, the state `step_update` builds directly (tests/test_tool_calls.py)."""
+        cg, P = self.cg, self.P
+        b, a = Record(cg, before), Record(cg, after)
+        out: Dict[str, List[dict]] = {"BotBehaviorNode": [], "PhaseNode": [], "RefereeNode": []}
+        if a.step == b.step:                                        # terminal session: PhaseNode would not transition
+            out["PhaseNode"].append({"name": "set_next_phase", "id": "ph", "args": {
+                "transition": False, "next_phase_id": cg.phase_ids[a.phase], "transition_reason": "terminal"}})
+            return out
+        if b.step == 0:                                             # phase-0 first visit: no LLM is consulted at all
+            return out
+        X, Y = b.phase, a.phase
+        phX = cg.table.phases[X]
+        wait = self.stayed(before, after, human_mask)
+        ps_old = state.get("player_states") or {}
+        names = [ps_old.get(str(p + 1), {}).get("name", "Player %d" % (p + 1)) for p in range(P)]
+        actors = _bits(b.eval_pred(cg.table.preds[phX.actor_pred]), P) if phX.kind == T.KIND_ACTION else []
+        if not wait:
+            for p in actors:
+                if (human_mask >> p) & 1:
+                    continue                                        # the router logged the person's own message
+                out["BotBehaviorNode"].append({"name": "update_player_actions", "id": "bot-%d-%d" % (b.step, p + 1), "args": {
+                    "player_id": str(p + 1), "actions": self.action_text(X, self._choice_of(phX, a, p)), "phase": cg.phase_names[X]}})
+        out["PhaseNode"].append({"name": "set_next_phase", "id": "ph", "args": {
+            "transition": not wait, "next_phase_id": cg.phase_ids[Y],
+            "transition_reason": "waiting for the human player's action" if wait else "phase complete"}})
+        if wait:
+            return out
+        # RefereeNode: every field of every player that differs, plus the fields the effects write even when the value
+        # stays the same (they create keys the template does not declare), then the notes
+        new_ps = self.player_states_from_record(a, names, prev_ps=ps_old, written=self.written_fields(b, a))
+        n = 0
+        for p in range(P):
+            pid = str(p + 1)
+            old, new = ps_old.get(pid, {}), new_ps[pid]
+            for k, v in new.items():
+                if k == "name":
+                    continue
+                if k not in old or old[k] != v:
+                    out["RefereeNode"].append({"name": "update_player_state", "id": "r%d" % n, "args": {"player_id": pid, "state_name": k, "state_value": v}})
+                    n += 1
+        for t_, c_ in self.notes_for(b, a, names):
+            out["RefereeNode"].append({"name": "add_game_note", "id": "n%d" % n, "args": {"note_type": t_, "content": c_}})
+            n += 1
+        return out
+
+    def _choice_of(self, phX, a: Record, p: int) -> int:
+        if self.cg.family == T.FAMILY_WEREWOLF:
+            return a.target[p]
+        if phX.exit_op == T.EX_T_LIE:
+            return a.lie_index
+        if phX.exit_op == T.EX_T_VOTES:
+            return a.vote[p]
+        return 1
 
     def written_fields(self, b: Record, a: Record) -> Dict[int, set]:
         """{player index: canonical fields the referee writes in the step b -> a} (SPEC.md section 4 effects)."""

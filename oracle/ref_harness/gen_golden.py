@@ -34,7 +34,33 @@ CASES = [
 ]
 
 
+# Games with a PERSON in seat 1 (SPEC D3h): the reference's router logs their messages, its PhaseNode waits for them.
+# Fixtures go to tests/golden/human/ and carry what the person typed before every step.
+HUMAN_CASES = [
+    ("werewolf-(mafia)", 6, 5, 77), ("werewolf-(mafia)", 8, 2, 5), ("werewolf-(mafia)", 16, 8, 1), ("werewolf-revote", 8, 46, 3010),
+    ("werewolf-draft", 7, 4, 4), ("two-truths-and-a-lie", 4, 3, 9), ("two-truths-and-a-lie", 6, 1, 2),
+]
+
+
+def main_human():
+    out_dir = os.path.join(ROOT, "tests", "golden", "human")
+    os.makedirs(out_dir, exist_ok=True)
+    for game, P, seed, sid in HUMAN_CASES:
+        name = "%s_p%d_seed%d_sid%d.json.gz" % (game.replace("(", "").replace(")", ""), P, seed, sid)
+        if os.environ.get("GOLDEN_ONLY_MISSING") and os.path.exists(os.path.join(out_dir, name)):
+            continue
+        trace = run_session(game, P, seed, sid, human=True)
+        msgs = trace[0].pop("_human_messages")
+        blob = json.dumps({"game": game, "players": P, "seed": seed, "sid": sid, "human_seats": [1], "human_messages": msgs, "trace": trace},
+                          ensure_ascii=False, sort_keys=True, separators=(",", ":")).encode("utf-8")
+        with gzip.GzipFile(os.path.join(out_dir, name), "wb", mtime=0) as f:
+            f.write(blob)
+        print("human/%-54s %3d steps  %6d bytes" % (name, len(trace) - 1, os.path.getsize(os.path.join(out_dir, name))))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--human":
+        return main_human()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else None          # optional: regenerate one game's fixtures

@@ -67,9 +67,20 @@ def plurality(choices: List[int]) -> int:
     return max(set(votes), key=lambda c: (votes.count(c), -c))
 
 
+def human_number(text: str):
+    """The number a person's message chooses (the UI's `Player 1 voted "<option>" in voting <id>`, reference
+    src/app/page.tsx:302-305, or `... Player N` / `... statement N`), or None.  Written independently of
+    game_engine_b200.adapter.parse_choice: the fixtures only use messages both read the same way."""
+    m = re.search(r'voted\s+"([^"]*)"', text)
+    body = m.group(1) if m else re.sub(r"^\s*Player\s+\d+\s*[:,-]?\s*", "", text, count=1)
+    m = re.search(r"(\d+)", body)
+    return int(m.group(1)) if m else None
+
+
 class StubChatModel:
-    def __init__(self, rules: dict, seed: int, sid: int):
+    def __init__(self, rules: dict, seed: int, sid: int, human_seats=()):
         self.rules, self.seed, self.sid = rules, seed, sid
+        self.human_seats = tuple(int(x) for x in human_seats)       # SPEC D3h; the reference's room: (1,)
         self.state: Dict[str, Any] = {}
         self.calls = 0
         # rules `fields:` maps a DSL field name to the canonical one; the referee writes / reads the DSL's names
@@ -107,6 +118,43 @@ class StubChatModel:
         cond = cc["target_players"]["condition"]
         return [i for i in self._ids() if holds(cond, self._ps(i))]
 
+    # ------------------------------------------------------------------ people at the table (SPEC D3h)
+    def _human_text(self):
+        msgs = self.state.get("messages") or []
+        if not msgs or type(msgs[-1]).__name__ != "HumanMessage":
+            return None
+        c = str(msgs[-1].content)
+        low = c.lower().strip()
+        if "in game chat:" in low or "to bot" in low or low in ("continue", "start game", "start game."):
+            return None
+        return c
+
+    def _legal(self, act: dict, i: int) -> List[int]:
+        return [q for q in self._ids() if holds(act["legal"], self._ps(q)) and not (act.get("exclude_self") and q == i)]
+
+    def _human_answer(self, i: int, act: dict):
+        """What human seat i chooses in this graph run, or None when the phase has to wait for it."""
+        if act["op"] == "PICK_PLAYER" and not self._legal(act, i):
+            return 0
+        text = self._human_text()
+        if text is None:
+            return None
+        if act["op"] == "MARK":
+            return 1
+        c = human_number(text)
+        if c is None:
+            return None
+        if act["op"] == "PICK_PLAYER":
+            return c if c in self._legal(act, i) else None
+        return c if 1 <= c <= int(act["options"]) else None
+
+    def _waiting(self, X) -> bool:
+        """Phase X (a player_action phase) still lacks the answer of a human seat among its actors."""
+        act = self._prules(X).get("action")
+        if not act or not self.human_seats:
+            return False
+        return any(self._human_answer(i, act) is None for i in self._actors(self._phase(X)) if i in self.human_seats)
+
     # ------------------------------------------------------------------ BotBehaviorNode
     def bots(self) -> List[dict]:
         st = self.state
@@ -116,8 +164,12 @@ class StubChatModel:
         act = self._prules(X).get("action")
         if step == 0 or not act:
             return []
+        if self._waiting(X):                      # bots act on the run that completes the phase
+            return []
         calls = []
         for i in self._actors(phase):
+            if i in self.human_seats:             # "Player ID 1 (human) NEVER generates actions" (bot prompt :3)
+                continue
             r = draw(self.seed, self.sid, step, 0, i - 1)
             if act["op"] == "PICK_PLAYER":
                 legal = [q for q in self._ids() if holds(act["legal"], self._ps(q)) and not (act.get("exclude_self") and q == i)]
@@ -139,6 +191,8 @@ class StubChatModel:
         nxt = self._phase(X).get("next_phase")
         if nxt is None:
             return [{"name": "set_next_phase", "args": {"transition": False, "next_phase_id": X, "transition_reason": "terminal"}, "id": "ph"}]
+        if (st.get("phase_history") or []) and self._waiting(X):
+            return [{"name": "set_next_phase", "args": {"transition": False, "next_phase_id": X, "transition_reason": "waiting for the human player's action"}, "id": "ph"}]
         if "id" in nxt and not isinstance(nxt["id"], dict):
             target, why = nxt["id"], "phase complete"
         else:
@@ -180,6 +234,8 @@ class StubChatModel:
             return []
         X, Y = hist[-2]["phase_id"], st.get("current_phase_id")
         phX = self._phase(X)
+        if X == Y and self._waiting(X):           # PhaseNode stayed: nothing to apply
+            return []
         step = len(hist) - 1                      # step count at the start of this step
         ids = self._ids()
         calls: List[dict] = []
@@ -187,7 +243,8 @@ class StubChatModel:
         note = lambda t, c: calls.append({"name": "add_game_note", "args": {"note_type": t, "content": c}, "id": "n%d" % len(calls)})
         ex, en = self._prules(X).get("exit"), self._prules(Y).get("entry")
         actors = self._actors(phX)
-        choice = {i: self._latest_choice(i, phX["name"]) for i in actors}
+        act_x = self._prules(X).get("action")
+        choice = {i: (self._human_answer(i, act_x) or 0) if i in self.human_seats else self._latest_choice(i, phX["name"]) for i in actors}
         roles = self.rules.get("roles") or {}
         wolf_team, village = self.rules.get("wolf_team"), self.rules.get("village_team")
         dead: List[int] = []

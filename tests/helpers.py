@@ -70,3 +70,35 @@ def pick(paths, *needles):
         assert len(hit) == 1, (nd, hit)
         out.append(hit[0])
     return out
+
+
+def play_with_human(cg, messages, step_fn, human_seats=(1,)):
+    """Replays a game with a person in the given seats.  messages[k] = what they typed before step k + 1.
+    step_fn(record_before, human_mask, inputs_row) -> record_after does the stepping (Oracle B or the GPU).
+    Per step: the router's logging of the message (adapter.log_human_action), the inputs the adapter reads from it,
+    the step, and the adapter's update.  Returns (records, dict trace) like replay_records."""
+    from game_engine_b200.adapter import SessionCodec
+    codec = SessionCodec(cg)
+    state = codec.initial_state()
+    rec = codec.record_from_state(state)
+    records, trace = [rec.copy()], [normalise(state)]
+    for text in messages:
+        state["messages"] = [{"type": "human", "content": text}]
+        state["playerActions"] = codec.log_human_action(state, text, now_ms=0)
+        mask, row = codec.human_inputs(state, human_seats)
+        before = codec.record_from_state(state)
+        after = step_fn(before, mask, row)
+        state.update(codec.step_update(state, before, after, now_ms=0, now_iso="", human_mask=mask))
+        records.append(after.copy())
+        trace.append(normalise(state))
+    return records, trace
+
+
+def oracle_step_fn(o, sid, seed):
+    import numpy as np
+
+    def step(before, mask, row):
+        rec = np.array(before.reshape(1, -1), dtype=np.uint8, copy=True)
+        o.step_humans(rec, sid, seed, np.array([mask], dtype=np.uint32), row.reshape(1, -1))
+        return rec[0]
+    return step
