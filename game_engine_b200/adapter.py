@@ -118,6 +118,11 @@ class Record:
         ALL = (1 << P) - 1
         if f == T.F_ALL:
             return ALL
+        k = f - T.cmp_field_id(self.cg.family, 0)             # comparison fields (numeric conditions)
+        if 0 <= k < len(self.cg.table.cmps) and f < T.F_ALL:
+            vf, op, const = self.cg.table.cmps[k]
+            vals = self.target if self.cg.family == T.FAMILY_WEREWOLF else (self.score, self.rounds, self.vote)[vf]
+            return sum(1 << p for p in range(P) if T.cmp_holds(op, vals[p], const))
         if self.cg.family == T.FAMILY_WEREWOLF:
             base = [self.alive, self.can_vote, self.eligible, self.submitted, self.revealed, self.investigated, self.wolf, self.secret]
             if f < 8:
@@ -131,10 +136,19 @@ class Record:
             return sum(1 << p for p in range(P) if (self.flags[p] >> f) & 1)
         return 0
 
-    def eval_pred(self, pred: Tuple[int, int, int, int]) -> int:
+    def eval_pred(self, pred) -> int:
+        """Lane mask of a predicate record (4-tuple) — or of a table predicate INDEX, following continued records."""
+        if isinstance(pred, int):
+            out, i = 0, pred
+            while True:
+                rec = self.cg.table.preds[i]
+                out |= self.eval_pred(tuple(rec))
+                if not (rec[0] & T.PRED_CONTINUED):
+                    return out
+                i += 1
         ALL = (1 << self.cg.n_players) - 1
         out = 0
-        for pos, neg in ((pred[0], pred[1]), (pred[2], pred[3])):
+        for pos, neg in ((pred[0] & ~T.PRED_CONTINUED, pred[1]), (pred[2], pred[3])):
             m = ALL
             for f in range(16):
                 if (pos >> f) & 1:
@@ -325,7 +339,7 @@ class SessionCodec:
                     "current_phase_name": cg.phase_names[Y], "phase_history": history, "game_notes": notes}
         # ---- BotBehaviorNode part: the actions the bots took in phase X
         if b.step > 0 and phX.kind == T.KIND_ACTION:
-            actors = b.eval_pred(cg.table.preds[phX.actor_pred]) & ~human_mask
+            actors = b.eval_pred(int(phX.actor_pred)) & ~human_mask
             for p in _bits(actors, P):
                 if cg.family == T.FAMILY_WEREWOLF:
                     choice = a.target[p]
@@ -405,7 +419,7 @@ class SessionCodec:
         phX = self.cg.table.phases[b.phase]
         if b.step == 0 or a.step != b.step + 1 or a.phase != b.phase or a.prev != b.phase or phX.kind != T.KIND_ACTION:
             return False
-        if not (b.eval_pred(self.cg.table.preds[phX.actor_pred]) & human_mask):
+        if not (b.eval_pred(int(phX.actor_pred)) & human_mask):
             return False
         return bool(np.array_equal(before[4:], after[4:]))
 
@@ -432,7 +446,7 @@ class SessionCodec:
         wait = self.stayed(before, after, human_mask)
         ps_old = state.get("player_states") or {}
         names = [ps_old.get(str(p + 1), {}).get("name", "Player %d" % (p + 1)) for p in range(P)]
-        actors = _bits(b.eval_pred(cg.table.preds[phX.actor_pred]), P) if phX.kind == T.KIND_ACTION else []
+        actors = _bits(b.eval_pred(int(phX.actor_pred)), P) if phX.kind == T.KIND_ACTION else []
         if not wait:
             for p in actors:
                 if (human_mask >> p) & 1:
@@ -479,7 +493,7 @@ class SessionCodec:
             return w
         phX = cg.table.phases[b.phase]
         ex, en = phX.exit_op, cg.table.phases[a.phase].entry_op
-        actors = _bits(b.eval_pred(cg.table.preds[phX.actor_pred]), P) if phX.kind == T.KIND_ACTION else []
+        actors = _bits(b.eval_pred(int(phX.actor_pred)), P) if phX.kind == T.KIND_ACTION else []
         died = _bits(b.alive & ~a.alive, P)
         if ex in (T.EX_VOTE_KILL, T.EX_PROTECT, T.EX_INVESTIGATE_RESOLVE):
             for p in actors:

@@ -242,11 +242,20 @@ class SessionBatch:
 
     def audience_masks(self, first: int = 0, count: Optional[int] = None) -> dict:
         """{group name: uint32[count]} for every audience group of the game's declaration."""
-        aud = self.table.game.audience_preds
+        aud = self.table.game.audience_chains
         if not aud:
             return {}
-        m = self.eval_preds(list(aud.values()), first, count)
-        return {name: m[:, j].copy() for j, name in enumerate(aud)}
+        flat, span = [], {}
+        for name, chain in aud.items():                      # a long criterion is a run of records: OR its columns
+            span[name] = (len(flat), len(chain))
+            flat += chain
+        out = {}
+        for lo in range(0, len(flat), 32):                   # the library takes up to 32 records per call
+            m = self.eval_preds(flat[lo:lo + 32], first, count)
+            for name, (a, n) in span.items():
+                for j in range(max(a, lo), min(a + n, lo + 32)):
+                    out[name] = out.get(name, 0) | m[:, j - lo]
+        return {name: np.asarray(out[name], dtype=np.uint32).copy() for name in aud}
 
     # ---- statistics
     def stats(self) -> np.ndarray:

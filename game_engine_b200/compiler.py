@@ -32,7 +32,7 @@ class DSLCompileError(ValueError):
 
 # --------------------------------------------------------------------------- condition grammar
 _TOKEN_RE = re.compile(
-    r"\s*(?:(?P<field>player\.[A-Za-z_][A-Za-z0-9_]*)|(?P<op>==|!=)|(?P<lp>\()|(?P<rp>\))|(?P<lb>\[)|(?P<rb>\])|"
+    r"\s*(?:(?P<field>player\.[A-Za-z_][A-Za-z0-9_]*)|(?P<op>==|!=|<=|>=|<|>)|(?P<lp>\()|(?P<rp>\))|(?P<lb>\[)|(?P<rb>\])|"
     r"(?P<comma>,)|(?P<str>'[^']*'|\"[^\"]*\")|(?P<num>-?\d+)|(?P<word>[A-Za-z_]+))"
 )
 
@@ -139,11 +139,28 @@ class _FieldMap:
                  alias: Optional[Dict[str, str]] = None):
         self.family, self.roles, self.wolf_team, self.village_team = family, role_names, wolf_team, village_team
         self.alias = dict(alias or {})           # DSL field name -> canonical field name (rules `fields:`)
+        self.cmps: List[Tuple[int, int, int]] = []      # comparison fields allocated so far (table.Table.cmps)
+
+    def _comparison(self, name: str, op: str, val: Any) -> List[Clause]:
+        """`player.<numeric field> <op> <int>` -> a derived mask field (table.py, "comparison fields")."""
+        vals = T.W_VAL_FIELDS if self.family == T.FAMILY_WEREWOLF else T.T_VAL_FIELDS
+        if isinstance(val, bool) or not isinstance(val, int) or not (0 <= val <= 255):
+            raise DSLCompileError("numeric field %r compared with %r (need an integer 0..255)" % (name, val))
+        c = (vals[name], T.CMP_OPS[op], int(val))
+        if c not in self.cmps:
+            if len(self.cmps) >= T.MAX_CMP[self.family]:
+                raise DSLCompileError("the table has room for %d numeric comparisons (%r is one too many)" % (T.MAX_CMP[self.family], name))
+            self.cmps.append(c)
+        return [self._lit(T.cmp_field_id(self.family, self.cmps.index(c)), True)]
 
     def literal(self, name: str, op: str, val: Any) -> List[Clause]:
         """DNF of `player.<name> <op> <val>`."""
-        neg = op == "!="
         name = self.alias.get(name, name)
+        if name in (T.W_VAL_FIELDS if self.family == T.FAMILY_WEREWOLF else T.T_VAL_FIELDS):
+            return self._comparison(name, op, val)
+        if op not in ("==", "!="):
+            raise DSLCompileError("field %r is not numeric: only == and != apply" % name)
+        neg = op == "!="
         if self.family == T.FAMILY_WEREWOLF:
             if name == "role":
                 if val not in self.roles:
@@ -177,7 +194,7 @@ def _dnf(node, fm: _FieldMap, negate=False) -> List[Clause]:
     if kind == "cmp":
         _, name, op, val = node
         if negate:
-            op = "!=" if op == "==" else "=="
+            op = T.CMP_NEG[op]
         return fm.literal(name, op, val)
     if kind == "in":
         _, name, vals = node
@@ -206,16 +223,30 @@ def _and(a: List[Clause], b: List[Clause]) -> List[Clause]:
     return out
 
 
-def compile_predicate(cond: str, fm: _FieldMap) -> Tuple[int, int, int, int]:
+def compile_predicate_chain(cond: str, fm: _FieldMap) -> List[Tuple[int, int, int, int]]:
+    """The condition as a run of predicate records: two DNF clauses each, every record but the last flagged
+    "continued" (table.PRED_CONTINUED), so the DNF can have any number of clauses."""
     clauses = []
     for c in _dnf(parse_condition(cond), fm):
         if c not in clauses:
             clauses.append(c)
-    if len(clauses) > 2:
-        raise DSLCompileError("condition %r needs %d DNF clauses (max 2)" % (cond, len(clauses)))
-    while len(clauses) < 2:
+    if not clauses:                              # every clause was contradictory: selects nobody
+        clauses = [T.CLAUSE_EMPTY]
+    if len(clauses) % 2:
         clauses.append(T.CLAUSE_EMPTY)
-    return (clauses[0][0], clauses[0][1], clauses[1][0], clauses[1][1])
+    out = []
+    for i in range(0, len(clauses), 2):
+        cont = T.PRED_CONTINUED if i + 2 < len(clauses) else 0
+        out.append((clauses[i][0] | cont, clauses[i][1], clauses[i + 1][0], clauses[i + 1][1]))
+    return out
+
+
+def compile_predicate(cond: str, fm: _FieldMap) -> Tuple[int, int, int, int]:
+    """Single-record form (conditions of at most two DNF clauses)."""
+    chain = compile_predicate_chain(cond, fm)
+    if len(chain) > 1:
+        raise DSLCompileError("condition %r needs %d predicate records" % (cond, len(chain)))
+    return chain[0]
 
 
 # canonical per-player keys that are not mask fields (targets of a rules `fields:` alias)
@@ -237,7 +268,10 @@ class CompiledGame:
     teams: Tuple[str, str]                      # (village_team, wolf_team)
     action_text: Dict[int, str]                 # phase index -> action text template
     template: Dict[str, Any]                    # declaration.player_states_template entry
-    audience_preds: Dict[str, Tuple[int, int, int, int]] = field(default_factory=dict)
+    audience_preds: Dict[str, Tuple[int, int, int, int]] = field(default_factory=dict)     # groups that fit one record
+    audience_chains: Dict[str, List[Tuple[int, int, int, int]]] = field(default_factory=dict)    # every compiled group
+    audience_errors: Dict[str, str] = field(default_factory=dict)    # groups whose selection_criteria did not compile
+    wait_for: Dict[int, str] = field(default_factory=dict)           # phase index -> completion_criteria.wait_for
     field_alias: Dict[str, str] = field(default_factory=dict)      # DSL field name -> canonical field name
     dsl: Dict[str, Any] = field(default_factory=dict)
     # session-level record items that the DSL carries in per-player fields (rules `session_fields:`): the re-vote
@@ -277,7 +311,7 @@ def n_wolves_for(rule: Any, n_players: int) -> int:
 
 
 def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: Optional[dict] = None,
-                 max_revotes: Optional[int] = None) -> CompiledGame:
+                 max_revotes: Optional[int] = None, strict_audience: bool = False) -> CompiledGame:
     dsl = dsl if dsl is not None else load_dsl(game)
     rules = rules if rules is not None else load_rules(game)
     if max_revotes is None:
@@ -330,10 +364,12 @@ def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: O
     preds: List[tuple] = []
 
     def pred_index(cond: str) -> int:
-        p = compile_predicate(cond, fm)
-        if p not in preds:
-            preds.append(p)
-        return preds.index(p)
+        chain = compile_predicate_chain(cond, fm)
+        for i in range(len(preds) - len(chain) + 1):              # an identical run is shared
+            if preds[i:i + len(chain)] == chain and (i == 0 or not (preds[i - 1][0] & T.PRED_CONTINUED)):
+                return i
+        preds.extend(chain)
+        return len(preds) - len(chain)
 
     n_wolves = n_wolves_for(rules.get("wolves", 0), n_players) if fam == T.FAMILY_WEREWOLF else 0
     if fam == T.FAMILY_WEREWOLF and n_wolves + 2 > n_players:
@@ -342,6 +378,7 @@ def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: O
     tab = T.Table(family=fam, n_players=n_players, n_wolves=n_wolves, rounds=rounds,
                   max_revotes=max_revotes, init_masks=init_masks)
     action_text: Dict[int, str] = {}
+    wait_for: Dict[int, str] = {}
     prules = {int(k): v for k, v in (rules.get("phases") or {}).items()}
     kind_map = {"UI_displayed": T.KIND_UI, "timer": T.KIND_TIMER, "player_action": T.KIND_ACTION}
 
@@ -359,6 +396,14 @@ def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: O
             if not cond:
                 raise DSLCompileError("player_action phase %d has no target_players.condition" % pid)
             out.actor_pred = pred_index(cond)
+            # wait_for (grammar prompt/dsl_phases_generation_prompt.txt:110-113) names three kinds of waiting; the
+            # completion logic is the same for all of them (:128 "whether feedback has been collected from all
+            # target_players"), which is the rule of SPEC D3h.  An unknown value is a malformed game file.
+            wf = cc.get("wait_for")
+            if wf is not None:
+                if wf not in ("single_player_choice", "all_players_action", "multiple_players_action"):
+                    raise DSLCompileError("phase %d: unknown completion_criteria.wait_for %r" % (pid, wf))
+                wait_for[index[pid]] = wf
             act = pr.get("action")
             if not act:
                 raise DSLCompileError("rules annotation lacks an action for player_action phase %d" % pid)
@@ -399,16 +444,28 @@ def compile_game(game: str, n_players: int, dsl: Optional[dict] = None, rules: O
         # every id referenced must exist: the reference validates ids the same way (game_agent_v2.py:1173-1204)
         tab.phases.append(out)
 
-    tab.preds = preds
-    aud = {}
+    # audience groups (declaration.audience_groups[*].selection_criteria): compiled after the phases, so the comparison
+    # fields they allocate never displace one a phase needs.  A group that does not compile is REPORTED
+    # (audience_errors; strict_audience=True raises) instead of silently missing from the masks.
+    aud, aud_chains, aud_err = {}, {}, {}
     for gname, g in (decl.get("audience_groups") or {}).items():
+        saved = list(fm.cmps)
         try:
-            aud[gname] = compile_predicate(g["selection_criteria"], fm)
-        except DSLCompileError:
-            pass
+            chain = compile_predicate_chain(g["selection_criteria"], fm)
+            aud_chains[gname] = chain
+            if len(chain) == 1:
+                aud[gname] = chain[0]
+        except (DSLCompileError, KeyError, TypeError) as e:
+            fm.cmps[:] = saved
+            if strict_audience:
+                raise DSLCompileError("audience group %r: %s" % (gname, e))
+            aud_err[gname] = str(e)
+    tab.preds = preds
+    tab.cmps = list(fm.cmps)
     return CompiledGame(
         name=game, family=fam, n_players=n_players, table=tab, blob=tab.pack(), phase_ids=ids,
         phase_names=[get(p).get("name", "Phase %d" % p) for p in ids], role_names=role_names,
-        teams=(village_team, wolf_team), action_text=action_text, template=tpl, audience_preds=aud, dsl=dsl,
+        teams=(village_team, wolf_team), action_text=action_text, template=tpl, audience_preds=aud, audience_chains=aud_chains,
+        audience_errors=aud_err, wait_for=wait_for, dsl=dsl,
         field_alias=alias, session_fields=session_fields,
     )

@@ -138,11 +138,21 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     t->dev.h = h;
     memcpy(t->dev.phase, blob + sizeof h, (size_t)h.n_phases * sizeof(ge_phase_t));
     memcpy(t->dev.pred, blob + sizeof h + (size_t)h.n_phases * sizeof(ge_phase_t), (size_t)h.n_preds * sizeof(ge_pred_t));
-    // predicates may only name mask fields the family defines (SPEC.md section 2): werewolf 0-12 and 15, TTL 0-4 and 15
-    const uint16_t defined = h.family == FAM_WEREWOLF ? 0x9FFFu : 0x801Fu;
+    // comparison fields (numeric conditions): werewolf up to 2 on selected_target_id, TTL up to 4 on its value fields
+    if (h.n_cmp > (h.family == FAM_WEREWOLF ? 2 : 4) || h.reserved[0] || h.reserved[1]) return fail(GE_ERR_ARG, "bad comparison-field count");
+    for (int k = 0; k < 4; ++k) {
+        const ge_cmp_t& c = h.cmp[k];
+        if (k >= h.n_cmp) { if (c.value_field | c.op | c.constant) return fail(GE_ERR_ARG, "unused comparison field is not zero"); continue; }
+        if (c.op > 5 || c.value_field > (h.family == FAM_WEREWOLF ? 0 : 2)) return fail(GE_ERR_ARG, "bad comparison field");
+    }
+    // predicates may only name mask fields the table defines (SPEC.md section 2): werewolf 0-12, TTL 0-4, the table's
+    // comparison fields, and 15; bit 15 of pos0 chains the record to the next one
+    uint16_t defined = h.family == FAM_WEREWOLF ? 0x9FFFu : 0x801Fu;
+    for (int k = 0; k < h.n_cmp; ++k) defined |= (uint16_t)(1u << ((h.family == FAM_WEREWOLF ? 13 : 11) + k));
     for (int i = 0; i < h.n_preds; ++i) {
         const ge_pred_t& p = t->dev.pred[i];
         if ((p.pos0 | p.neg0 | p.pos1 | p.neg1) & ~defined) return fail(GE_ERR_ARG, "predicate names an undefined mask field");
+        if ((p.pos0 & GE_PRED_CONTINUED) && i + 1 >= h.n_preds) return fail(GE_ERR_ARG, "the last predicate record is marked continued");
     }
     for (int i = 0; i < h.n_phases; ++i) {
         const ge_phase_t& ph = t->dev.phase[i];
@@ -178,15 +188,18 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     // predicate reads one of its fields or an effect read-modify-writes it; effects that overwrite a
     // whole group (ASSIGN_ROLES -> C2, NIGHT_RESET -> player bytes) need no read.
     auto pred_need = [&](int pi) -> uint8_t {
-        if (pi < 0 || pi >= h.n_preds) return 0;
-        const ge_pred_t& p = t->dev.pred[pi];
         uint8_t out = 0;
-        const uint16_t lits[4] = {p.pos0, p.neg0, p.pos1, p.neg1};
-        for (int c = 0; c < 2; ++c) {
-            if (lits[2 * c + 1] & 0x8000u) continue;          // clause marked empty (& ~ALL)
-            const uint16_t used = lits[2 * c] | lits[2 * c + 1];
-            if (used & 0x003Cu) out |= 1;
-            if (used & 0x1FC0u) out |= 2;
+        for (; pi >= 0 && pi < h.n_preds; ++pi) {             // the whole run of a continued predicate
+            const ge_pred_t& p = t->dev.pred[pi];
+            const uint16_t lits[4] = {p.pos0, p.neg0, p.pos1, p.neg1};
+            for (int c = 0; c < 2; ++c) {
+                if (lits[2 * c + 1] & 0x8000u) continue;      // clause marked empty (& ~ALL)
+                const uint16_t used = lits[2 * c] | lits[2 * c + 1];
+                if (used & 0x003Cu) out |= 1;
+                if (used & 0x1FC0u) out |= 2;
+                if (used & 0x6000u) out |= 4;                 // comparison fields read the per-player bytes
+            }
+            if (!(p.pos0 & GE_PRED_CONTINUED)) break;
         }
         return out;
     };

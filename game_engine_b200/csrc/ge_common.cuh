@@ -165,6 +165,20 @@ __device__ __forceinline__ int human_choice_of(const HumanIn& H, int p, int op, 
     return c != HUMAN_NONE ? 1 : -1;                               // MARK
 }
 
+// comparison fields (numeric conditions of the DSL; include/game_engine_b200.h ge_cmp_t)
+__device__ __forceinline__ bool cmp_holds(int op, uint32_t v, uint32_t c) {
+    return op == 0 ? v == c : op == 1 ? v != c : op == 2 ? v < c : op == 3 ? v <= c : op == 4 ? v > c : v >= c;
+}
+// lane mask of "byte p of the packed words <op> constant" over the first P players (werewolf: selected_target_id)
+template <int NW>
+__device__ __forceinline__ uint32_t cmp_mask_bytes(const uint32_t (&w)[NW], int P, const ge_cmp_t& c) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int p = 0; p < 4 * NW; ++p)
+        if (p < P && cmp_holds(c.op, (w[p >> 2] >> (8 * (p & 3))) & 0xFFu, c.constant)) m |= 1u << p;
+    return m;
+}
+
 __device__ __forceinline__ uint32_t all_mask(int P) { return P >= 32 ? 0xFFFFFFFFu : ((1u << P) - 1u); }
 
 // byte offset inside a tile of record byte `o` of session-lane `sl` (S = record bytes)

@@ -624,11 +624,17 @@ __global__ void k_eval_preds(const __grid_constant__ DevTable T, const __grid_co
             F[0] = c0.z; F[1] = c0.w; F[2] = c1.x; F[3] = c1.y; F[4] = c1.z; F[5] = c1.w; F[6] = c2.x; F[7] = c2.y;
             F[8] = c2.y ? ~(c2.z | c2.w) & ALL : 0u; F[9] = c2.z & ~c2.w; F[10] = ~c2.z & c2.w; F[11] = c2.z & c2.w;
             F[12] = c2.y ? ALL : 0u;
+            for (int k = 0; k < T.h.n_cmp && k < 2; ++k)            // comparison fields: selected_target_id <op> constant
+                for (int p = 0; p < P; ++p)
+                    if (cmp_holds(T.h.cmp[k].op, base[rt_tile_off(48 + p, sl, n16)], T.h.cmp[k].constant)) F[13 + k] |= 1u << p;
         } else {
             for (int p = 0; p < P; ++p) {
-                const uint32_t fl = *reinterpret_cast<const uint32_t*>(base + rt_tile_off(8 + 4 * p, sl, n16)) >> 24;
+                const uint32_t pw = *reinterpret_cast<const uint32_t*>(base + rt_tile_off(8 + 4 * p, sl, n16));
+                const uint32_t fl = pw >> 24;
 #pragma unroll
                 for (int f = 0; f < 5; ++f) F[f] |= ((fl >> f) & 1u) << p;
+                for (int k = 0; k < T.h.n_cmp && k < 4; ++k)
+                    if (cmp_holds(T.h.cmp[k].op, (pw >> (8 * T.h.cmp[k].value_field)) & 0xFFu, T.h.cmp[k].constant)) F[11 + k] |= 1u << p;
             }
         }
         for (int j = 0; j < PL.n; ++j) {
@@ -636,7 +642,7 @@ __global__ void k_eval_preds(const __grid_constant__ DevTable T, const __grid_co
             uint32_t res = 0;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
+                const uint32_t pos = (c ? pr.pos1 : pr.pos0) & 0x7FFFu, neg = c ? pr.neg1 : pr.neg0;      // bit 15 of pos0: "continued" (the caller ORs)
                 uint32_t m = ALL;
 #pragma unroll
                 for (int f = 0; f < 16; ++f) {

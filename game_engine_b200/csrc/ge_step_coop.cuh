@@ -35,6 +35,7 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred, int gshift) {
 // =============================================================================== werewolf family
 struct WScalars {
     uint32_t h0, h1, alive, can_vote, eligible, submitted, revealed, investigated, wolf, secret, role_lo, role_hi;
+    uint32_t cmp0, cmp1;        // comparison fields 13 / 14 of the table, balloted from the lanes' own target bytes
 };
 __device__ __forceinline__ uint32_t wc_field(const WScalars& s, int f, uint32_t ALL) {
     switch (f) {
@@ -46,19 +47,24 @@ __device__ __forceinline__ uint32_t wc_field(const WScalars& s, int f, uint32_t 
     case 9: return s.role_lo & ~s.role_hi;
     case 10: return ~s.role_lo & s.role_hi;
     case 11: return s.role_lo & s.role_hi;
+    case 13: return s.cmp0;
+    case 14: return s.cmp1;
     case 15: return ALL;
     default: return 0u;
     }
 }
 __device__ __forceinline__ uint32_t wc_pred(const DevTable& T, const WScalars& s, int pi, uint32_t ALL) {
-    const ge_pred_t pr = T.pred[pi];
     uint32_t out = 0;
+    for (;; ++pi) {                                            // a continued predicate is a run of records, ORed
+        const ge_pred_t pr = T.pred[pi];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0, m = ALL;
-        while (pos) { const int f = __ffs(pos) - 1; pos &= pos - 1; m &= wc_field(s, f, ALL); }
-        while (neg) { const int f = __ffs(neg) - 1; neg &= neg - 1; m &= ~wc_field(s, f, ALL); }
-        out |= m;
+        for (int c = 0; c < 2; ++c) {
+            uint32_t pos = (c ? pr.pos1 : pr.pos0) & 0x7FFFu, neg = c ? pr.neg1 : pr.neg0, m = ALL;
+            while (pos) { const int f = __ffs(pos) - 1; pos &= pos - 1; m &= wc_field(s, f, ALL); }
+            while (neg) { const int f = __ffs(neg) - 1; neg &= neg - 1; m &= ~wc_field(s, f, ALL); }
+            out |= m;
+        }
+        if (!(pr.pos0 & GE_PRED_CONTINUED)) break;
     }
     return out;
 }
@@ -125,6 +131,12 @@ k_step_w_coop(const __grid_constant__ DevTable T, const __grid_constant__ StepAr
 
             uint32_t winner = s.h1 & 0xFF, kill = (s.h1 >> 8) & 0xFF, protect = (s.h1 >> 16) & 0xFF, revote = s.h1 >> 24;
             const uint32_t prev = (s.h0 >> 8) & 0xFF;
+            // comparison fields on the state at the start of the step (warp-uniform point: full-warp ballots)
+            {
+                const ge_cmp_t c0 = T.h.cmp[0], c1 = T.h.cmp[1];
+                s.cmp0 = group_ballot<L>(T.h.n_cmp > 0 && is_player && cmp_holds(c0.op, my_tgt, c0.constant), gshift);
+                s.cmp1 = group_ballot<L>(T.h.n_cmp > 1 && is_player && cmp_holds(c1.op, my_tgt, c1.constant), gshift);
+            }
 
             // ---- PhaseNode: branch selection (replicated scalar work)
             int Y = X; uint32_t tag = 0;
@@ -311,16 +323,29 @@ k_step_t_coop(const __grid_constant__ DevTable T, const __grid_constant__ StepAr
             uint32_t m0 = group_ballot<L>(fl & TF_SPEAKER, gshift), m1 = group_ballot<L>(fl & TF_STMTS, gshift);
             uint32_t m2 = group_ballot<L>(fl & TF_REVEALED, gshift), m3 = group_ballot<L>(fl & TF_CANVOTE, gshift);
             uint32_t m4 = group_ballot<L>(fl & TF_VOTED, gshift);
-            auto field = [&](int f) -> uint32_t { return f == 15 ? ALL : f == 0 ? m0 : f == 1 ? m1 : f == 2 ? m2 : f == 3 ? m3 : f == 4 ? m4 : 0u; };
-            auto pred = [&](int pi) -> uint32_t {
-                const ge_pred_t pr = T.pred[pi];
-                uint32_t out = 0;
+            // comparison fields (numeric conditions): every lane tests its own value byte, one ballot per field
+            uint32_t cm[4];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0, mm = ALL;
-                    while (pos) { const int f = __ffs(pos) - 1; pos &= pos - 1; mm &= field(f); }
-                    while (neg) { const int f = __ffs(neg) - 1; neg &= neg - 1; mm &= ~field(f); }
-                    out |= mm;
+            for (int k = 0; k < 4; ++k) {
+                const ge_cmp_t c = T.h.cmp[k];
+                cm[k] = group_ballot<L>(k < T.h.n_cmp && is_player && cmp_holds(c.op, (pw >> (8 * c.value_field)) & 0xFFu, c.constant), gshift);
+            }
+            auto field = [&](int f) -> uint32_t {
+                return f == 15 ? ALL : f == 0 ? m0 : f == 1 ? m1 : f == 2 ? m2 : f == 3 ? m3 : f == 4 ? m4
+                     : f == 11 ? cm[0] : f == 12 ? cm[1] : f == 13 ? cm[2] : f == 14 ? cm[3] : 0u;
+            };
+            auto pred = [&](int pi) -> uint32_t {
+                uint32_t out = 0;
+                for (;; ++pi) {                                // a continued predicate is a run of records, ORed
+                    const ge_pred_t pr = T.pred[pi];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t pos = (c ? pr.pos1 : pr.pos0) & 0x7FFFu, neg = c ? pr.neg1 : pr.neg0, mm = ALL;
+                        while (pos) { const int f = __ffs(pos) - 1; pos &= pos - 1; mm &= field(f); }
+                        while (neg) { const int f = __ffs(neg) - 1; neg &= neg - 1; mm &= ~field(f); }
+                        out |= mm;
+                    }
+                    if (!(pr.pos0 & GE_PRED_CONTINUED)) break;
                 }
                 return out;
             };

@@ -45,17 +45,26 @@ struct FieldTable {
         f[11][tid] = s.role_lo & s.role_hi;
         f[15][tid] = ALL;
     }
+    // comparison fields of the table (numeric conditions on selected_target_id): mask fields 13 and 14
+    template <int P8>
+    __device__ __forceinline__ void fill_cmp(const DevTable& T, const WState<P8>& s) const {
+        if (T.h.n_cmp > 0) f[13][tid] = cmp_mask_bytes(s.tw, T.h.n_players, T.h.cmp[0]);
+        if (T.h.n_cmp > 1) f[14][tid] = cmp_mask_bytes(s.tw, T.h.n_players, T.h.cmp[1]);
+    }
     __device__ __forceinline__ uint32_t pred(const DevTable& T, int pi, uint32_t ALL) const {
-        const ge_pred_t pr = T.pred[pi];
         uint32_t out = 0;
+        for (;; ++pi) {                                        // a continued predicate is a run of records, ORed
+            const ge_pred_t pr = T.pred[pi];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
-            if (neg & 0x8000u) continue;                       // "& ~ALL": unused clause
-            uint32_t m = ALL;
-            while (pos) { const int k = __ffs(pos) - 1; pos &= pos - 1; m &= f[k][tid]; }
-            while (neg) { const int k = __ffs(neg) - 1; neg &= neg - 1; m &= ~f[k][tid]; }
-            out |= m;
+            for (int c = 0; c < 2; ++c) {
+                uint32_t pos = (c ? pr.pos1 : pr.pos0) & 0x7FFFu, neg = c ? pr.neg1 : pr.neg0;
+                if (neg & 0x8000u) continue;                   // "& ~ALL": unused clause
+                uint32_t m = ALL;
+                while (pos) { const int k = __ffs(pos) - 1; pos &= pos - 1; m &= f[k][tid]; }
+                while (neg) { const int k = __ffs(neg) - 1; neg &= neg - 1; m &= ~f[k][tid]; }
+                out |= m;
+            }
+            if (!(pr.pos0 & GE_PRED_CONTINUED)) break;
         }
         return out;
     }
@@ -242,7 +251,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
     uint32_t winner = s.h1 & 0xFF, kill = (s.h1 >> 8) & 0xFF, protect = (s.h1 >> 16) & 0xFF, revote = s.h1 >> 24;
     const uint32_t prev = (s.h0 >> 8) & 0xFF;
     const bool acting = v.kind() == KIND_ACTION;
-    if (v.wants_fields()) F.fill(s, ALL);
+    if (v.wants_fields()) { F.fill(s, ALL); if constexpr (!V::is_const) F.fill_cmp(v.T, s); }
 
     // ---- PhaseNode: ordered branch evaluation on the state before this step's effects
     const int nb = v.n_branches();
@@ -532,18 +541,21 @@ __device__ __forceinline__ int w_step_light(const DevTable& T, uint4& c) {
     if (ph.n_branches > 1) {
         const uint32_t ALL = all_mask(T.h.n_players);
         auto lp = [&](int pi) -> uint32_t {                    // predicates of need==0 phases only read fields 0, 1, 15
-            const ge_pred_t pr = T.pred[pi];
             uint32_t out = 0;
+            for (;; ++pi) {
+                const ge_pred_t pr = T.pred[pi];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint32_t pos = k ? pr.pos1 : pr.pos0, neg = k ? pr.neg1 : pr.neg0;
-                if (neg & 0x8000u) continue;
-                uint32_t m = ALL;
-                if (pos & 1u) m &= c.z;
-                if (pos & 2u) m &= c.w;
-                if (neg & 1u) m &= ~c.z;
-                if (neg & 2u) m &= ~c.w;
-                out |= m;
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t pos = k ? pr.pos1 : pr.pos0, neg = k ? pr.neg1 : pr.neg0;
+                    if (neg & 0x8000u) continue;
+                    uint32_t m = ALL;
+                    if (pos & 1u) m &= c.z;
+                    if (pos & 2u) m &= c.w;
+                    if (neg & 1u) m &= ~c.z;
+                    if (neg & 2u) m &= ~c.w;
+                    out |= m;
+                }
+                if (!(pr.pos0 & GE_PRED_CONTINUED)) break;
             }
             return out;
         };
@@ -874,19 +886,24 @@ struct TFlags {
 
 template <class V, class FieldFn>
 __device__ __forceinline__ uint32_t t_pred(const V& v, FieldFn field, int pi, uint32_t ALL) {
-    const ge_pred_t pr = v.pred_rec(pi);
     uint32_t out = 0;
+#pragma unroll 1
+    for (;; ++pi) {                                        // a continued predicate is a run of records, ORed
+        const ge_pred_t pr = v.pred_rec(pi);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
-        if (neg & 0x8000u) continue;                       // "& ~ALL": unused clause
-        uint32_t m = ALL;
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t pos = c ? pr.pos1 : pr.pos0, neg = c ? pr.neg1 : pr.neg0;
+            if (neg & 0x8000u) continue;                   // "& ~ALL": unused clause
+            uint32_t m = ALL;
 #pragma unroll
-        for (int f = 0; f < 5; ++f) {
-            if ((pos >> f) & 1u) m &= field(f);
-            if ((neg >> f) & 1u) m &= ~field(f);
+            for (int f = 0; f < 15; ++f) {                 // 0-4 flag fields, 11-14 comparison fields (the rest: never set)
+                if (f >= 5 && f < 11) continue;
+                if ((pos >> f) & 1u) m &= field(f);
+                if ((neg >> f) & 1u) m &= ~field(f);
+            }
+            out |= m;
         }
-        out |= m;
+        if (V::is_const || !(pr.pos0 & GE_PRED_CONTINUED)) break;      // build-time tables have no continued records
     }
     return out;
 }
@@ -903,7 +920,21 @@ __device__ __forceinline__ int t_step_body(const V v, const int X, TState<PB>& s
     TFlags<PB> F;
     F.load(s.pw);
     bool flags_dirty = false;
-    auto field = [&](int f) -> uint32_t { return F.get(f); };
+    // comparison fields of a run-time table (numeric conditions): "value field <op> constant" per player, computed
+    // once per step; build-time tables have none (specgen asserts it)
+    uint32_t cm[4] = {0u, 0u, 0u, 0u};
+    if constexpr (!V::is_const) {
+#pragma unroll 1
+        for (int k = 0; k < v.T.h.n_cmp; ++k) {
+            const ge_cmp_t c = v.T.h.cmp[k];
+            uint32_t m = 0;
+#pragma unroll
+            for (int p = 0; p < PB; ++p)
+                if (p < P && cmp_holds(c.op, (s.pw[p] >> (8 * c.value_field)) & 0xFFu, c.constant)) m |= 1u << p;
+            cm[k] = m;
+        }
+    }
+    auto field = [&](int f) -> uint32_t { return f < 5 ? F.get(f) : (f >= 11 && f < 15) ? cm[f - 11] : 0u; };
 
     const int nb = v.n_branches();
     int taken = nb - 1;

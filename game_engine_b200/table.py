@@ -6,12 +6,20 @@ agent/tools/utils.py:19-31) plus the SPEC.md opcodes.  Layout (little-endian), m
 `include/game_engine_b200.h` (`ge_table_header_t`, `ge_phase_t`, `ge_pred_t`):
 
     header  32 B : "GETB" u16 version | u8 family | u8 n_phases | u8 n_players | u8 n_preds |
-                   u8 n_wolves | u8 rounds | u8 max_revotes | u8 reserved[3] |
-                   u32 init_masks (bit f: mask field f starts as "all players") | u32 reserved[3]
+                   u8 n_wolves | u8 rounds | u8 max_revotes | u8 n_cmp | u8 reserved[2] |
+                   u32 init_masks (bit f: mask field f starts as "all players") |
+                   4 x cmp { u8 value_field | u8 op | u8 constant }      (comparison fields, see below)
     phase   48 B : u8 id | u8 kind | u8 action_op | u8 action_arg | u8 action_flags | u8 exit_op |
                    u8 entry_op | u8 n_branches | u8 actor_pred | u8 pad[7] |
                    4 x branch { u8 op | u8 next | u8 tag | u8 a | u32 arg }
-    pred     8 B : u16 pos0 | u16 neg0 | u16 pos1 | u16 neg1     (DNF, two clauses)
+    pred     8 B : u16 pos0 | u16 neg0 | u16 pos1 | u16 neg1     (DNF, two clauses; bit 15 of pos0 = "continued":
+                   the predicate is this record OR the next one, so a DNF of any length is a run of records)
+
+Comparison fields: the DSL's numeric conditions (`player.total_score >= 3`, `player.selected_target_id != 0`;
+grammar prompt/dsl_phases_generation_prompt.txt:106-128) compile to up to n_cmp derived MASK fields — bit p = "player
+p's value field <op> constant" — that predicates use like any other mask field.  Comparison k has mask-field id
+13 + k in the werewolf family (k < 2; value field 0 = selected_target_id) and 11 + k in the TTL family (k < 4; value
+fields 0 total_score, 1 rounds_as_speaker, 2 vote_choice).  ops: 0 ==, 1 !=, 2 <, 3 <=, 4 >, 5 >=.
 """
 from __future__ import annotations
 
@@ -72,10 +80,26 @@ T_FIELDS = {"is_speaker": 0, "statements_submitted": 1, "lie_revealed": 2, "can_
 # per-player value fields usable by ALL_VAL_GE
 T_VAL_FIELDS = {"total_score": 0, "rounds_as_speaker": 1, "vote_choice": 2}
 
+# comparison fields
+CMP_OPS = {"==": 0, "!=": 1, "<": 2, "<=": 3, ">": 4, ">=": 5}
+CMP_NEG = {"==": "!=", "!=": "==", "<": ">=", ">=": "<", "<=": ">", ">": "<="}
+W_VAL_FIELDS = {"selected_target_id": 0}
+MAX_CMP = {FAMILY_WEREWOLF: 2, FAMILY_TTL: 4}
+PRED_CONTINUED = 1 << 15       # in pos0: OR with the next predicate record
+
+
+def cmp_field_id(family: int, k: int) -> int:
+    return (13 if family == FAMILY_WEREWOLF else 11) + k
+
+
+def cmp_holds(op: int, value: int, const: int) -> bool:
+    return [value == const, value != const, value < const, value <= const, value > const, value >= const][op]
+
+
 PRED_NONE = 0xFF
 CLAUSE_EMPTY = (0, 1 << F_ALL)      # "& ~ALL" selects nobody: marks an unused clause
 
-HEADER_FMT = "<4sHBBBBBBB3sI3I"
+HEADER_FMT = "<4sHBBBBBBBB2sI12s"
 PHASE_HEAD_FMT = "<9B7x"
 BRANCH_FMT = "<BBBBI"
 PRED_FMT = "<4H"
@@ -117,6 +141,7 @@ class Table:
     init_masks: int = 0
     phases: List[Phase] = field(default_factory=list)
     preds: List[tuple] = field(default_factory=list)     # (pos0, neg0, pos1, neg1)
+    cmps: List[tuple] = field(default_factory=list)      # (value_field, op, constant): comparison fields
 
     def pack(self) -> bytes:
         if not (0 < len(self.phases) <= MAX_PHASES):
@@ -125,9 +150,12 @@ class Table:
             raise ValueError("too many predicates")
         if not (2 <= self.n_players <= 32):
             raise ValueError("n_players must be 2..32")
+        if len(self.cmps) > MAX_CMP.get(self.family, 0):
+            raise ValueError("too many comparison fields")
+        cmp_bytes = b"".join(bytes(c) for c in self.cmps).ljust(12, b"\0")
         out = [struct.pack(HEADER_FMT, MAGIC, VERSION, self.family, len(self.phases), self.n_players,
-                           len(self.preds), self.n_wolves, self.rounds, self.max_revotes, b"\0\0\0",
-                           self.init_masks, 0, 0, 0)]
+                           len(self.preds), self.n_wolves, self.rounds, self.max_revotes, len(self.cmps), b"\0\0",
+                           self.init_masks, cmp_bytes)]
         for ph in self.phases:
             if len(ph.branches) > MAX_BRANCHES:
                 raise ValueError("too many branches in phase %d" % ph.id)
@@ -142,10 +170,11 @@ class Table:
 
     @staticmethod
     def unpack(blob: bytes) -> "Table":
-        magic, ver, fam, nph, npl, npr, nw, rounds, mrv, _, init_masks, *_r = struct.unpack_from(HEADER_FMT, blob, 0)
+        magic, ver, fam, nph, npl, npr, nw, rounds, mrv, ncmp, _, init_masks, cmpb = struct.unpack_from(HEADER_FMT, blob, 0)
         if magic != MAGIC or ver != VERSION:
             raise ValueError("bad table blob")
         t = Table(family=fam, n_players=npl, n_wolves=nw, rounds=rounds, max_revotes=mrv, init_masks=init_masks)
+        t.cmps = [tuple(cmpb[3 * k: 3 * k + 3]) for k in range(min(ncmp, 4))]
         off = HEADER_SIZE
         for _ in range(nph):
             pid, kind, aop, aarg, afl, exo, eno, nbr, apred = struct.unpack_from(PHASE_HEAD_FMT, blob, off)

@@ -54,7 +54,7 @@ def materialise(cg: CompiledGame, frames: np.ndarray, room_players: Optional[Lis
         if a.step != b.step and b.step > 0:
             ph = cg.table.phases[b.phase]
             if ph.exit_op in (T.EX_DAY_VOTE, T.EX_T_VOTES):          # VoteRecord[] (types.ts:312-316)
-                actors = b.eval_pred(cg.table.preds[ph.actor_pred])
+                actors = b.eval_pred(int(ph.actor_pred))
                 vid = "phase-%d-step-%d" % (cg.phase_ids[b.phase], b.step)
                 for p in range(cg.n_players):
                     if (actors >> p) & 1:

@@ -56,16 +56,26 @@ typedef struct {
     ge_branch_t br[4];
 } ge_phase_t;
 
+/* DNF of two clauses over the mask fields of SPEC.md section 2; clause = AND(pos fields) & ~OR(neg fields).  Bit 15 of
+ * pos0 = "continued": the predicate is this record OR the next one (a DNF of any length is a run of records). */
 typedef struct {
     uint16_t pos0, neg0, pos1, neg1;
 } ge_pred_t;
+#define GE_PRED_CONTINUED 0x8000u
+
+/* Comparison field: "player's value field <op> constant" as a derived mask field (numeric conditions of the DSL).
+ * Comparison k is mask field 13 + k (werewolf, k < 2; value field 0 = selected_target_id) or 11 + k (TTL, k < 4; value
+ * fields 0 total_score, 1 rounds_as_speaker, 2 vote_choice).  ops: 0 ==, 1 !=, 2 <, 3 <=, 4 >, 5 >=. */
+typedef struct {
+    uint8_t value_field, op, constant;
+} ge_cmp_t;
 
 typedef struct {
     char magic[4];                /* "GETB" */
     uint16_t version;             /* 1 */
-    uint8_t family, n_phases, n_players, n_preds, n_wolves, rounds, max_revotes, reserved[3];
+    uint8_t family, n_phases, n_players, n_preds, n_wolves, rounds, max_revotes, n_cmp, reserved[2];
     uint32_t init_masks;
-    uint32_t reserved2[3];
+    ge_cmp_t cmp[4];
 } ge_table_header_t;
 
 typedef struct ge_table ge_table;

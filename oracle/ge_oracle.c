@@ -87,11 +87,22 @@ static int tab_open(tab_t *t, const uint8_t *blob, size_t n) {
             if (wolfy ? (br[0] == BR_ALL_VAL_GE || br[2] > 2) : br[0] == BR_TIE_PENDING) return -1;
         }
     }
-    /* predicates may only name mask fields the family defines (SPEC.md section 2) */
+    /* comparison fields: count at byte 13, four {value field, op, constant} triples at 20; the rest of the header zero */
+    const int n_cmp = blob[13], wolfy_t = t->family == FAM_WEREWOLF;
+    if (n_cmp > (wolfy_t ? 2 : 4) || blob[14] || blob[15]) return -1;
+    for (int k = 0; k < 4; ++k) {
+        const uint8_t *c = blob + 20 + 3 * k;
+        if (k >= n_cmp) { if (c[0] | c[1] | c[2]) return -1; continue; }
+        if (c[1] > 5 || c[0] > (wolfy_t ? 0 : 2)) return -1;
+    }
+    /* predicates may only name mask fields the table defines (SPEC.md section 2); the last record cannot be continued */
+    unsigned defined = wolfy_t ? 0x9FFFu : 0x801Fu;
+    for (int k = 0; k < n_cmp; ++k) defined |= 1u << ((wolfy_t ? 13 : 11) + k);
     for (int i = 0; i < t->n_preds; ++i) {
         const uint8_t *pr = blob + 32 + 48 * t->n_phases + 8 * i;
         const unsigned used = rd16(pr) | rd16(pr + 2) | rd16(pr + 4) | rd16(pr + 6);
-        if (used & ~(t->family == FAM_WEREWOLF ? 0x9FFFu : 0x801Fu)) return -1;
+        if (used & ~defined) return -1;
+        if ((rd16(pr) & 0x8000) && i + 1 >= t->n_preds) return -1;
     }
     if (wolfy_counts_bad(t)) return -1;
     return 0;
@@ -194,9 +205,24 @@ static void pack(const tab_t *t, const sess_t *s, uint8_t *r) {
     }
 }
 
+/* comparison field k of the table: "player p's value field <op> constant" (numeric conditions of the DSL,
+ * prompt/dsl_phases_generation_prompt.txt:106-128); header bytes 13 = count, 20 + 3k = {value field, op, constant} */
+static int cmp_field(const tab_t *t, const sess_t *s, int k, int p) {
+    if (k < 0 || k >= t->blob[13]) return 0;
+    const uint8_t *c = t->blob + 20 + 3 * k;
+    int v;
+    if (t->family == FAM_WEREWOLF) v = s->target[p];
+    else v = c[0] == 0 ? s->score[p] : c[0] == 1 ? s->rounds_done[p] : s->vote[p];
+    switch (c[1]) {
+    case 0: return v == c[2]; case 1: return v != c[2]; case 2: return v < c[2];
+    case 3: return v <= c[2]; case 4: return v > c[2];  default: return v >= c[2];
+    }
+}
+
 /* value of mask field f for player p (SPEC section 2) */
 static int field_of(const tab_t *t, const sess_t *s, int f, int p) {
     if (f == 15) return 1;
+    if (t->family == FAM_WEREWOLF ? (f == 13 || f == 14) : (f >= 11 && f <= 14)) return cmp_field(t, s, f - (t->family == FAM_WEREWOLF ? 13 : 11), p);
     if (t->family == FAM_WEREWOLF) {
         switch (f) {
         case 0: return s->alive[p];     case 1: return s->can_vote[p];  case 2: return s->eligible[p];
@@ -222,10 +248,11 @@ static int field_of(const tab_t *t, const sess_t *s, int f, int p) {
     }
 }
 
-static int pred_holds(const tab_t *t, const sess_t *s, int pred, int p) {
-    const uint8_t *q = tab_pred(t, pred);
+/* one predicate record: a DNF of two clauses (bit 15 of pos0 is the "continued" flag, not a field) */
+static int pred_record_holds(const tab_t *t, const sess_t *s, const uint8_t *q, int p) {
     for (int c = 0; c < 2; ++c) {
         uint16_t pos = rd16(q + 4 * c), neg = rd16(q + 4 * c + 2);
+        if (c == 0) pos &= 0x7FFF;
         int ok = 1;
         for (int f = 0; f < 16 && ok; ++f) {
             if (!(((pos | neg) >> f) & 1)) continue;
@@ -236,6 +263,14 @@ static int pred_holds(const tab_t *t, const sess_t *s, int pred, int p) {
         if (ok) return 1;
     }
     return 0;
+}
+/* a predicate of the table: the record, ORed with the following ones while they are marked continued */
+static int pred_holds(const tab_t *t, const sess_t *s, int pred, int p) {
+    for (;; ++pred) {
+        const uint8_t *q = tab_pred(t, pred);
+        if (pred_record_holds(t, s, q, p)) return 1;
+        if (!(rd16(q) & 0x8000)) return 0;
+    }
 }
 static int pred_count(const tab_t *t, const sess_t *s, int pred) {
     int n = 0;
@@ -574,19 +609,8 @@ int ge_cpu_eval_preds(const uint8_t *blob, size_t nb, const uint8_t *records, ui
         for (int j = 0; j < n_preds; ++j) {
             const uint8_t *q = preds + 8 * j;
             uint32_t m = 0;
-            for (int p = 0; p < t.P; ++p) {
-                int any = 0;
-                for (int c = 0; c < 2; ++c) {
-                    uint16_t pos = rd16(q + 4 * c), neg = rd16(q + 4 * c + 2);
-                    int ok = 1;
-                    for (int f = 0; f < 16; ++f) {
-                        if (((pos >> f) & 1) && !field_of(&t, &s, f, p)) ok = 0;
-                        if (((neg >> f) & 1) && field_of(&t, &s, f, p)) ok = 0;
-                    }
-                    any |= ok;
-                }
-                if (any) m |= 1u << p;
-            }
+            for (int p = 0; p < t.P; ++p)          /* each record on its own: the caller ORs continued runs */
+                if (pred_record_holds(&t, &s, q, p)) m |= 1u << p;
             out[i * (uint64_t)n_preds + j] = m;
         }
     }

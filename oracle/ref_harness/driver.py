@@ -25,6 +25,9 @@ REFERENCE_GAME_NAME = {
     # the repo's extended game (tie -> re-vote, BASELINE config 4), loaded by the reference's loader from this repo
     "werewolf-revote": os.path.relpath(os.path.join(REPO, "game_engine_b200", "games", "werewolf-revote"),
                                        os.path.join(shims.REFERENCE_ROOT, "games")),
+    # the repo's two-truths variant with numeric conditions (tools/make_handicap_variant.py)
+    "two-truths-handicap": os.path.relpath(os.path.join(REPO, "game_engine_b200", "games", "two-truths-handicap"),
+                                           os.path.join(shims.REFERENCE_ROOT, "games")),
 }
 
 

@@ -31,6 +31,9 @@ CASES = [
     # sid 3010 uses both re-votes of a day and its third vote is tied again (lowest id among the tied dies)
     ("werewolf-revote", 8, 42, 2001), ("werewolf-revote", 8, 46, 3010), ("werewolf-revote", 5, 44, 2003),
     ("werewolf-revote", 16, 45, 7), ("werewolf-revote", 32, 43, 2002),
+    # numeric conditions (`player.total_score < 2` decides who votes) and audience groups with >=, >, negated <=, a
+    # three-clause `or`: the repo's two-truths variant, conditions evaluated by plain Python in the stub
+    ("two-truths-handicap", 4, 51, 4000), ("two-truths-handicap", 6, 52, 4001), ("two-truths-handicap", 9, 53, 4002),
 ]
 
 

@@ -236,3 +236,97 @@ def test_dnf_compiler_agrees_with_direct_evaluation():
             assert got == want, (cond, st, pred)
             checked += 1
     assert checked > 3000
+
+
+# ------------------------------------------------------------------ grammar beyond the shipped games
+def _fm(family):
+    from game_engine_b200.compiler import _FieldMap
+    if family == T.FAMILY_WEREWOLF:
+        return _FieldMap(family, ["Villager", "Werewolf", "Doctor", "Detective"], "werewolves", "villagers")
+    return _FieldMap(family, [], "", "")
+
+
+def test_numeric_comparisons_become_comparison_fields():
+    """`< <= > >= == !=` on the per-player value fields (grammar: prompt/dsl_phases_generation_prompt.txt:106-128)."""
+    from game_engine_b200.compiler import compile_predicate_chain
+    fm = _fm(T.FAMILY_TTL)
+    chain = compile_predicate_chain("player.total_score >= 3 and player.can_vote == true", fm)
+    assert fm.cmps == [(0, T.CMP_OPS[">="], 3)] and chain == [((1 << 11) | (1 << 3), 0) + T.CLAUSE_EMPTY]
+    # a negated comparison flips the operator instead of needing a negative literal
+    compile_predicate_chain("not (player.rounds_as_speaker < 1)", fm)
+    assert fm.cmps[-1] == (1, T.CMP_OPS[">="], 1)
+    # the same comparison is allocated once
+    compile_predicate_chain("player.total_score >= 3 or player.vote_choice != 0", fm)
+    assert fm.cmps == [(0, 5, 3), (1, 5, 1), (2, 1, 0)]
+    fw = _fm(T.FAMILY_WEREWOLF)
+    assert compile_predicate_chain("player.selected_target_id > 0 and player.is_alive == true", fw) == [((1 << 13) | 1, 0) + T.CLAUSE_EMPTY]
+    with pytest.raises(DSLCompileError):
+        compile_predicate_chain("player.is_alive >= 1", fw)                      # ordering on a boolean field
+    with pytest.raises(DSLCompileError):
+        compile_predicate_chain("player.selected_target_id < 'x'", fw)
+    for k in range(2, 4):                                                         # the werewolf family has two slots
+        try:
+            compile_predicate_chain("player.selected_target_id == %d" % k, fw)
+        except DSLCompileError:
+            assert k == 3
+            break
+    else:
+        raise AssertionError("a third comparison field was accepted")
+
+
+def test_conditions_of_any_length_chain_predicate_records():
+    from game_engine_b200.compiler import compile_predicate_chain
+    fw = _fm(T.FAMILY_WEREWOLF)
+    chain = compile_predicate_chain("player.role in ['Werewolf', 'Doctor', 'Detective'] and player.is_alive == true", fw)
+    assert len(chain) == 2 and chain[0][0] & T.PRED_CONTINUED and not chain[1][0] & T.PRED_CONTINUED
+    chain = compile_predicate_chain("(player.is_alive == true or player.role_revealed == true) and (player.can_vote == true or player.role == 'Doctor') "
+                                    "and player.team != 'werewolves'", fw)
+    assert len(chain) >= 2 and all(c[0] & T.PRED_CONTINUED for c in chain[:-1])
+    # the evaluation of a chained predicate == Python's evaluation of the text, on every combination of the fields
+    from game_engine_b200.adapter import Record
+    cg = compile_game("werewolf-(mafia)", 8)
+    import itertools
+    import numpy as np
+    from oracle.ref_harness.stub_llm import holds
+    cond = "(player.is_alive == true or player.role_revealed == true) and (player.can_vote == true or player.night_action_eligible == true) and not (player.night_action_submitted == true and player.is_alive == false)"
+    chain = compile_predicate_chain(cond, _fm(T.FAMILY_WEREWOLF))
+    names = ["is_alive", "role_revealed", "can_vote", "night_action_eligible", "night_action_submitted"]
+    slots = {"is_alive": 0, "can_vote": 1, "night_action_eligible": 2, "night_action_submitted": 3, "role_revealed": 4}
+    for bits in itertools.product([False, True], repeat=5):
+        raw = np.zeros(cg.record_size, dtype=np.uint8)
+        ps = dict(zip(names, bits))
+        for n, v in ps.items():
+            raw[8 + 4 * slots[n]] = 1 if v else 0                              # player 1 only
+        rec = Record(cg, raw)
+        got = 0
+        for c in chain:
+            got |= rec.eval_pred(tuple(c))
+        assert bool(got & 1) == holds(cond, ps), (ps, chain)
+
+
+def test_wait_for_is_validated_and_audience_groups_that_do_not_compile_are_reported():
+    import copy
+    from game_engine_b200.compiler import load_dsl, load_rules
+    cg = compile_game("werewolf-(mafia)", 8)
+    assert set(cg.wait_for.values()) <= {"single_player_choice", "all_players_action", "multiple_players_action"} and cg.wait_for
+    assert cg.audience_errors == {} and set(cg.audience_chains) == set(cg.dsl["declaration"]["audience_groups"])
+    dsl, rules = copy.deepcopy(load_dsl("werewolf-(mafia)")), load_rules("werewolf-(mafia)")
+    dsl["declaration"]["audience_groups"]["nicknamed"] = {"selection_criteria": "player.nickname == 'x'"}
+    dsl["declaration"]["audience_groups"]["armed"] = {"selection_criteria": "player.selected_target_id >= 1 and player.is_alive == true"}
+    cg2 = compile_game("werewolf-(mafia)", 8, dsl=dsl, rules=rules)
+    assert list(cg2.audience_errors) == ["nicknamed"] and "armed" in cg2.audience_chains and cg2.table.cmps == [(0, 5, 1)]
+    with pytest.raises(DSLCompileError):
+        compile_game("werewolf-(mafia)", 8, dsl=dsl, rules=rules, strict_audience=True)
+    bad = copy.deepcopy(load_dsl("werewolf-(mafia)"))
+    bad["phases"][7]["completion_criteria"]["wait_for"] = "whoever_feels_like_it"
+    with pytest.raises(DSLCompileError):
+        compile_game("werewolf-(mafia)", 8, dsl=bad, rules=rules)
+
+
+def test_the_numeric_variant_compiles_to_four_comparison_fields():
+    cg = compile_game("two-truths-handicap", 6)
+    assert len(cg.table.cmps) == 4 and not cg.audience_errors
+    assert len(cg.audience_chains["busy"]) == 2                                  # four clauses: two records
+    vote = cg.table.phases[cg.index_of(5)]
+    rec = cg.table.preds[vote.actor_pred]
+    assert rec[0] & (1 << T.cmp_field_id(T.FAMILY_TTL, cg.table.cmps.index((0, T.CMP_OPS["<"], 2))))

@@ -35,7 +35,16 @@ def random_table(seed: int, family: int) -> T.Table:
     tab = T.Table(family=family, n_players=P, n_wolves=int(rng.integers(1, max(2, P // 3))) if wolf else 0,
                   rounds=0 if wolf else int(rng.integers(1, 3)), max_revotes=int(rng.integers(0, 3)) if wolf else 0,
                   init_masks=(0b11 | (int(rng.integers(0, 2)) << 2)) if wolf else (1 << 3 | int(rng.integers(0, 2))))
+    # comparison fields (numeric conditions) and the mask-field ids they occupy
+    n_cmp = int(rng.integers(0, T.MAX_CMP[family] + 1)) if rng.random() < 0.6 else 0
+    tab.cmps = [(0 if wolf else int(rng.integers(0, 3)), int(rng.integers(0, 6)), int(rng.integers(0, 4 if not wolf else P + 1)))
+                for _ in range(n_cmp)]
+    fields = fields + [T.cmp_field_id(family, k) for k in range(n_cmp)]
     tab.preds = [_pred(rng, fields) for _ in range(int(rng.integers(3, 9)))]
+    for i in range(len(tab.preds) - 1):                             # some predicates continue in the next record
+        if rng.random() < 0.25:
+            p0 = tab.preds[i]
+            tab.preds[i] = (p0[0] | T.PRED_CONTINUED,) + tuple(p0[1:])
     tab.preds.append((1, 0) + T.CLAUSE_EMPTY)                       # "field 0" (alive / speaker): keeps games lively
     npred = len(tab.preds)
     exits = [T.EX_VOTE_KILL, T.EX_PROTECT, T.EX_INVESTIGATE_RESOLVE, T.EX_DAY_VOTE] if wolf else \
@@ -102,7 +111,8 @@ def test_random_tables_are_accepted_and_deterministic(family):
         np.testing.assert_array_equal(sa, sb)
 
 
-@pytest.mark.parametrize("bad", ["exit_on_ui", "foreign_exit", "foreign_entry", "no_action_op", "option_vote", "foreign_branch"])
+@pytest.mark.parametrize("bad", ["exit_on_ui", "foreign_exit", "foreign_entry", "no_action_op", "option_vote", "foreign_branch",
+                                 "bad_cmp_op", "undefined_field", "dangling_chain", "too_many_cmps"])
 def test_ill_formed_tables_are_rejected_by_the_oracle(bad):
     from oracle.oracle import Oracle
     tab = random_table(3, T.FAMILY_WEREWOLF)
@@ -120,8 +130,18 @@ def test_ill_formed_tables_are_rejected_by_the_oracle(bad):
         act.exit_op, act.action_op, act.action_arg = T.EX_DAY_VOTE, T.ACT_PICK_OPTION, 3
     elif bad == "foreign_branch":
         ui.branches[0].op = T.BR_ALL_VAL_GE
+    elif bad == "bad_cmp_op":
+        tab.cmps = [(0, 9, 1)]
+    elif bad == "undefined_field":                      # a predicate on comparison field 14 the table does not define
+        tab.cmps = tab.cmps[:1]
+        tab.preds[0] = (1 << 14, 0) + T.CLAUSE_EMPTY
+    elif bad == "dangling_chain":
+        tab.preds[-1] = (tab.preds[-1][0] | T.PRED_CONTINUED,) + tuple(tab.preds[-1][1:])
+    blob = tab.pack()
+    if bad == "too_many_cmps":                          # the count byte says three; the werewolf family has two
+        blob = blob[:13] + bytes([3]) + blob[14:]
     with pytest.raises(ValueError):
-        Oracle(tab.pack())
+        Oracle(blob)
 
 
 class _Blob:
