@@ -94,6 +94,8 @@ def parse_args():
                          "of from the host after `cap` steps; measured: no gain at 2^20 sessions (some game always runs to the cap)")
     ap.add_argument("--compaction", default="", help="active-prefix compaction 'every,shift' (default: the library's choice for the family)")
     ap.add_argument("--regroup", default="", help="phase regrouping 'every,shift' (default: the library's choice for the table)")
+    ap.add_argument("--light-bulk", action="store_true",
+                    help="A/B: header-only launches fetch their tiles with cp.async.bulk + mbarrier (ge_batch_set_option)")
     ap.add_argument("--head-start-us", type=int, default=3000,
                     help="length of the spin kernel the timed launches are queued behind (host head start; 0 = none)")
     ap.add_argument("--seed", type=int, default=20261018)
@@ -413,6 +415,8 @@ def run_ours(a):
     for i, b in enumerate(ring):
         b.set_stream(streams[i % NS].cuda_stream)
         b.set_grid(0 if merged else a.ctas_per_sm)
+        if a.light_bulk:
+            b.set_option("light_bulk", 1)
         if a.regroup:
             b.set_regroup(*[int(x) for x in a.regroup.split(",")])
         if a.compaction:
@@ -682,7 +686,7 @@ def run_ours(a):
         "config": {
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
             "baseline_config": a.config,
-            "kernel": kern, "launch": "one ring launch per pass (ge_step_ring)" if merged else "one launch per batch", "streams": NS,
+            "light_path": "cp.async.bulk + mbarrier" if a.light_bulk else "LDG.128", "kernel": kern, "launch": "one ring launch per pass (ge_step_ring)" if merged else "one launch per batch", "streams": NS,
             "ctas_per_sm": "occupancy limit" if merged else a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
             "steps_before_reinit": "when every game of the batch is over (device-side auto-reset, checked every 8 steps)" if auto else cap,
             "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,

@@ -129,6 +129,10 @@ class SessionBatch:
         (0 steps = off; default (5, 2) for the werewolf family, off for TTL)."""
         capi.check(capi.lib().ge_batch_set_compaction(self._h, int(every_n_steps), int(min_dead_shift)))
 
+    def set_option(self, option: str, value: int) -> None:
+        """Tuning options: "light_bulk" (header-only launches fetch their tiles with cp.async.bulk + mbarrier)."""
+        capi.check(capi.lib().ge_batch_set_option(self._h, {"light_bulk": capi.OPT_LIGHT_BULK}[option], int(value)))
+
     def set_grid(self, ctas_per_sm: int) -> None:
         """Persistent grid of the step launches = SMs x ctas_per_sm (0 = as many as fit).  Smaller grids let the
         launches of other batches on other streams co-reside."""

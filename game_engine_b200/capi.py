@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgame_engine_b200.so")
 STATS_LEN = 560
 GE_OK, GE_ERR_ARG, GE_ERR_CUDA, GE_ERR_UNSUPPORTED, GE_ERR_NOMEM = 0, -1, -2, -3, -4
 KERNEL_AUTO, KERNEL_COOP, KERNEL_TPS, KERNEL_TPS_GENERIC = 0, 1, 2, 3
+OPT_LIGHT_BULK = 1
 WIRE_CANONICAL, WIRE_DENSE = 0, 1
 WIRE_NAMES = {"canonical": WIRE_CANONICAL, "dense": WIRE_DENSE}
 KERNEL_NAMES = {"auto": KERNEL_AUTO, "coop": KERNEL_COOP, "tps": KERNEL_TPS, "tps_generic": KERNEL_TPS_GENERIC}
@@ -44,6 +45,7 @@ SYMBOLS = [
     ("ge_batch_active", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_active_hint", _int, [_vp, ctypes.POINTER(_u64)]),
     ("ge_batch_get_kernel", _int, [_vp]),
+    ("ge_batch_set_option", _int, [_vp, _int, _int]),
     ("ge_batch_set_human_seats", _int, [_vp, _vp]),
     ("ge_batch_set_human_choices", _int, [_vp, _vp]),
     ("ge_table_human_stride", _sz, [_vp]),

@@ -93,6 +93,7 @@ struct ge_batch {
     uint32_t* d_hmask;            // human seats per session (NULL = all bots) and their inputs for the next step
     uint8_t* d_hchoice;
     bool hchoice_set;             // inputs are pending: the next step launch consumes them
+    uint32_t step_flags;          // StepArgs::flags (ge_batch_set_option)
     int wire;                     // host-buffer record format (GE_WIRE_*); rec_wire = its record size
     size_t rec_wire;
     uint32_t* d_err;              // import validation: [0] rejected records, [1] max(~index) (k_import)
@@ -603,6 +604,15 @@ extern "C" int ge_batch_set_human_choices(ge_batch* b, const uint8_t* host_choic
 }
 extern "C" size_t ge_table_human_stride(const ge_table* t) { return t ? human_stride(t) : 0; }
 
+extern "C" int ge_batch_set_option(ge_batch* b, int option, int value) {
+    if (!b) return fail(GE_ERR_ARG, "batch is NULL");
+    if (option == GE_OPT_LIGHT_BULK) {
+        b->step_flags = value ? (b->step_flags | STEP_LIGHT_BULK) : (b->step_flags & ~(uint32_t)STEP_LIGHT_BULK);
+        return GE_OK;
+    }
+    return fail(GE_ERR_ARG, "unknown option");
+}
+
 extern "C" int ge_batch_set_kernel(ge_batch* b, int kernel) {
     if (!b || kernel < GE_KERNEL_AUTO || kernel > GE_KERNEL_TPS_GENERIC) return fail(GE_ERR_ARG, "bad kernel id");
     kernel = kernel == GE_KERNEL_AUTO ? GE_KERNEL_TPS : kernel;
@@ -764,7 +774,7 @@ static int consume_human_inputs(ge_batch* b, cudaStream_t st) {
 }
 
 static void fill_common(const ge_batch* b, StepArgs& a, int steps_per_launch) {
-    a.seed = b->seed; a.n_steps = steps_per_launch;
+    a.seed = b->seed; a.n_steps = steps_per_launch; a.flags = b->step_flags;
     for (int r = 0; r < 10; ++r) {
         a.rk[2 * r] = (uint32_t)b->seed + (uint32_t)r * 0x9E3779B9u;
         a.rk[2 * r + 1] = (uint32_t)(b->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
@@ -804,7 +814,10 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
         const bool regroup_after = regroup && b->since_compact + 1 >= b->regroup_every;
         const bool compact_after = !regroup && b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
         fill_slot(b, a, compact_after || regroup_after, regroup);
-        fn<<<b->grid[b->kernel], 128, 0, st>>>(b->tab->dev, a);
+        // the bulk-copy variant of the light path stages its tiles in dynamic shared memory (werewolf single-batch kernels)
+        const bool bulk = (a.flags & STEP_LIGHT_BULK) && b->tab->family == FAM_WEREWOLF && !b->d_hmask && b->kernel != GE_KERNEL_COOP;
+        if (!bulk) a.flags &= ~(uint32_t)STEP_LIGHT_BULK;
+        fn<<<b->grid[b->kernel], 128, bulk ? sizeof(LightBulk) : 0, st>>>(b->tab->dev, a);
         b->launches++;
         b->since_compact++;
         if (b->hchoice_set) { const int rc = consume_human_inputs(b, st); if (rc != GE_OK) return rc; }

@@ -72,9 +72,11 @@ struct SlotArgs {
     // in slot i then has id first_sid + n_active[8] * sid_stride + origin[i].  0 = off.
     uint64_t sid_stride;
 };
+enum { STEP_LIGHT_BULK = 1 };     // StepArgs::flags
 struct StepArgs : SlotArgs {
     uint64_t seed;
     int n_steps;
+    uint32_t flags;               // STEP_LIGHT_BULK: header-only launches fetch their tiles with cp.async.bulk + mbarrier (A/B knob)
     // Philox round keys (k0 + r*W0, k1 + r*W1 for r = 0..9), expanded once on the host: as kernel parameters they
     // are constant-bank operands of the round's XOR, so the key schedule costs no instructions.
     uint32_t rk[20];
@@ -186,6 +188,27 @@ template <int S>
 __device__ __host__ __forceinline__ constexpr uint32_t tile_off(uint32_t o, uint32_t sl) {
     return (o / 16u < (uint32_t)(S / 16)) ? (o / 16u) * 512u + sl * 16u + (o % 16u)
                                           : (uint32_t)(S / 16) * 512u + sl * 8u + (o - 16u * (uint32_t)(S / 16));
+}
+
+// ---- bulk asynchronous copies (cp.async.bulk, the non-tensor TMA path) with mbarrier completion -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
 }
 
 // L1 prefetch of the 128-byte line that holds p (one warp instruction covers a 512-byte column of a tile)

@@ -615,6 +615,11 @@ struct WSmem {
     uint32_t fields[16][TPS_THREADS];
     uint8_t lut[P8 > 16 ? P8 : 1][TPS_THREADS];
 };
+// staging of the bulk-copy variant of the light path: per warp two stages of four 512-byte columns, one mbarrier each
+struct LightBulk {
+    alignas(16) uint8_t buf[TPS_THREADS / 32][2][4][512];
+    alignas(8) uint64_t bar[TPS_THREADS / 32][2];
+};
 
 // This CTA's share of ONE batch: every non-terminal session of the batch's active prefix advances by C.n_steps
 // steps.  C carries what a ring of batches shares (steps per launch, Philox round keys), A the batch, `bc` the block
@@ -626,7 +631,7 @@ struct WSmem {
 // the all-bot kernels are exactly what they were.
 template <int P8, class Spec, bool HUM = false>
 __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C, const SlotArgs& A, BlockCounters& bc,
-                                            uint32_t (*s_fields)[TPS_THREADS], uint8_t* s_lut_col) {
+                                            uint32_t (*s_fields)[TPS_THREADS], uint8_t* s_lut_col, LightBulk* lb = nullptr) {
     constexpr int S = 48 + P8;
     constexpr int NT16 = P8 / 16;          // full 16-byte target columns
     constexpr bool THALF = (P8 % 16) != 0; // trailing 8-byte column
@@ -662,11 +667,41 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
         }
         const bool y0_live = x0 >= 0 && ((T.nonterm >> y0) & 1u);
         const uint32_t hdr0 = y0 | ((uint32_t)x0 << 8);
-        for (uint32_t tile = warp0; tile < n_tiles_act; tile += 4 * nwarps, base += 4 * tile_stride) {
+        // A/B variant (STEP_LIGHT_BULK): the four columns of a group arrive by cp.async.bulk into shared memory (one
+        // elected lane issues four 512-byte copies, an mbarrier counts the bytes), double-buffered one group ahead,
+        // instead of four warp-wide LDG.128.  Measured, not kept as the default: DESIGN section 6.
+        const bool bulk = lb != nullptr && (C.flags & STEP_LIGHT_BULK);
+        const int wib = threadIdx.x >> 5;
+        auto issue_group = [&](uint32_t tile0, const uint8_t* gbase, int stage) {      // lane 0 only
+            uint32_t n = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) n += tile0 + j * nwarps < n_tiles_act;
+            mbar_expect_tx(&lb->bar[wib][stage], 512u * n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (tile0 + j * nwarps < n_tiles_act) bulk_g2s(lb->buf[wib][stage][j], gbase - lane * 16 + j * tile_stride, 512u, &lb->bar[wib][stage]);
+        };
+        uint32_t group = 0;
+        if (bulk) {
+            if (lane == 0) { mbar_init(&lb->bar[wib][0], 1); mbar_init(&lb->bar[wib][1], 1); mbar_init_fence(); }
+            __syncwarp();
+            if (lane == 0 && warp0 < n_tiles_act) issue_group(warp0, base, 0);
+        }
+        for (uint32_t tile = warp0; tile < n_tiles_act; tile += 4 * nwarps, base += 4 * tile_stride, ++group) {
             uint4 c[4];
+            if (bulk) {
+                const int stage = group & 1;
+                if (lane == 0 && tile + 4 * nwarps < n_tiles_act) issue_group(tile + 4 * nwarps, base + 4 * tile_stride, stage ^ 1);
+                mbar_wait(&lb->bar[wib][stage], (group >> 1) & 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    c[j] = tile + j * nwarps < n_tiles_act ? *reinterpret_cast<const uint4*>(&lb->buf[wib][stage][j][lane * 16]) : make_uint4(0, 0, 0, 0);
+                __syncwarp();                                   // every lane has its copy before the stage is refilled
+            } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 c[j] = tile + j * nwarps < n_tiles_act ? ld128(base + j * tile_stride) : make_uint4(0, 0, 0, 0);
+            }
 
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -804,9 +839,11 @@ template <int P8, class Spec = void>
 __global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
 k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
     __shared__ WSmem<P8, 1> sm;
+    extern __shared__ __align__(16) uint8_t dyn_smem[];       // sizeof(LightBulk) when the launch asked for STEP_LIGHT_BULK
+    LightBulk* lb = (A.flags & STEP_LIGHT_BULK) ? reinterpret_cast<LightBulk*>(dyn_smem) : nullptr;
     counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
-    w_tps_tiles<P8, Spec>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
+    w_tps_tiles<P8, Spec>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0], lb);
     __syncthreads();
     w_tps_publish(A, sm.c[0]);
 }

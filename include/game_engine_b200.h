@@ -144,6 +144,12 @@ int ge_batch_epochs(ge_batch *b, uint64_t *out);
  * 0 means every game of the batch is over — the cue to re-initialise it without waiting for a step cap. */
 int ge_batch_active_hint(ge_batch *b, uint64_t *out);
 int ge_batch_get_kernel(const ge_batch *b);
+/* Tuning options of a batch.  GE_OPT_LIGHT_BULK (werewolf family, specialised / interpreter single-batch kernels):
+ * launches whose sessions are all in header-only phases fetch their 512-byte columns with cp.async.bulk into shared
+ * memory, completion counted by an mbarrier, double-buffered one group of four tiles ahead, instead of warp-wide
+ * 128-bit loads.  Off by default (measured: DESIGN section 6). */
+#define GE_OPT_LIGHT_BULK 1
+int ge_batch_set_option(ge_batch *b, int option, int value);
 
 /* Record format of the host-buffer calls of this batch (ge_export_state, ge_import_state, ge_run_host[_async]):
  * canonical (default) or dense.  The dense format carries the same fields in 32 bytes (<= 8 players) or 48 bytes
