@@ -96,8 +96,8 @@ struct ge_batch {
     uint32_t step_flags;          // StepArgs::flags (ge_batch_set_option)
     int wire;                     // host-buffer record format (GE_WIRE_*); rec_wire = its record size
     size_t rec_wire;
-    uint32_t* d_err;              // import validation: [0] rejected records, [1] max(~index) (k_import)
-    uint32_t* h_err;              // pinned copy, read after the next synchronisation
+    uint32_t* h_err;              // import validation: [0] rejected records, [1] max(~index): pinned host words that k_import
+    uint32_t* d_err;              //   bumps THROUGH THE MAPPING (d_err) only when it finds a bad record — no memset, no copy
     cudaEvent_t fence;            // orders a caller-supplied stream against the batch's own (ge_step / ge_run_fused / ge_stats_refresh)
 };
 
@@ -481,9 +481,9 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (e == cudaSuccess) e = cudaMalloc(&b->d_prefix, mask_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cstate, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc(&b->h_hint, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_err, 2 * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaHostAlloc(&b->h_err, 2 * sizeof(uint32_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&b->h_err, 2 * sizeof(uint32_t), cudaHostAllocMapped);
     if (e == cudaSuccess) { b->h_err[0] = 0; b->h_err[1] = 0; }
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&b->d_err, b->h_err, 0);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->fence, cudaEventDisableTiming);
     if (e == cudaSuccess) { b->h_hint[0] = n_sessions; b->h_hint[1] = 0; }
     b->scan_blocks = (int)((b->n_tiles + CS_TILES - 1) / CS_TILES);
@@ -499,7 +499,7 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (e != cudaSuccess) {
         cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_presence);
         cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
-        cudaFree(b->d_err); cudaFreeHost(b->h_err); if (b->fence) cudaEventDestroy(b->fence);
+        cudaFreeHost(b->h_err); if (b->fence) cudaEventDestroy(b->fence);
         delete b;
         return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_create: ") + cudaGetErrorString(e));
     }
@@ -540,7 +540,7 @@ extern "C" void ge_batch_destroy(ge_batch* b) {
     cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_stage); cudaFree(b->d_presence);
     cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
     cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin);
-    cudaFree(b->d_err); cudaFreeHost(b->h_err); if (b->fence) cudaEventDestroy(b->fence);
+    cudaFreeHost(b->h_err); if (b->fence) cudaEventDestroy(b->fence);
     cudaFree(b->d_hmask); cudaFree(b->d_hchoice);
     delete b;
 }
@@ -997,7 +997,7 @@ static int restore_order(ge_batch* b, bool keep_records) {
         InitRec rec;
         memcpy(rec.w, b->tab->init_words, sizeof rec.w);
         k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, b->d_origin, b->n, 0, b->n, b->d_stage);
-        k_import<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, 0, b->n, b->d_stage, nullptr);
+        k_import<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, 0, b->n, b->d_stage, nullptr, ImportReset{nullptr, nullptr, 0, 0});
         CU(cudaGetLastError());
         b->launches += 2;
     }
@@ -1012,26 +1012,35 @@ static int restore_order(ge_batch* b, bool keep_records) {
 }
 
 // Every import path comes through here: the records are range-checked ON THE DEVICE by k_import (record_invalid,
-// ge_glue.cuh) and the verdict is copied to pinned host memory behind it; sync_and_check reports it.
+// ge_glue.cuh); a bad record bumps two words of mapped pinned host memory (system-scope atomics, only on the rare
+// malformed record), which sync_and_check reads after the next synchronisation and clears.
 static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void* host_buf, int wire) {
     const bool dense = wire == GE_WIRE_DENSE && has_dense(b->tab);
     const size_t S = dense ? ge_table_wire_size(b->tab, GE_WIRE_DENSE) : b->tab->rec_canon;
-    int rc = restore_order(b, !(first == 0 && count == b->n));         // imported sessions may be live anywhere
-    if (rc) return rc;
-    rc = ensure_stage(b, count * S);
+    // imported sessions may be live anywhere: slot order and the active prefix go back to "everything".  A whole-batch
+    // import overwrites every record, so only the bookkeeping is reset — by the import kernel itself.
+    const bool whole = first == 0 && count == b->n;
+    ImportReset R{b->d_presence, nullptr, b->n, 0};
+    if (whole) {
+        b->compacted = false;
+        b->epoch++;
+        b->since_compact = 0;
+        R.cstate = b->d_cstate; R.epoch = b->epoch;
+    } else {
+        const int rc0 = restore_order(b, true);
+        if (rc0) return rc0;
+    }
+    int rc = ensure_stage(b, count * S);
     if (rc) return rc;
     InitRec rec;
     memcpy(rec.w, b->tab->init_words, sizeof rec.w);
     CU(cudaMemcpyAsync(b->d_stage, host_buf, count * S, cudaMemcpyHostToDevice, b->stream));
-    CU(cudaMemsetAsync(b->d_err, 0, 2 * sizeof(uint32_t), b->stream));
-    if (dense && b->tab->bucket == 8) k_import_dense<8><<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err);
-    else if (dense) k_import_dense<16><<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err);
-    else k_import<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage, b->d_err);
+    if (dense && b->tab->bucket == 8) k_import_dense<8><<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else if (dense) k_import_dense<16><<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else k_import<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage, b->d_err, R);
     CU(cudaGetLastError());
     b->launches++;
-    CU(cudaMemcpyAsync(b->h_err, b->d_err, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
-    b->next_override = 0xFFFFFFFFu;   // imported sessions can be in any phase
+    b->next_override = 0xFFFFFFFFu;   // imported sessions can be in any phase (the import kernel cleared the presence words)
     return GE_OK;
 }
 

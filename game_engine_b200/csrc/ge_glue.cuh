@@ -41,6 +41,22 @@ __global__ void k_export(const uint8_t* tiles, uint32_t S_dev, uint32_t S_canon,
     }
 }
 
+// Bookkeeping an import resets, done by the import kernel's first thread instead of separate stream operations (an
+// end-to-end call is a handful of short operations per sub-batch; each one saved shows): the phase-presence words
+// (the next step launch starts from an override) and, for a whole-batch import, the compaction state (every slot
+// active again, slot order = session order; the device epoch of auto-reset, word 8, survives).
+struct ImportReset {
+    uint32_t* presence;               // NULL = leave alone
+    unsigned long long* cstate;       // NULL = leave alone
+    unsigned long long n, epoch;
+};
+__device__ __forceinline__ void import_reset(const ImportReset& R) {
+    if (R.presence) { R.presence[0] = 0; R.presence[1] = 0; R.presence[2] = 0; }
+    if (R.cstate)
+        for (int i = 0; i < 16; ++i)
+            if (i != 8) R.cstate[i] = i == 0 ? R.n : i == 7 ? R.epoch : 0ull;
+}
+
 // Record validation (SPEC.md section 7b), shared by every import path: the step kernels index the table with the
 // phase bytes and shift by player ids, so a record must be range-checked before it reaches them.  0 = well-formed.
 __device__ __forceinline__ int record_invalid(const DevTable& T, const uint8_t* r, uint32_t S_canon) {
@@ -71,8 +87,9 @@ __device__ __forceinline__ int record_invalid(const DevTable& T, const uint8_t* 
 // canonical AoS records -> tiles.  A record that fails validation is replaced by the table's initial record (always
 // safe to step) and reported: err[0] counts such records, err[1] = max(~index) (so ~err[1] is the first one).
 __global__ void k_import(const __grid_constant__ DevTable T, const __grid_constant__ InitRec init, uint8_t* tiles, uint32_t S_dev, uint32_t S_canon,
-                         uint64_t first, uint64_t count, const uint8_t* in, uint32_t* err) {
+                         uint64_t first, uint64_t count, const uint8_t* in, uint32_t* err, ImportReset R) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) import_reset(R);
     const uint32_t n16 = S_dev / 16;
     for (uint64_t j = t; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = first + j;
@@ -80,7 +97,7 @@ __global__ void k_import(const __grid_constant__ DevTable T, const __grid_consta
         const uint32_t sl = (uint32_t)(i & 31);
         const uint8_t* r = in + j * S_canon;
         const bool bad = err != nullptr && record_invalid(T, r, S_canon) != 0;
-        if (bad) { atomicAdd(&err[0], 1u); atomicMax(&err[1], ~(uint32_t)(j > 0xFFFFFFFEull ? 0xFFFFFFFEull : j)); }
+        if (bad) { atomicAdd_system(&err[0], 1u); atomicMax_system(&err[1], ~(uint32_t)(j > 0xFFFFFFFEull ? 0xFFFFFFFEull : j)); }
         for (uint32_t k = 0; k < S_dev / 8; ++k) {
             uint2 v = make_uint2(0, 0);
             if (bad) v = make_uint2(init.w[2 * k], init.w[2 * k + 1]);
@@ -189,8 +206,9 @@ __device__ __forceinline__ void tile_store_words(uint8_t* tiles, uint64_t slot, 
 template <int P8>
 __global__ void __launch_bounds__(256)
 k_import_dense(const __grid_constant__ DevTable T, const __grid_constant__ InitRec init, uint8_t* tiles, uint64_t first, uint64_t count,
-               const uint8_t* in, uint32_t* err) {
+               const uint8_t* in, uint32_t* err, ImportReset R) {
     constexpr int DW = DenseW<P8>::WORDS;
+    if (blockIdx.x == 0 && threadIdx.x == 0) import_reset(R);
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t d[DW], w[12 + P8 / 4];
         const uint4* src = reinterpret_cast<const uint4*>(in + j * (4 * DW));
@@ -198,8 +216,8 @@ k_import_dense(const __grid_constant__ DevTable T, const __grid_constant__ InitR
         for (int k = 0; k < DW / 4; ++k) { const uint4 v = src[k]; d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w; }
         const uint32_t pad = dense_unpack<P8>(d, w);
         if (pad != 0 || words_invalid_w<P8>(T, w) != 0) {
-            atomicAdd(&err[0], 1u);
-            atomicMax(&err[1], ~(uint32_t)(j > 0xFFFFFFFEull ? 0xFFFFFFFEull : j));
+            atomicAdd_system(&err[0], 1u);
+            atomicMax_system(&err[1], ~(uint32_t)(j > 0xFFFFFFFEull ? 0xFFFFFFFEull : j));
 #pragma unroll
             for (int k = 0; k < 12 + P8 / 4; ++k) w[k] = init.w[k];
         }

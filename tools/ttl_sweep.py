@@ -24,13 +24,34 @@ from game_engine_b200.batch import SessionBatch, Table  # noqa: E402
 from game_engine_b200.parallel import shard_range  # noqa: E402
 
 
+def render(rows, world):
+    lines = ["# two-truths-and-a-lie batch-size sweep (tools/ttl_sweep.py), %d GPU(s): whole games (34 steps) from fresh sessions" % world, "",
+             "GPU time = max over ranks of the CUDA-event time between barriers, best of 3; CPU = Oracle B (oracle/ge_oracle.c, OpenMP, all host "
+             "threads; rows above 2^24 sessions are linear extrapolations of the 2^24 run and say so).", "",
+             "| total sessions | single-step launches: steps/s | algorithmic GB/s per GPU | fused launch: steps/s | CPU steps/s | best GPU / CPU |",
+             "|---|---|---|---|---|---|"]
+    for r in rows:
+        f = ("%.3e" % r["fused"]["steps_per_s"]) if "fused" in r else "—"
+        c = r.get("cpu")
+        best_gpu = max(r["single_step"]["steps_per_s"], r.get("fused", {}).get("steps_per_s", 0))
+        cs = ("%.3e (%d threads%s)" % (c["steps_per_s"], c["threads"], ", extrapolated" if c["extrapolated"] else "")) if c else "—"
+        ratio = ("%.0fx" % (best_gpu / c["steps_per_s"])) if c else "—"
+        lines.append("| 2^%d | %.3e | %.0f | %s | %s | %s |" % (r["log2_sessions"], r["single_step"]["steps_per_s"], r["single_step"]["alg_GBps_per_gpu"], f, cs, ratio))
+    return "\n".join(lines) + "\n"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
+    ap.add_argument("--render", default="", help="render a saved JSON-lines output of this tool to --out (no GPU needed)")
     ap.add_argument("--min-log2", type=int, default=10)
     ap.add_argument("--max-log2", type=int, default=28)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    if a.render:
+        rows = [json.loads(x) for x in open(a.render) if x.startswith("{")]
+        open(a.out, "w").write(render(rows, rows[0]["gpus"]))
+        return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -116,19 +137,7 @@ def main():
         if rank == 0:
             print(json.dumps(row), flush=True)
     if rank == 0 and a.out:
-        lines = ["# two-truths-and-a-lie batch-size sweep (tools/ttl_sweep.py), %d GPU(s): whole games (34 steps) from fresh sessions" % world, "",
-                 "GPU time = max over ranks of the CUDA-event time between barriers, best of 3; CPU = Oracle B (oracle/ge_oracle.c, OpenMP, all host "
-                 "threads; rows above 2^24 sessions are linear extrapolations of the 2^24 run and say so).", "",
-                 "| total sessions | single-step launches: steps/s | algorithmic GB/s per GPU | fused launch: steps/s | CPU steps/s | GPU / CPU |",
-                 "|---|---|---|---|---|---|"]
-        for r in rows:
-            f = ("%.3e" % r["fused"]["steps_per_s"]) if "fused" in r else "—"
-            c = r.get("cpu")
-            best_gpu = max(r["single_step"]["steps_per_s"], r.get("fused", {}).get("steps_per_s", 0))
-            cs = ("%.3e (%d threads%s)" % (c["steps_per_s"], c["threads"], ", extrapolated" if c["extrapolated"] else "")) if c else "—"
-            ratio = ("%.0fx" % (best_gpu / c["steps_per_s"])) if c else "—"
-            lines.append("| 2^%d | %.3e | %.0f | %s | %s | %s |" % (r["log2_sessions"], r["single_step"]["steps_per_s"], r["single_step"]["alg_GBps_per_gpu"], f, cs, ratio))
-        open(a.out, "w").write("\n".join(lines) + "\n")
+        open(a.out, "w").write(render(rows, world))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
