@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgame_engine_b200.so")
+# GE_LIB selects another build of the same library (A/B experiments with build-time knobs); default: the in-tree build
+LIB_PATH = os.environ.get("GE_LIB") or os.path.join(_HERE, "libgame_engine_b200.so")
 
 STATS_LEN = 560
 GE_OK, GE_ERR_ARG, GE_ERR_CUDA, GE_ERR_UNSUPPORTED, GE_ERR_NOMEM = 0, -1, -2, -3, -4

@@ -26,6 +26,12 @@ struct WState {
 };
 
 constexpr int TPS_THREADS = 128;
+// resident CTAs per SM the werewolf kernels are compiled for (register budget = 65536 / (128 x this)); the 24/32-player
+// figure can be overridden at build time for occupancy experiments (-DGE_P32_CTAS=5)
+#ifndef GE_P32_CTAS
+#define GE_P32_CTAS 5
+#endif
+#define GE_W_CTAS(P8) ((P8) <= 8 ? 8 : (P8) <= 16 ? 6 : GE_P32_CTAS)
 
 // Per-thread table of the 12 predicate field masks (SPEC.md section 2) in shared memory, laid out
 // [field][thread] (conflict-free).  Predicates index it dynamically; this replaced a switch over the field
@@ -836,7 +842,7 @@ __device__ __forceinline__ void w_tps_publish(const SlotArgs& A, const BlockCoun
 }
 
 template <int P8, class Spec = void>
-__global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
+__global__ void __launch_bounds__(TPS_THREADS, GE_W_CTAS(P8))
 k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
     __shared__ WSmem<P8, 1> sm;
     extern __shared__ __align__(16) uint8_t dyn_smem[];       // sizeof(LightBulk) when the launch asked for STEP_LIGHT_BULK
@@ -850,7 +856,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
 
 // the run-time-table kernel with the human-seat path (batches that have people at the table)
 template <int P8>
-__global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
+__global__ void __launch_bounds__(TPS_THREADS, GE_W_CTAS(P8))
 k_step_w_tps_h(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
     __shared__ WSmem<P8, 1> sm;
     counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
@@ -868,7 +874,7 @@ k_step_w_tps_h(const __grid_constant__ DevTable T, const __grid_constant__ StepA
 // the ring kernel itself issues at 64 % of the scheduler peak (ncu, profiles/r02_ring_*), but the compaction and
 // re-initialisation launches that sit between ring passes on the single stream are no longer hidden.
 template <int P8, class Spec = void>
-__global__ void __launch_bounds__(TPS_THREADS, (P8 <= 8 ? 8 : P8 <= 16 ? 6 : 4))
+__global__ void __launch_bounds__(TPS_THREADS, GE_W_CTAS(P8))
 k_ring_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs C, const __grid_constant__ RingArgs R) {
     __shared__ WSmem<P8, GE_RING_MAX> sm;
     counters_init(sm.c, R.n, [&](int k) -> const SlotArgs& { return R.slot[k]; });

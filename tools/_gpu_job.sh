@@ -1,7 +1,11 @@
-python -m pytest tests/test_wire.py tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/r02q_tests.log 2>&1; echo tests rc=$?; tail -8 gpurun_out/r02q_tests.log | cut -c1-400
-for i in 1 2; do python bench.py --steps 300 --no-cpu-baseline > gpurun_out/r02q_bench$i.json 2>>gpurun_out/r02q_bench.err; done
-python -c "
-import json
-for m in ('1','2'):
-    d=json.load(open('gpurun_out/r02q_bench%s.json'%m)); e=d['e2e']; print(m, '%.4e'%d['value'], 'e2e %.3e'%e['value'], e['ms_per_call'], 'single %.3e'%e['single_step_round_trip']['value'])
-"
+# config 4 experiments on one GPU (2^23 sessions, the N=8 shard size): regroup cadence and occupancy of the 32-player kernel
+B="python bench.py --config 4 --sessions 8388608 --steps 300 --no-e2e --no-cpu-baseline"
+for rg in 5,3 3,3 2,3 1,3 1,2 1,4 2,4; do $B --regroup $rg 2>>gpurun_out/r02s.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('regroup $rg', '%.4e'%d['value'], 'frac %.3f'%d['roofline']['frac'], d['gpu_launches'])"; done
+for v in 5 6; do GE_LIB=$PWD/tools/_variants/libge_occ$v.so $B 2>>gpurun_out/r02s.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('occ $v cfg4', '%.4e'%d['value'], 'frac %.3f'%d['roofline']['frac'])"; done
+for v in 5 6; do GE_LIB=$PWD/tools/_variants/libge_occ$v.so python bench.py --players 32 --steps 300 --no-e2e --no-cpu-baseline 2>>gpurun_out/r02s.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('occ $v werewolf P32', '%.4e'%d['value'], 'frac %.3f'%d['roofline']['frac'])"; done
+python bench.py --players 32 --steps 300 --no-e2e --no-cpu-baseline 2>>gpurun_out/r02s.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('occ 4 werewolf P32', '%.4e'%d['value'], 'frac %.3f'%d['roofline']['frac'])"
+tail -3 gpurun_out/r02s.err
