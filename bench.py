@@ -85,6 +85,8 @@ def parse_args():
     ap.add_argument("--launch", default="streams", choices=["streams", "ring"],
                     help="streams: one step launch per batch, the ring's batches spread over --streams CUDA streams; "
                          "ring: ONE launch per pass over the ring on one stream (ge_step_ring, full-occupancy grid)")
+    ap.add_argument("--ring-streams", type=int, default=1, help="--launch ring: streams the ring is split over (one ring launch per stream per pass)")
+    ap.add_argument("--ring-ctas", type=int, default=4, help="--launch ring with several streams: CTAs per SM of each ring launch")
     ap.add_argument("--streams", type=int, default=None, help="CUDA streams the ring's independent batches are spread over")
     ap.add_argument("--ctas-per-sm", type=int, default=None,
                     help="persistent grid of a step launch = SMs x this (0 = occupancy limit); small grids let the launches "
@@ -402,7 +404,7 @@ def run_ours(a):
     # the ring's batches are independent sessions: batch i runs on stream i % NS so that one batch's launch
     # ramp / tail and near-empty late-game launches overlap with another batch's work
     merged = a.launch == "ring" and a.kernel != "coop"
-    NS = 1 if merged else max(1, min(a.streams, R))
+    NS = max(1, min(a.ring_streams if merged else a.streams, R))
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     stream = streams[0]
     torch.cuda.set_stream(stream)
@@ -414,7 +416,7 @@ def run_ours(a):
     ring = [SessionBatch(tab, N, first_session_id=sid_base(0, i), seed=a.seed, device=local_rank, kernel=a.kernel) for i in range(R)]
     for i, b in enumerate(ring):
         b.set_stream(streams[i % NS].cuda_stream)
-        b.set_grid(0 if merged else a.ctas_per_sm)
+        b.set_grid((a.ring_ctas if NS > 1 else 0) if merged else a.ctas_per_sm)
         if a.light_bulk:
             b.set_option("light_bulk", 1)
         if a.regroup:
@@ -440,10 +442,18 @@ def run_ours(a):
     k_global = 0
     resets = 0
 
+    def ring_groups(batches):
+        """--launch ring with several streams: the batches of one stream form one ring launch"""
+        groups = {}
+        for b in batches:
+            groups.setdefault(ring.index(b) % NS, []).append(b)
+        return list(groups.values())
+
     def step_each(batches):
-        """one step of each batch of the list: a launch per batch, or (--launch ring) one launch for the list"""
+        """one step of each batch of the list: a launch per batch, or (--launch ring) one launch per stream's share of the list"""
         if merged and batches:
-            step_ring(batches, 1)
+            for g in ring_groups(batches):
+                step_ring(g, 1)
         else:
             for b in batches:
                 b.step(1)
@@ -467,8 +477,12 @@ def run_ours(a):
             head = min(run, (R - i) % R)              # finish the current round first
             step_each([ring[(i + j) % R] for j in range(head)])
             full, tail = divmod(run - head, R)
-            if full:
-                (step_ring if merged else step_many)(ring, full)
+            if full and merged:
+                for _ in range(full):
+                    for g in ring_groups(ring):
+                        step_ring(g, 1)
+            elif full:
+                step_many(ring, full)
             step_each(ring[:tail])
             for j in range(run):
                 age[(i + j) % R] += 1
@@ -656,7 +670,7 @@ def run_ours(a):
     per_gpu = counted_all / world / (ms_max * 1e-3)                       # counted steps per second per GPU
     achieved = per_gpu * B / 1e9
     kern = ring[0].kernel
-    step_launches = a.steps * (1 if merged else R)                        # step-kernel launches per GPU in the timed region
+    step_launches = a.steps * (NS if merged else R)                       # step-kernel launches per GPU in the timed region
     # physical DRAM traffic: bytes per counted step from the committed ncu capture of THIS workload (same table, players,
     # kernel and batch size; anything else is refused), times the live step rate
     tr = ncu_traffic(a.game, a.players, kern, N, R, S)
@@ -665,7 +679,7 @@ def run_ours(a):
             "traffic": (tr["bytes_per_step"] * counted_all / world / step_launches) if tr else None, "peak_source": peak_src,
             "frac_of_nominal_8000": achieved / 8000.0,         # BASELINE.md section 2 asks for the nominal figure too
             "algorithmic_bytes_per_step": B, "kernel": "k_%s_%s_%s" % ("ring" if merged else "step", "w" if cg.family == 1 else "t", "tps" if kern.startswith("tps") else kern),
-            "steps_per_launch": counted_all / world / step_launches, "launches_per_step": 1 if merged else R,
+            "steps_per_launch": counted_all / world / step_launches, "launches_per_step": NS if merged else R,
             "necessary_bytes_per_step": nec, "necessary_gbs": per_gpu * nec / 1e9, "frac_necessary": per_gpu * nec / 1e9 / peak,
             "note": "achieved = counted steps x 2S (SURVEY 8d: the whole record read and written every step); necessary = the columns "
                     "each phase must move (ge_table_phase_io) weighted by the visit histogram; dram_physical = what crossed the "
@@ -686,7 +700,7 @@ def run_ours(a):
         "config": {
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
             "baseline_config": a.config,
-            "light_path": "cp.async.bulk + mbarrier" if a.light_bulk else "LDG.128", "kernel": kern, "launch": "one ring launch per pass (ge_step_ring)" if merged else "one launch per batch", "streams": NS,
+            "light_path": "cp.async.bulk + mbarrier" if a.light_bulk else "LDG.128", "kernel": kern, "launch": ("%d ring launch(es) per pass (ge_step_ring)" % NS) if merged else "one launch per batch", "streams": NS,
             "ctas_per_sm": "occupancy limit" if merged else a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
             "steps_before_reinit": "when every game of the batch is over (device-side auto-reset, checked every 8 steps)" if auto else cap,
             "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,

@@ -89,6 +89,7 @@ struct ge_batch {
     step_fn fn[4];               // by kernel id (COOP, TPS, TPS_GENERIC)
     ring_fn rfn[4];              // ring-launch twins (thread-per-session kernels only)
     int grid[4], occ[4];         // persistent grid size / occupancy limit (CTAs per SM) per kernel id
+    int ctas_per_sm;             // ge_batch_set_grid's request (0 = the occupancy limit)
     uint64_t launches;
     uint32_t* d_hmask;            // human seats per session (NULL = all bots) and their inputs for the next step
     uint8_t* d_hchoice;
@@ -639,6 +640,7 @@ extern "C" int ge_batch_set_compaction(ge_batch* b, int every_n_steps, int min_d
 // the work available); 0 restores the occupancy limit.
 extern "C" int ge_batch_set_grid(ge_batch* b, int ctas_per_sm) {
     if (!b || ctas_per_sm < 0) return fail(GE_ERR_ARG, "bad arguments to ge_batch_set_grid");
+    b->ctas_per_sm = ctas_per_sm;
     for (int k = GE_KERNEL_COOP; k <= GE_KERNEL_TPS_GENERIC; ++k) {
         int per_sm = b->occ[k];
         if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
@@ -869,8 +871,11 @@ extern "C" int ge_step_ring(ge_batch** batches, int n_batches, int n_rounds) {
     uint64_t warps = 0;
     for (int i = 0; i < n_batches; ++i) if (batches[i]->n_tiles > warps) warps = batches[i]->n_tiles;
     uint64_t g = (warps + 3) / 4;
-    uint64_t cap = (uint64_t)b0->sm_count * b0->occ[b0->kernel];
-    if (const char* e = getenv("GE_RING_CTAS_PER_SM")) { const int v = atoi(e); if (v > 0 && v < b0->occ[b0->kernel]) cap = (uint64_t)b0->sm_count * v; }
+    // (ge_batch_set_grid on the first batch asks for a smaller grid, so that ring launches of OTHER rings on other streams
+    // can be resident at the same time)
+    int per_sm = b0->occ[b0->kernel];
+    if (b0->ctas_per_sm > 0 && b0->ctas_per_sm < per_sm) per_sm = b0->ctas_per_sm;
+    const uint64_t cap = (uint64_t)b0->sm_count * per_sm;
     if (g > cap) g = cap;
     for (int r = 0; r < n_rounds; ++r) {
         RingArgs ra;

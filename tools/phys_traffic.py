@@ -64,6 +64,8 @@ def main():
     step_k = [g for k, g in agg.items() if "k_step_" in k or "k_ring_" in k]
     n_step_launches = sum(g["n"] for g in step_k)
     key = "%s_p%d_%s_n%d" % (run["game"], run["players"], a.kernel, run["sessions_per_batch"])
+    if run.get("launch", "streams") != "streams":              # the ring launch is profiled for DESIGN, bench.py looks up the default mode
+        key += "_" + run["launch"]
     entry = {
         "read_bytes_per_step": rd / steps, "write_bytes_per_step": wr / steps, "bytes_per_step": (rd + wr) / steps,
         "bytes_per_step_launch": (rd + wr) / max(1, n_step_launches), "warp_instructions_per_step": inst / steps,

@@ -3,8 +3,7 @@
 
     python tools/summarize_ncu.py --launches gpurun_out/launches_r01.csv --rep gpurun_out/prof_r01_tps.ncu-rep \
         --tag r01 --workload "werewolf-(mafia)_p8_tps" --cmd "python bench.py --steps 240 ..."
-Writes profiles/<tag>_launches.md, profiles/<tag>_full_<kernel>.md and updates profiles/traffic.json
-(average dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel)."""
+Writes profiles/<tag>_launches.md and profiles/<tag>_full_<kernel>.md (physical DRAM traffic: tools/phys_traffic.py)."""
 import argparse
 import collections
 import csv
@@ -74,13 +73,8 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "%s_launches.md" % a.tag), "w") as f:
         f.write("\n".join(out) + "\n")
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    if traffic is not None:
-        tj[a.workload] = traffic
-        tj[a.workload + "__source"] = "%s: mean dram__bytes_read.sum + dram__bytes_write.sum per %s launch over %d launches" % (
-            os.path.basename(a.launches), a.kernel, len([1 for e in data.values() if a.kernel in e["k"]]))
-        json.dump(tj, open(tpath, "w"), indent=1, sort_keys=True)
+    # (profiles/traffic.json is written by tools/phys_traffic.py from a capture with the caches left alone; the cold-cache
+    # per-launch read bytes of this listing do not include write-backs and are not used by bench.py)
     print("\n".join(out[:16]))
     print("traffic per launch:", traffic)
     if a.rep:
@@ -93,7 +87,10 @@ def main():
                 "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
                 "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
                 "sm__cycles_active.avg", "sm__cycles_elapsed.max", "launch__registers_per_thread", "launch__grid_size",
-                "launch__occupancy_limit_registers", "lts__t_sector_hit_rate.pct"]
+                "launch__occupancy_limit_registers", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"] + [
+                "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % r for r in (
+                    "long_scoreboard", "wait", "short_scoreboard", "not_selected", "math_pipe_throttle", "no_instruction",
+                    "branch_resolving", "barrier", "dispatch_stall", "lg_throttle", "mio_throttle")]
         lines = ["# %s — ncu `--set full` capture of `%s`" % (a.tag, a.kernel), "",
                  "Command (after the same command exited 0 without ncu): `ncu --set full --clock-control none --import-source on "
                  "-k regex:%s ... %s`" % (a.kernel, a.cmd), "", "| metric | unit | " + " | ".join("L%d" % i for i in range(len(rr) - 2)) + " |",
