@@ -46,6 +46,7 @@ struct ge_table {
     uint32_t init_words[40];     // initial device record
     void (*spec_fn)(const DevTable, const StepArgs);   // build-time specialised step kernel for this exact table, or NULL
     void (*spec_ring_fn)(const DevTable, const StepArgs, const RingArgs);   // its ring-launch twin
+    void (*spec_tiled_fn)(const DevTable, const StepArgs);                  // its twin with per-tile column needs (werewolf)
 };
 
 typedef void (*step_fn)(const DevTable, const StepArgs);
@@ -80,6 +81,8 @@ struct ge_batch {
     uint32_t* d_rg;               // RG_WORDS control words (histogram, trigger, bases, cursors)
     uint8_t* d_rg_tiles;          // scratch session store (same size as d_tiles)
     uint32_t* d_rg_origin;
+    uint32_t* d_tile_present;     // per-tile phase presence (SlotArgs::tile_present), kept while regrouping is on
+    bool tile_valid;              // the words describe the records as they are now (false after a reset / import / re-order)
     int regroup_every, rg_mixed_shift;
     uint64_t sid_stride;          // auto-reset: session ids of device epoch e start at first_sid + e * sid_stride (0 = off)
     uint32_t* d_presence;         // 3 rotating phase-presence words (StepArgs::presence)
@@ -303,18 +306,20 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
 }
 
 // build-time specialised kernels (ge_spec_gen.cuh), matched by byte-identical table blobs
-struct SpecEntry { const unsigned char* blob; size_t len; step_fn fn; ring_fn rfn; };
+struct SpecEntry { const unsigned char* blob; size_t len; step_fn fn; ring_fn rfn; step_fn tfn; };
 template <int FAM, int BUCKET, class S> struct SpecKernel;
 template <int BUCKET, class S> struct SpecKernel<FAM_WEREWOLF, BUCKET, S> {
     static step_fn fn() { return (step_fn)k_step_w_tps<BUCKET, S>; }
     static ring_fn rfn() { return (ring_fn)k_ring_w_tps<BUCKET, S>; }
+    static step_fn tfn() { return (step_fn)k_step_w_tps_tiled<BUCKET, S>; }
 };
 template <int BUCKET, class S> struct SpecKernel<FAM_TTL, BUCKET, S> {
     static step_fn fn() { return (step_fn)k_step_t_tps<BUCKET, S>; }
     static ring_fn rfn() { return (ring_fn)k_ring_t_tps<BUCKET, S>; }
+    static step_fn tfn() { return nullptr; }
 };
-#define GE_SPEC_ENTRY(S, FAM, BUCKET) {spec::S##_blob, sizeof(spec::S##_blob), SpecKernel<FAM, BUCKET, spec::S>::fn(), SpecKernel<FAM, BUCKET, spec::S>::rfn()},
-static const SpecEntry g_specs[] = { GE_SPEC_LIST(GE_SPEC_ENTRY) {nullptr, 0, nullptr, nullptr} };
+#define GE_SPEC_ENTRY(S, FAM, BUCKET) {spec::S##_blob, sizeof(spec::S##_blob), SpecKernel<FAM, BUCKET, spec::S>::fn(), SpecKernel<FAM, BUCKET, spec::S>::rfn(), SpecKernel<FAM, BUCKET, spec::S>::tfn()},
+static const SpecEntry g_specs[] = { GE_SPEC_LIST(GE_SPEC_ENTRY) {nullptr, 0, nullptr, nullptr, nullptr} };
 
 extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
     if (!out) return fail(GE_ERR_ARG, "out is NULL");
@@ -324,9 +329,10 @@ extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
     if (rc != GE_OK) { delete t; return rc; }
     t->spec_fn = nullptr;
     t->spec_ring_fn = nullptr;
+    t->spec_tiled_fn = nullptr;
     const size_t used = sizeof(ge_table_header_t) + (size_t)t->dev.h.n_phases * sizeof(ge_phase_t) + (size_t)t->dev.h.n_preds * sizeof(ge_pred_t);
     for (const SpecEntry* e = g_specs; e->blob; ++e)
-        if (e->len == used && memcmp(e->blob, blob, used) == 0) { t->spec_fn = e->fn; t->spec_ring_fn = e->rfn; }
+        if (e->len == used && memcmp(e->blob, blob, used) == 0) { t->spec_fn = e->fn; t->spec_ring_fn = e->rfn; t->spec_tiled_fn = e->tfn; }
     *out = t;
     return GE_OK;
 }
@@ -362,6 +368,18 @@ static step_fn pick_fn(const ge_table* t, int kernel) {
         case 16: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<16> : (step_fn)k_step_t_tps<16>;
         case 32: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<32> : (step_fn)k_step_t_tps<32>;
         }
+    }
+    return nullptr;
+}
+
+static step_fn pick_tiled_fn(const ge_table* t, int kernel) {
+    if (t->family != FAM_WEREWOLF) return nullptr;
+    if (kernel == GE_KERNEL_TPS && t->spec_tiled_fn) return t->spec_tiled_fn;
+    switch (t->bucket) {
+    case 8: return (step_fn)k_step_w_tps_tiled<8>;
+    case 16: return (step_fn)k_step_w_tps_tiled<16>;
+    case 24: return (step_fn)k_step_w_tps_tiled<24>;
+    case 32: return (step_fn)k_step_w_tps_tiled<32>;
     }
     return nullptr;
 }
@@ -432,6 +450,7 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
     CU(cudaGetLastError());
     b->compacted = false;
     b->since_compact = 0;
+    b->tile_valid = false;
     return GE_OK;
 }
 
@@ -540,7 +559,7 @@ extern "C" void ge_batch_destroy(ge_batch* b) {
     if (b->own_stream) { cudaStreamSynchronize(b->own_stream); cudaStreamDestroy(b->own_stream); }
     cudaFree(b->d_tiles); cudaFree(b->d_stats); cudaFree(b->d_stats_out); cudaFree(b->d_stage); cudaFree(b->d_presence);
     cudaFree(b->d_origin); cudaFree(b->d_live_mask); cudaFree(b->d_prefix); cudaFree(b->d_blk); cudaFree(b->d_cstate); cudaFreeHost(b->h_hint);
-    cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin);
+    cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin); cudaFree(b->d_tile_present);
     cudaFreeHost(b->h_err); if (b->fence) cudaEventDestroy(b->fence);
     cudaFree(b->d_hmask); cudaFree(b->d_hchoice);
     delete b;
@@ -664,9 +683,11 @@ extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixe
         if (e == cudaSuccess) e = cudaMemset(b->d_rg, 0, RG_WORDS * sizeof(uint32_t));
         if (e == cudaSuccess) e = cudaMalloc(&b->d_rg_tiles, b->tiles_bytes);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_rg_origin, b->n_tiles * 32 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_tile_present, (b->n_tiles + 1) * sizeof(uint32_t));
+        b->tile_valid = false;
         if (e != cudaSuccess) {
-            cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin);
-            b->d_rg = nullptr; b->d_rg_tiles = nullptr; b->d_rg_origin = nullptr;
+            cudaFree(b->d_rg); cudaFree(b->d_rg_tiles); cudaFree(b->d_rg_origin); cudaFree(b->d_tile_present);
+            b->d_rg = nullptr; b->d_rg_tiles = nullptr; b->d_rg_origin = nullptr; b->d_tile_present = nullptr;
             return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_set_regroup: ") + cudaGetErrorString(e));
         }
     }
@@ -756,7 +777,7 @@ static int enqueue_regroup(ge_batch* b, cudaStream_t st) {
     uint64_t g = (b->n + 1023) / 1024;
     if (g > (uint64_t)b->sm_count * 2) g = (uint64_t)b->sm_count * 2;
     k_regroup_scatter<<<(int)g, 1024, 0, st>>>(b->d_tiles, S, b->d_origin, b->d_rg, b->tab->dev.nonterm, b->d_rg_tiles, b->d_rg_origin);
-    k_regroup_copyback<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->d_tiles, S, b->d_origin, b->d_rg, b->d_rg_tiles, b->d_rg_origin, b->d_cstate, b->d_hint);
+    k_regroup_copyback<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->d_tiles, S, b->d_origin, b->d_rg, b->d_rg_tiles, b->d_rg_origin, b->d_cstate, b->d_hint, b->d_tile_present);
     CU(cudaGetLastError());
     b->launches += 3;
     b->since_compact = 0;
@@ -790,6 +811,11 @@ static void fill_slot(ge_batch* b, SlotArgs& a, bool count_live, bool regroup) {
     a.n_active = b->d_cstate; a.live_mask = b->d_live_mask; a.live_count = b->d_cstate + 5;
     a.sid_stride = b->sid_stride;
     a.rg = regroup ? b->d_rg : nullptr;
+    // per-tile column needs ride on regrouping (tables whose sessions de-synchronise); the device-side auto-reset
+    // rewrites every record behind the host's back, so the words are not trusted while it is on
+    a.tile_present_out = (regroup && b->sid_stride == 0) ? b->d_tile_present : nullptr;
+    a.tile_present = (a.tile_present_out && b->tile_valid) ? b->d_tile_present : nullptr;
+    b->tile_valid = a.tile_present_out != nullptr;          // this launch writes the word of every tile it steps
     a.count_live = count_live ? 1u : 0u;
     a.launch_idx = b->launch_idx++;
     a.presence_override = b->next_override;
@@ -802,7 +828,9 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
     if (b->d_hmask && (b->kernel == GE_KERNEL_COOP || steps_per_launch > 1))
         return fail(GE_ERR_UNSUPPORTED, "human seats are served by single-step launches of the thread-per-session kernels");
     // a batch with people at the table runs the run-time-table kernel that carries the human-seat path
-    const step_fn fn = b->d_hmask ? pick_human_fn(b->tab) : b->fn[b->kernel];
+    const bool regroup_on = b->regroup_every > 0 && b->kernel != GE_KERNEL_COOP && steps_per_launch == 1;
+    const bool tiled = regroup_on && b->sid_stride == 0 && !b->d_hmask && pick_tiled_fn(b->tab, b->kernel) != nullptr;
+    const step_fn fn = b->d_hmask ? pick_human_fn(b->tab) : tiled ? pick_tiled_fn(b->tab, b->kernel) : b->fn[b->kernel];
     StepArgs a;
     fill_common(b, a, steps_per_launch);
     // phase regrouping replaces the swap compaction (it also moves finished games behind the live ones)
@@ -816,6 +844,7 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
         const bool regroup_after = regroup && b->since_compact + 1 >= b->regroup_every;
         const bool compact_after = !regroup && b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
         fill_slot(b, a, compact_after || regroup_after, regroup);
+        if (!tiled) { a.tile_present = nullptr; a.tile_present_out = nullptr; b->tile_valid = false; }
         // the bulk-copy variant of the light path stages its tiles in dynamic shared memory (werewolf single-batch kernels)
         const bool bulk = (a.flags & STEP_LIGHT_BULK) && b->tab->family == FAM_WEREWOLF && !b->d_hmask && b->kernel != GE_KERNEL_COOP;
         if (!bulk) a.flags &= ~(uint32_t)STEP_LIGHT_BULK;
@@ -1007,6 +1036,7 @@ static int restore_order(ge_batch* b, bool keep_records) {
         b->launches += 2;
     }
     b->compacted = false;
+    b->tile_valid = false;
     b->epoch++;
     k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch, 1);
     CU(cudaGetLastError());
@@ -1026,6 +1056,7 @@ static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void*
     // import overwrites every record, so only the bookkeeping is reset — by the import kernel itself.
     const bool whole = first == 0 && count == b->n;
     ImportReset R{b->d_presence, nullptr, b->n, 0};
+    b->tile_valid = false;
     if (whole) {
         b->compacted = false;
         b->epoch++;

@@ -63,6 +63,12 @@ struct SlotArgs {
     // thread-per-session kernel also adds, per phase index, the sessions that entered it to rg[0..31] and the
     // number of tiles whose live sessions sit in more than one phase to rg[32].  NULL = not collected.
     uint32_t* rg;
+    // Per-TILE phase presence (tables whose sessions de-synchronise, i.e. batches with phase regrouping): word t = the
+    // phases the 32 sessions of tile t were in after the previous launch.  tile_present_out (NULL = not kept) is written
+    // by every launch; tile_present (NULL = not valid: first launch after a reset / import) lets a tile load only the
+    // columns ITS phases need instead of the union over the whole batch.
+    const uint32_t* tile_present;
+    uint32_t* tile_present_out;
     // Human seats (SPEC.md section 1, D3h): human_mask[i] = seats of session i (original index) played by people,
     // human_choice[i * stride + p] = the input of seat p+1 for THIS step (0xFF = has not acted).  NULL = all bots.
     const uint32_t* human_mask;

@@ -595,7 +595,7 @@ k_regroup_scatter(const uint8_t* __restrict__ tiles, uint32_t S, const uint32_t*
 
 __global__ void k_regroup_copyback(uint8_t* __restrict__ tiles, uint32_t S, uint32_t* __restrict__ origin, const uint32_t* __restrict__ rg,
                                    const uint8_t* __restrict__ in_tiles, const uint32_t* __restrict__ in_origin,
-                                   const unsigned long long* cstate, unsigned long long* hint) {
+                                   const unsigned long long* cstate, unsigned long long* hint, uint32_t* tile_present) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && hint) {           // progress hint for the host (see k_compact_swap)
         ((volatile unsigned long long*)hint)[0] = cstate[0];
         __threadfence_system();
@@ -604,13 +604,30 @@ __global__ void k_regroup_copyback(uint8_t* __restrict__ tiles, uint32_t S, uint
     const uint32_t old = rg[RG_OLD];
     const uint32_t n16 = S / 16;
     const bool half = (S % 16) != 0;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < old; slot += gridDim.x * blockDim.x) {
+    // whole tiles (a warp = the 32 slots of one tile), so that the per-tile phase-presence word of every tile the sort
+    // touched can be rebuilt on the way: the step kernel's per-tile column needs stay valid across a regroup
+    const uint32_t end = (old + 31u) & ~31u;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < end; slot += gridDim.x * blockDim.x) {
         const uint64_t off = (uint64_t)(slot >> 5) * (32ull * S);
-        for (uint32_t c = 0; c < n16; ++c)
-            *reinterpret_cast<uint4*>(tiles + off + c * 512u + (slot & 31) * 16u) = *reinterpret_cast<const uint4*>(in_tiles + off + c * 512u + (slot & 31) * 16u);
-        if (half)
-            *reinterpret_cast<uint2*>(tiles + off + n16 * 512u + (slot & 31) * 8u) = *reinterpret_cast<const uint2*>(in_tiles + off + n16 * 512u + (slot & 31) * 8u);
-        origin[slot] = in_origin[slot];
+        uint32_t ph;
+        if (slot < old) {
+            uint4 h = make_uint4(0, 0, 0, 0);
+            for (uint32_t c = 0; c < n16; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(in_tiles + off + c * 512u + (slot & 31) * 16u);
+                if (c == 0) h = v;
+                *reinterpret_cast<uint4*>(tiles + off + c * 512u + (slot & 31) * 16u) = v;
+            }
+            if (half)
+                *reinterpret_cast<uint2*>(tiles + off + n16 * 512u + (slot & 31) * 8u) = *reinterpret_cast<const uint2*>(in_tiles + off + n16 * 512u + (slot & 31) * 8u);
+            origin[slot] = in_origin[slot];
+            ph = h.x & 31u;
+        } else {                                                  // beyond the sorted prefix: the record stays, its phase still counts
+            ph = *reinterpret_cast<const uint32_t*>(tiles + off + (slot & 31) * 16u) & 31u;
+        }
+        if (tile_present) {
+            const uint32_t bits = __reduce_or_sync(0xFFFFFFFFu, 1u << ph);
+            if ((threadIdx.x & 31) == 0) tile_present[slot >> 5] = bits;
+        }
     }
 }
 

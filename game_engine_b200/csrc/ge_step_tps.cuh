@@ -635,7 +635,9 @@ struct LightBulk {
 // build time (the host only selects this instantiation when the blobs are byte-identical).
 // HUM: the batch has human seats (SPEC D3h); only the run-time-table instantiations k_step_*_tps_h carry that path, so
 // the all-bot kernels are exactly what they were.
-template <int P8, class Spec, bool HUM = false>
+// TILED: per-tile column needs (batches with phase regrouping); its own instantiations (k_step_w_tps_tiled), so the
+// lockstep kernels do not carry the extra words and branches (measured: -2.3 % on the headline when they did).
+template <int P8, class Spec, bool HUM = false, bool TILED = false>
 __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C, const SlotArgs& A, BlockCounters& bc,
                                             uint32_t (*s_fields)[TPS_THREADS], uint8_t* s_lut_col, LightBulk* lb = nullptr) {
     constexpr int S = 48 + P8;
@@ -647,11 +649,10 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     // which column groups can any session of this batch need?  (bit0 C1, bit1 C2, bit2 player bytes, bit3 session id)
     const uint32_t present_in = bc.present_in;
-    const uint32_t need = C.n_steps > 1 ? 15u : need_of(T, present_in);
+    const uint32_t need_batch = C.n_steps > 1 ? 15u : need_of(T, present_in);
     const uint64_t n_act = bc.n_act;
     const uint64_t sid0 = bc.sid0;
     const uint32_t n_tiles_act = (uint32_t)((n_act + 31) >> 5);
-    const bool use_origin = A.origin != nullptr && (need & 8);
     const FieldTable F{s_fields, (int)threadIdx.x, s_lut_col};
     uint32_t present_out = 0, live_cnt = 0, mixed = 0;
     VisitAcc visits;
@@ -661,7 +662,7 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
     const uint32_t full_tiles = (uint32_t)(n_act >> 5), rem = (uint32_t)n_act & 31u;
     const uint64_t tile_stride = (uint64_t)nwarps * (32 * S);
     uint8_t* base = A.tiles + (uint64_t)warp0 * (32 * S) + lane * 16;      // column c of this lane: base + c * 512
-    if (need == 0) {
+    if (need_batch == 0) {
         // ---- light path: every present phase touches column 0 only.  Four tiles in flight per warp.
         // Sessions move in lockstep, so usually ONE non-terminal phase x0 is present: its single successor is
         // resolved once here and the common lane only rewrites the header word.
@@ -725,6 +726,7 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
                         visits.count += 32;
                         present_out |= 1u << y0;
                         lm = y0_live ? 0xFFFFFFFFu : 0u;
+                        if (TILED && A.tile_present_out != nullptr && lane == 0) A.tile_present_out[t] = 1u << y0;
                     } else {
                         int np = -1;
                         if (fast) {
@@ -738,6 +740,10 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
                         mixed += visits.add(s_visits, np, lane) > 1;
                         if (in_range) present_out |= 1u << (c[j].x & 31);
                         lm = __ballot_sync(0xFFFFFFFFu, in_range && ((T.nonterm >> (c[j].x & 31)) & 1u));
+                        if (TILED && A.tile_present_out != nullptr) {
+                            const uint32_t bits = __reduce_or_sync(0xFFFFFFFFu, in_range ? 1u << (c[j].x & 31) : 0u);
+                            if (lane == 0) A.tile_present_out[t] = bits;
+                        }
                     }
                     if (lane == 0) A.live_mask[t] = lm;
                     live_cnt += __popc(lm);
@@ -745,10 +751,27 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             }
         }
     } else {
+        // Per-tile column needs (batches with phase regrouping): between regroups a tile holds one or two phases while
+        // the batch as a whole holds many, so the union `need` would make every tile move every column.  The words are
+        // read two tiles ahead (one for this tile's loads, one for the next tile's prefetch).
+        const uint32_t* tp = (TILED && C.n_steps == 1) ? A.tile_present : nullptr;
+        uint32_t w_cur = 0, w_nxt = 0;
+        if (tp) {
+            if (warp0 < n_tiles_act) w_cur = tp[warp0];
+            if (warp0 + nwarps < n_tiles_act) w_nxt = tp[warp0 + nwarps];
+        }
         for (uint32_t tile = warp0; tile < n_tiles_act; tile += nwarps, base += tile_stride) {
+            uint32_t need = need_batch, need_next = need_batch;
+            if (tp) {
+                uint32_t w_nn = 0;
+                if (tile + 2 * nwarps < n_tiles_act) w_nn = tp[tile + 2 * nwarps];
+                need = need_of(T, w_cur) & need_batch;
+                need_next = need_of(T, w_nxt) & need_batch;
+                w_cur = w_nxt; w_nxt = w_nn;
+            }
             const bool in_range = tile < full_tiles || (uint32_t)lane < rem;
             uint32_t org = tile * 32u + lane;
-            if (use_origin && in_range) org = A.origin[org];
+            if (A.origin != nullptr && (need & 8) && in_range) org = A.origin[org];
             WState<P8> s;
             // all loads are issued up front (no dependent second round trip)
             const uint4 c0 = ld128(base);
@@ -774,9 +797,9 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             if (tile + nwarps < n_tiles_act) {
                 const uint8_t* nb = base + tile_stride;
                 prefetch_l1(nb);
-                if (need & 1) prefetch_l1(nb + 512);
-                if (need & 2) prefetch_l1(nb + 1024);
-                if (need & 4) {
+                if (need_next & 1) prefetch_l1(nb + 512);
+                if (need_next & 2) prefetch_l1(nb + 1024);
+                if (need_next & 4) {
 #pragma unroll
                     for (int c = 0; c < NT16; ++c) prefetch_l1(nb + (3 + c) * 512);
                     if (THALF) prefetch_l1(base8 + tile_stride);
@@ -809,6 +832,10 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             if (in_range) present_out |= 1u << (s.h0 & 31);
             const uint32_t lm = __ballot_sync(0xFFFFFFFFu, in_range && ((T.nonterm >> (s.h0 & 31)) & 1u));
             if (lane == 0) A.live_mask[tile] = lm;
+            if (TILED && A.tile_present_out != nullptr) {          // what the next launch may skip for this tile
+                const uint32_t bits = __reduce_or_sync(0xFFFFFFFFu, in_range ? 1u << (s.h0 & 31) : 0u);
+                if (lane == 0) A.tile_present_out[tile] = bits;
+            }
             live_cnt += __popc(lm);
             if (dirty & DIRTY_C0) st128(base, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
             if (dirty & DIRTY_C1) st128(base + 512, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
@@ -850,6 +877,18 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
     w_tps_tiles<P8, Spec>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0], lb);
+    __syncthreads();
+    w_tps_publish(A, sm.c[0]);
+}
+
+// the step kernel with per-tile column needs (batches whose sessions de-synchronise: phase regrouping on)
+template <int P8, class Spec = void>
+__global__ void __launch_bounds__(TPS_THREADS, GE_W_CTAS(P8))
+k_step_w_tps_tiled(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
+    __shared__ WSmem<P8, 1> sm;
+    counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
+    __syncthreads();
+    w_tps_tiles<P8, Spec, false, true>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
     __syncthreads();
     w_tps_publish(A, sm.c[0]);
 }

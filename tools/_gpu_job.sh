@@ -1,5 +1,12 @@
-CMD="python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e"
-$CMD > gpurun_out/r02u_plain.json 2> gpurun_out/r02u_plain.err && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02u_launches.csv $CMD > gpurun_out/r02u_ncu1.log 2>&1; echo launches rc=$?
-ncu --set full --clock-control none --import-source on -k regex:k_step_w_tps -s 60 -c 6 -o gpurun_out/r02u_full $CMD > gpurun_out/r02u_ncu2.log 2>&1; echo full rc=$?
-python tools/range_profile.py --launch ring --steps 56 > gpurun_out/r02u_ring_plain.json 2>/dev/null && ncu --cache-control none --clock-control none --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum --csv --log-file gpurun_out/r02u_ring_phys.csv python tools/range_profile.py --launch ring --steps 56 > gpurun_out/r02u_ring_phys.log 2>&1; echo ringphys rc=$?
-ls -la gpurun_out/ | tail -8
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py tests/test_fuzz_tables.py tests/test_humans.py -m gpu -x -q > gpurun_out/r02v_tests.log 2>&1; echo tests rc=$?; tail -8 gpurun_out/r02v_tests.log | cut -c1-400
+B="python bench.py --steps 300 --no-e2e --no-cpu-baseline"
+$B --config 4 --sessions 8388608 2>>gpurun_out/r02v.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('cfg4 n23', '%.4e'%d['value'], 'frac %.3f'%d['roofline']['frac'])"
+$B --config 4 2>>gpurun_out/r02v.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('cfg4 n26', '%.4e'%d['value'], 'frac %.3f'%d['roofline']['frac'])"
+$B --game werewolf-revote --players 8 2>>gpurun_out/r02v.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('revote p8', '%.4e'%d['value'], 'frac %.3f'%d['roofline']['frac'])"
+python bench.py --steps 1000 --no-e2e --no-cpu-baseline 2>>gpurun_out/r02v.err | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('cfg2', '%.4e'%d['value'])"
+bash tools/capture_traffic.sh r02v_cfg4_n23 --game werewolf-revote --players 32 --sessions 8388608 --ring 1 --streams 1 --ctas-per-sm 0
+tail -3 gpurun_out/r02v.err
