@@ -637,6 +637,7 @@ extern "C" int ge_batch_set_kernel(ge_batch* b, int kernel) {
     if (!b || kernel < GE_KERNEL_AUTO || kernel > GE_KERNEL_TPS_GENERIC) return fail(GE_ERR_ARG, "bad kernel id");
     kernel = kernel == GE_KERNEL_AUTO ? GE_KERNEL_TPS : kernel;
     if (kernel == GE_KERNEL_COOP && b->d_hmask) return fail(GE_ERR_UNSUPPORTED, "human seats are served by the thread-per-session kernels");
+    if (kernel == GE_KERNEL_COOP && b->sid_stride != 0) return fail(GE_ERR_UNSUPPORTED, "auto-reset rides on the thread-per-session kernels");
     if (kernel == GE_KERNEL_COOP && b->kernel != GE_KERNEL_COOP) {
         // the lane-per-player kernels walk every slot in session order: undo any compaction first
         CU(cudaSetDevice(b->device));
@@ -700,6 +701,7 @@ extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixe
 extern "C" int ge_batch_set_autoreset(ge_batch* b, uint64_t sid_stride) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     if (sid_stride != 0 && sid_stride < b->n) return fail(GE_ERR_ARG, "sid_stride must be 0 (off) or >= n_sessions (ids of different epochs must not overlap)");
+    if (sid_stride != 0 && b->kernel == GE_KERNEL_COOP) return fail(GE_ERR_UNSUPPORTED, "auto-reset rides on the thread-per-session kernels (the lane-per-player kernels do not follow device epochs)");
     b->sid_stride = sid_stride;
     if (sid_stride != 0 && b->compact_every == 0 && b->regroup_every == 0 && b->scan_blocks <= 1024)
         b->compact_every = 8;                 // the check that notices "every game is over" rides on compaction
