@@ -596,8 +596,8 @@ def run_ours(a):
         # The public host-buffer call on the same 2^20 sessions, split into NSUB sub-batches driven with
         # run_host_async so that H2D, the steps and D2H of different sub-batches overlap (two copy engines + SMs).
         NSUB = max(1, a.e2e_subs)
-        NE = min(N, 1 << 20)                                  # sessions per end-to-end call (bounded: 2 x NE x W bytes of pinned memory)
-        sub = NE // NSUB
+        sub = min(N, 1 << 20) // NSUB
+        NE = sub * NSUB                                       # sessions per end-to-end call (bounded: 2 x NE x W bytes of pinned memory)
         subs = [SessionBatch(tab, sub, first_session_id=sid_base(1 << 20, 0) + j * sub, seed=a.seed, device=local_rank, kernel=a.kernel)
                 for j in range(NSUB)]
         for sb in subs:

@@ -7,8 +7,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "ge_common.cuh"
 #include "ge_step_tps.cuh"
@@ -960,10 +964,105 @@ extern "C" int ge_step(ge_batch* b, int n_steps, void* cuda_stream) {
     return rc;
 }
 
+// ---- host-side launch workers of ge_step_many --------------------------------------------------------------------
+// A step launch of a 2^20-session batch is ~8 us of device time in the co-resident state, so a ring of 8 batches wants
+// ~190 000 launches per second (steps + compaction checks): as much as ONE host thread can enqueue (4-7 us per launch
+// with this parameter block), and on a slower host the device starves (measured: 4.99e10 instead of 6.2e10 steps/s
+// with enqueue time > device time).  The batches of a ring are independent and sit on their own streams, so their
+// launch sequences can be enqueued by different host threads: a small persistent pool, worker w takes batches
+// w, w + T, ... (a batch always goes to the same worker, so its own launches stay in order).  GE_STEP_THREADS sets
+// T (default 4, 1 = the calling thread only).
+namespace {
+struct StepPool {
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    std::vector<std::thread> workers;
+    ge_batch** batches = nullptr;
+    int n = 0, rounds = 0, T = 1, pending = 0;
+    unsigned long long gen = 0;
+    bool stop = false;
+    int rc[16];
+    std::string err[16];
+
+    void share(int w) {
+        int cur_dev = -1, r_ = GE_OK;
+        for (int r = 0; r < rounds && r_ == GE_OK; ++r)
+            for (int i = w; i < n && r_ == GE_OK; i += T) {
+                ge_batch* b = batches[i];
+                if (b->device != cur_dev) {
+                    if (cudaSetDevice(b->device) != cudaSuccess) { r_ = fail(GE_ERR_CUDA, "cudaSetDevice failed in a launch worker"); break; }
+                    cur_dev = b->device;
+                }
+                r_ = launch_steps(b, 1, 1, b->stream);
+            }
+        rc[w] = r_;
+        if (r_ != GE_OK) err[w] = g_err;
+    }
+    void loop(int w) {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_go.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+            }
+            share(w);
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    explicit StepPool(int t) : T(t) {
+        for (int w = 1; w < T; ++w) workers.emplace_back([this, w] { loop(w); });
+    }
+    ~StepPool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv_go.notify_all();
+        for (auto& t : workers) t.join();
+    }
+    int run(ge_batch** b, int n_, int rounds_) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            batches = b; n = n_; rounds = rounds_; pending = T - 1; ++gen;
+        }
+        cv_go.notify_all();
+        share(0);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        for (int w = 0; w < T; ++w)
+            if (rc[w] != GE_OK) return fail(rc[w], err[w]);
+        return GE_OK;
+    }
+};
+std::mutex g_pool_mutex;
+StepPool* g_pool = nullptr;
+int step_threads() {
+    static const int t = [] {
+        const char* e = getenv("GE_STEP_THREADS");
+        int v = e ? atoi(e) : 4;
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw && (unsigned)v > hw) v = (int)hw;
+        return v < 1 ? 1 : v > 16 ? 16 : v;
+    }();
+    return t;
+}
+}  // namespace
+
 extern "C" int ge_step_many(ge_batch** batches, int n_batches, int n_rounds) {
     if (!batches || n_batches < 0 || n_rounds < 0) return fail(GE_ERR_ARG, "bad arguments to ge_step_many");
     for (int i = 0; i < n_batches; ++i)
         if (!batches[i]) return fail(GE_ERR_ARG, "NULL batch in ge_step_many");
+    // several launch workers pay off for a ring of distinct batches and more than a handful of launches
+    bool distinct = true;
+    for (int i = 0; i < n_batches && distinct; ++i)
+        for (int j = 0; j < i; ++j)
+            if (batches[j] == batches[i]) { distinct = false; break; }
+    const int T = step_threads();
+    if (T > 1 && distinct && n_batches >= 4 && (long long)n_batches * n_rounds >= 16) {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);            // one ge_step_many at a time uses the pool
+        if (!g_pool) g_pool = new (std::nothrow) StepPool(T);
+        if (g_pool) return g_pool->run(batches, n_batches, n_rounds);
+    }
     int cur_dev = -1;
     for (int r = 0; r < n_rounds; ++r)
         for (int i = 0; i < n_batches; ++i) {
