@@ -15,9 +15,9 @@
 #include <vector>
 
 #include "ge_common.cuh"
-#include "ge_step_tps.cuh"
-#include "ge_step_coop.cuh"
+#include "ge_step_tps.cuh"      // LightBulk, TPS_THREADS (the kernels themselves are instantiated in ge_k_*.cu)
 #include "ge_spec_gen.cuh"
+#include "ge_kernels.h"
 #include "ge_glue.cuh"
 
 using namespace ge;
@@ -48,13 +48,9 @@ struct ge_table {
     size_t rec_canon, rec_dev;   // canonical / device record bytes
     uint16_t io_read[GE_MAX_PHASES], io_write[GE_MAX_PHASES];   // bytes a step that starts in phase i must read / write (ge_table_phase_io)
     uint32_t init_words[40];     // initial device record
-    void (*spec_fn)(const DevTable, const StepArgs);   // build-time specialised step kernel for this exact table, or NULL
-    void (*spec_ring_fn)(const DevTable, const StepArgs, const RingArgs);   // its ring-launch twin
-    void (*spec_tiled_fn)(const DevTable, const StepArgs);                  // its twin with per-tile column needs (werewolf)
+    KernelSet ks;                // the run-time-table kernels of this (family, bucket)  (ge_kernels.h)
+    SpecKernels spec;            // build-time specialised twins for this exact table (all NULL when it is not a shipped one)
 };
-
-typedef void (*step_fn)(const DevTable, const StepArgs);
-typedef void (*ring_fn)(const DevTable, const StepArgs, const RingArgs);
 
 struct ge_batch {
     ge_table* tab;
@@ -309,21 +305,21 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     return GE_OK;
 }
 
-// build-time specialised kernels (ge_spec_gen.cuh), matched by byte-identical table blobs
-struct SpecEntry { const unsigned char* blob; size_t len; step_fn fn; ring_fn rfn; step_fn tfn; };
-template <int FAM, int BUCKET, class S> struct SpecKernel;
-template <int BUCKET, class S> struct SpecKernel<FAM_WEREWOLF, BUCKET, S> {
-    static step_fn fn() { return (step_fn)k_step_w_tps<BUCKET, S>; }
-    static ring_fn rfn() { return (ring_fn)k_ring_w_tps<BUCKET, S>; }
-    static step_fn tfn() { return (step_fn)k_step_w_tps_tiled<BUCKET, S>; }
-};
-template <int BUCKET, class S> struct SpecKernel<FAM_TTL, BUCKET, S> {
-    static step_fn fn() { return (step_fn)k_step_t_tps<BUCKET, S>; }
-    static ring_fn rfn() { return (ring_fn)k_ring_t_tps<BUCKET, S>; }
-    static step_fn tfn() { return nullptr; }
-};
-#define GE_SPEC_ENTRY(S, FAM, BUCKET) {spec::S##_blob, sizeof(spec::S##_blob), SpecKernel<FAM, BUCKET, spec::S>::fn(), SpecKernel<FAM, BUCKET, spec::S>::rfn(), SpecKernel<FAM, BUCKET, spec::S>::tfn()},
-static const SpecEntry g_specs[] = { GE_SPEC_LIST(GE_SPEC_ENTRY) {nullptr, 0, nullptr, nullptr, nullptr} };
+// build-time specialised kernels (ge_k_spec.cu, one translation unit per shipped table), matched by byte-identical blobs
+#define GE_DECL_SPEC(S, FAM, BUCKET) void ge_spec_kernels_##S(SpecKernels* e);
+GE_SPEC_LIST(GE_DECL_SPEC)
+#undef GE_DECL_SPEC
+typedef void (*spec_getter)(SpecKernels*);
+#define GE_SPEC_GETTER(S, FAM, BUCKET) ge_spec_kernels_##S,
+static const spec_getter g_spec_getters[] = { GE_SPEC_LIST(GE_SPEC_GETTER) nullptr };
+#undef GE_SPEC_GETTER
+
+static bool kernel_set_of(int family, int bucket, KernelSet* out) {
+#define GE_PICK_KSET(F, B) if (family == F && bucket == B) { ge_kernel_set_##F##_##B(out); return true; }
+    GE_KERNEL_SETS(GE_PICK_KSET)
+#undef GE_PICK_KSET
+    return false;
+}
 
 extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
     if (!out) return fail(GE_ERR_ARG, "out is NULL");
@@ -331,12 +327,14 @@ extern "C" int ge_table_create(const uint8_t* blob, size_t n, ge_table** out) {
     if (!t) return fail(GE_ERR_NOMEM, "out of host memory");
     const int rc = validate_and_build(blob, n, t);
     if (rc != GE_OK) { delete t; return rc; }
-    t->spec_fn = nullptr;
-    t->spec_ring_fn = nullptr;
-    t->spec_tiled_fn = nullptr;
+    t->spec = SpecKernels{};
+    if (!kernel_set_of(t->family, t->bucket, &t->ks)) { delete t; return fail(GE_ERR_UNSUPPORTED, "no kernels for this table's player bucket"); }
     const size_t used = sizeof(ge_table_header_t) + (size_t)t->dev.h.n_phases * sizeof(ge_phase_t) + (size_t)t->dev.h.n_preds * sizeof(ge_pred_t);
-    for (const SpecEntry* e = g_specs; e->blob; ++e)
-        if (e->len == used && memcmp(e->blob, blob, used) == 0) { t->spec_fn = e->fn; t->spec_ring_fn = e->rfn; t->spec_tiled_fn = e->tfn; }
+    for (const spec_getter* g = g_spec_getters; *g; ++g) {
+        SpecKernels e;
+        (*g)(&e);
+        if (e.len == used && memcmp(e.blob, blob, used) == 0) t->spec = e;
+    }
     *out = t;
     return GE_OK;
 }
@@ -357,74 +355,13 @@ extern "C" size_t ge_table_wire_size(const ge_table* t, int wire) {
 }
 
 // ------------------------------------------------------------------------------------ dispatch
-static step_fn pick_fn(const ge_table* t, int kernel) {
-    if (t->family == FAM_WEREWOLF) {
-        switch (t->bucket) {
-        case 8: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_w_coop<8> : (step_fn)k_step_w_tps<8>;
-        case 16: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_w_coop<16> : (step_fn)k_step_w_tps<16>;
-        case 24: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_w_coop<24> : (step_fn)k_step_w_tps<24>;
-        case 32: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_w_coop<32> : (step_fn)k_step_w_tps<32>;
-        }
-    } else {
-        switch (t->bucket) {
-        case 4: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<4> : (step_fn)k_step_t_tps<4>;
-        case 8: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<8> : (step_fn)k_step_t_tps<8>;
-        case 16: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<16> : (step_fn)k_step_t_tps<16>;
-        case 32: return kernel == GE_KERNEL_COOP ? (step_fn)k_step_t_coop<32> : (step_fn)k_step_t_tps<32>;
-        }
-    }
-    return nullptr;
-}
-
+static step_fn pick_fn(const ge_table* t, int kernel) { return kernel == GE_KERNEL_COOP ? t->ks.coop : t->ks.tps; }
 static step_fn pick_tiled_fn(const ge_table* t, int kernel) {
     if (t->family != FAM_WEREWOLF) return nullptr;
-    if (kernel == GE_KERNEL_TPS && t->spec_tiled_fn) return t->spec_tiled_fn;
-    switch (t->bucket) {
-    case 8: return (step_fn)k_step_w_tps_tiled<8>;
-    case 16: return (step_fn)k_step_w_tps_tiled<16>;
-    case 24: return (step_fn)k_step_w_tps_tiled<24>;
-    case 32: return (step_fn)k_step_w_tps_tiled<32>;
-    }
-    return nullptr;
+    return (kernel == GE_KERNEL_TPS && t->spec.tiled) ? t->spec.tiled : t->ks.tiled;
 }
-
-static step_fn pick_human_fn(const ge_table* t) {
-    if (t->family == FAM_WEREWOLF) {
-        switch (t->bucket) {
-        case 8: return (step_fn)k_step_w_tps_h<8>;
-        case 16: return (step_fn)k_step_w_tps_h<16>;
-        case 24: return (step_fn)k_step_w_tps_h<24>;
-        case 32: return (step_fn)k_step_w_tps_h<32>;
-        }
-    } else {
-        switch (t->bucket) {
-        case 4: return (step_fn)k_step_t_tps_h<4>;
-        case 8: return (step_fn)k_step_t_tps_h<8>;
-        case 16: return (step_fn)k_step_t_tps_h<16>;
-        case 32: return (step_fn)k_step_t_tps_h<32>;
-        }
-    }
-    return nullptr;
-}
-
-static ring_fn pick_ring_fn(const ge_table* t) {
-    if (t->family == FAM_WEREWOLF) {
-        switch (t->bucket) {
-        case 8: return (ring_fn)k_ring_w_tps<8>;
-        case 16: return (ring_fn)k_ring_w_tps<16>;
-        case 24: return (ring_fn)k_ring_w_tps<24>;
-        case 32: return (ring_fn)k_ring_w_tps<32>;
-        }
-    } else {
-        switch (t->bucket) {
-        case 4: return (ring_fn)k_ring_t_tps<4>;
-        case 8: return (ring_fn)k_ring_t_tps<8>;
-        case 16: return (ring_fn)k_ring_t_tps<16>;
-        case 32: return (ring_fn)k_ring_t_tps<32>;
-        }
-    }
-    return nullptr;
-}
+static step_fn pick_human_fn(const ge_table* t) { return t->ks.human; }
+static ring_fn pick_ring_fn(const ge_table* t) { return t->ks.ring; }
 
 static int lanes_per_session(const ge_table* t) {
     if (t->family == FAM_WEREWOLF) return t->bucket <= 8 ? 8 : t->bucket <= 16 ? 16 : 32;
@@ -528,8 +465,8 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
         return fail(e == cudaErrorMemoryAllocation ? GE_ERR_NOMEM : GE_ERR_CUDA, std::string("ge_batch_create: ") + cudaGetErrorString(e));
     }
     for (int k = GE_KERNEL_COOP; k <= GE_KERNEL_TPS_GENERIC; ++k) {
-        b->fn[k] = k == GE_KERNEL_TPS_GENERIC ? pick_fn(t, GE_KERNEL_TPS) : (k == GE_KERNEL_TPS && t->spec_fn) ? t->spec_fn : pick_fn(t, k);
-        b->rfn[k] = k == GE_KERNEL_COOP ? nullptr : (k == GE_KERNEL_TPS && t->spec_ring_fn) ? t->spec_ring_fn : pick_ring_fn(t);
+        b->fn[k] = k == GE_KERNEL_TPS_GENERIC ? pick_fn(t, GE_KERNEL_TPS) : (k == GE_KERNEL_TPS && t->spec.tps) ? t->spec.tps : pick_fn(t, k);
+        b->rfn[k] = k == GE_KERNEL_COOP ? nullptr : (k == GE_KERNEL_TPS && t->spec.ring) ? t->spec.ring : pick_ring_fn(t);
         if (!b->fn[k]) { ge_batch_destroy(b); return fail(GE_ERR_UNSUPPORTED, "no kernel for this table"); }
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)b->fn[k], 128, 0);

@@ -32,7 +32,8 @@ struct DevTable {
     ge_phase_t phase[GE_MAX_PHASES];
     ge_pred_t pred[GE_MAX_PREDS];
     // per phase: which column groups a step that starts in this phase must READ besides column 0
-    // (bit0 = dynamic masks column, bit1 = role/team column, bit2 = per-player bytes); host-computed.
+    // (bit0 = dynamic masks column, bit1 = role/team column, bit2 = per-player bytes, bit3 = session id; bit4 = column D1
+    // of the PACKED store: role bytes + target bytes); host-computed.
     uint8_t need[GE_MAX_PHASES];
     uint32_t nonterm;          // bit i: phase index i is not terminal (host-computed)
 };

@@ -536,8 +536,11 @@ __device__ __forceinline__ int w_step_spec(WState<P8>& s, const FieldTable& F, c
 
 // A step of a session whose phase needs nothing but column 0 (UI / timer phases with no effects; the host
 // proves this per phase in DevTable::need).  c = {h0, h1, is_alive, can_vote}.  Same SPEC as w_step.
+// PK: the packed store (below): c.z = is_alive | can_vote << 8 | ... as bytes instead of two 32-bit masks.
+template <bool PK = false>
 __device__ __forceinline__ int w_step_light(const DevTable& T, uint4& c) {
     const int X = c.x & 0xFF;
+    const uint32_t f_alive = PK ? (c.z & 0xFFu) : c.z, f_vote = PK ? ((c.z >> 8) & 0xFFu) : c.w;
     const uint32_t step0 = c.x >> 16;
     const ge_phase_t& ph = T.phase[X];
     if (ph.kind == KIND_TERMINAL) return -1;
@@ -555,10 +558,10 @@ __device__ __forceinline__ int w_step_light(const DevTable& T, uint4& c) {
                     const uint32_t pos = k ? pr.pos1 : pr.pos0, neg = k ? pr.neg1 : pr.neg0;
                     if (neg & 0x8000u) continue;
                     uint32_t m = ALL;
-                    if (pos & 1u) m &= c.z;
-                    if (pos & 2u) m &= c.w;
-                    if (neg & 1u) m &= ~c.z;
-                    if (neg & 2u) m &= ~c.w;
+                    if (pos & 1u) m &= f_alive;
+                    if (pos & 2u) m &= f_vote;
+                    if (neg & 1u) m &= ~f_alive;
+                    if (neg & 2u) m &= ~f_vote;
                     out |= m;
                 }
                 if (!(pr.pos0 & GE_PRED_CONTINUED)) break;
@@ -637,10 +640,15 @@ struct LightBulk {
 // the all-bot kernels are exactly what they were.
 // TILED: per-tile column needs (batches with phase regrouping); its own instantiations (k_step_w_tps_tiled), so the
 // lockstep kernels do not carry the extra words and branches (measured: -2.3 % on the headline when they did).
-template <int P8, class Spec, bool HUM = false, bool TILED = false>
+// PK: the PACKED session store (werewolf tables up to 8 players; ge_capi.cu GE_OPT_STORE_PACKED): a record is the 32
+// bytes of the dense wire format (SPEC 5b) in two 16-byte columns — D0 = header + the eight masks is_alive ... has_secret_role
+// as bytes, D1 = role_lo, role_hi bytes + the eight target bytes — instead of 3.5 columns whose mask words are 3/4 zeros.
+// D0 moves on every step; D1 only when DevTable::need says so (bit 4).
+template <int P8, class Spec, bool HUM = false, bool TILED = false, bool PK = false>
 __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C, const SlotArgs& A, BlockCounters& bc,
                                             uint32_t (*s_fields)[TPS_THREADS], uint8_t* s_lut_col, LightBulk* lb = nullptr) {
-    constexpr int S = 48 + P8;
+    static_assert(!PK || P8 == 8, "the packed store covers tables up to 8 players");
+    constexpr int S = PK ? 32 : 48 + P8;
     constexpr int NT16 = P8 / 16;          // full 16-byte target columns
     constexpr bool THALF = (P8 % 16) != 0; // trailing 8-byte column
     uint32_t (&s_visits)[32] = bc.visits;
@@ -649,7 +657,7 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     // which column groups can any session of this batch need?  (bit0 C1, bit1 C2, bit2 player bytes, bit3 session id)
     const uint32_t present_in = bc.present_in;
-    const uint32_t need_batch = C.n_steps > 1 ? 15u : need_of(T, present_in);
+    const uint32_t need_batch = C.n_steps > 1 ? 31u : need_of(T, present_in);
     const uint64_t n_act = bc.n_act;
     const uint64_t sid0 = bc.sid0;
     const uint32_t n_tiles_act = (uint32_t)((n_act + 31) >> 5);
@@ -734,7 +742,7 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
                             if (tag0) c[j].y = (c[j].y & ~0xFFu) | tag0;
                             np = (int)y0;
                         } else if (in_range) {
-                            np = w_step_light(T, c[j]);
+                            np = w_step_light<PK>(T, c[j]);
                         }
                         if (np >= 0) st128(base + j * tile_stride, c[j]);
                         mixed += visits.add(s_visits, np, lane) > 1;
@@ -773,7 +781,22 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             uint32_t org = tile * 32u + lane;
             if (A.origin != nullptr && (need & 8) && in_range) org = A.origin[org];
             WState<P8> s;
+            uint8_t* base8 = nullptr;
             // all loads are issued up front (no dependent second round trip)
+            if constexpr (PK) {
+                const uint4 d0 = ld128(base);
+                uint4 d1 = make_uint4(0, 0, 0, 0);
+                if (need & 16) d1 = ld128(base + 512);
+                if (tile + nwarps < n_tiles_act) {                       // next tile -> L1 (see below)
+                    prefetch_l1(base + tile_stride);
+                    if (need_next & 16) prefetch_l1(base + tile_stride + 512);
+                }
+                s.h0 = d0.x; s.h1 = d0.y;
+                s.alive = d0.z & 0xFFu; s.can_vote = (d0.z >> 8) & 0xFFu; s.eligible = (d0.z >> 16) & 0xFFu; s.submitted = d0.z >> 24;
+                s.revealed = d0.w & 0xFFu; s.investigated = (d0.w >> 8) & 0xFFu; s.wolf = (d0.w >> 16) & 0xFFu; s.secret = d0.w >> 24;
+                s.role_lo = d1.x & 0xFFu; s.role_hi = (d1.x >> 8) & 0xFFu;
+                s.tw[0] = d1.y; s.tw[1] = d1.z;
+            } else {
             const uint4 c0 = ld128(base);
             uint4 c1 = make_uint4(0, 0, 0, 0), c2 = make_uint4(0, 0, 0, 0);
             if (need & 1) c1 = ld128(base + 512);
@@ -784,13 +807,12 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
                 if (need & 4) t = ld128(base + (3 + c) * 512);
                 s.tw[4 * c] = t.x; s.tw[4 * c + 1] = t.y; s.tw[4 * c + 2] = t.z; s.tw[4 * c + 3] = t.w;
             }
-            uint8_t* const base8 = base - lane * 8 + (3 + NT16) * 512;       // trailing 8-byte column of this lane
+            base8 = base - lane * 8 + (3 + NT16) * 512;       // trailing 8-byte column of this lane
             if (THALF) {
                 uint2 t = make_uint2(0, 0);
                 if (need & 4) t = ld64(base8);
                 s.tw[4 * NT16] = t.x; s.tw[4 * NT16 + 1] = t.y;
             }
-            const PlSink K{base + 3 * 512, base8, (need & 4u) == 0};
             // The next tile of this warp: bring its columns to L1 while this one computes, so the warp does not sit out a
             // full DRAM round trip at the top of every iteration (+7 % at 8 players; two tiles ahead, or prefetching
             // in the light path, measured no better).
@@ -808,6 +830,9 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             s.h0 = c0.x; s.h1 = c0.y; s.alive = c0.z; s.can_vote = c0.w;
             s.eligible = c1.x; s.submitted = c1.y; s.revealed = c1.z; s.investigated = c1.w;
             s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
+            }
+            // (packed store: the target bytes always travel through registers — D1 is loaded whenever a phase records them)
+            const PlSink K{base + 3 * 512, base8, !PK && (need & 4u) == 0};
             bool live = in_range;
             const uint64_t sid = sid0 + org;
             uint32_t dirty = 0;
@@ -837,6 +862,12 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
                 if (lane == 0) A.tile_present_out[tile] = bits;
             }
             live_cnt += __popc(lm);
+            if constexpr (PK) {
+                if (dirty & (DIRTY_C0 | DIRTY_C1 | DIRTY_C2))
+                    st128(base, make_uint4(s.h0, s.h1, s.alive | (s.can_vote << 8) | (s.eligible << 16) | (s.submitted << 24),
+                                           s.revealed | (s.investigated << 8) | (s.wolf << 16) | (s.secret << 24)));
+                if (dirty & (DIRTY_C2 | DIRTY_PL)) st128(base + 512, make_uint4(s.role_lo | (s.role_hi << 8), s.tw[0], s.tw[1], 0u));
+            } else {
             if (dirty & DIRTY_C0) st128(base, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
             if (dirty & DIRTY_C1) st128(base + 512, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
             if (dirty & DIRTY_C2) st128(base + 1024, make_uint4(s.wolf, s.secret, s.role_lo, s.role_hi));
@@ -845,6 +876,7 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
                 for (int c = 0; c < NT16; ++c)
                     st128(base + (3 + c) * 512, make_uint4(s.tw[4 * c], s.tw[4 * c + 1], s.tw[4 * c + 2], s.tw[4 * c + 3]));
                 if (THALF) st64(base8, make_uint2(s.tw[4 * NT16], s.tw[4 * NT16 + 1]));
+            }
             }
         }
     }
@@ -868,7 +900,7 @@ __device__ __forceinline__ void w_tps_publish(const SlotArgs& A, const BlockCoun
     }
 }
 
-template <int P8, class Spec = void>
+template <int P8, class Spec = void, bool PK = false>
 __global__ void __launch_bounds__(TPS_THREADS, GE_W_CTAS(P8))
 k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
     __shared__ WSmem<P8, 1> sm;
@@ -876,7 +908,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     LightBulk* lb = (A.flags & STEP_LIGHT_BULK) ? reinterpret_cast<LightBulk*>(dyn_smem) : nullptr;
     counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
-    w_tps_tiles<P8, Spec>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0], lb);
+    w_tps_tiles<P8, Spec, false, false, PK>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0], lb);
     __syncthreads();
     w_tps_publish(A, sm.c[0]);
 }
@@ -912,7 +944,7 @@ k_step_w_tps_h(const __grid_constant__ DevTable T, const __grid_constant__ StepA
 // for separate launches on one stream and 6.3e10 for separate launches on eight streams, which remains the default:
 // the ring kernel itself issues at 64 % of the scheduler peak (ncu, profiles/r02_ring_*), but the compaction and
 // re-initialisation launches that sit between ring passes on the single stream are no longer hidden.
-template <int P8, class Spec = void>
+template <int P8, class Spec = void, bool PK = false>
 __global__ void __launch_bounds__(TPS_THREADS, GE_W_CTAS(P8))
 k_ring_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs C, const __grid_constant__ RingArgs R) {
     __shared__ WSmem<P8, GE_RING_MAX> sm;
@@ -920,7 +952,7 @@ k_ring_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     __syncthreads();
     int i = ring_first_slot(R);
     for (int k = 0; k < R.n; ++k) {                    // no barrier between batches: warps drift freely
-        w_tps_tiles<P8, Spec>(T, C, R.slot[i], sm.c[i], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
+        w_tps_tiles<P8, Spec, false, false, PK>(T, C, R.slot[i], sm.c[i], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
         i = i + 1 == R.n ? 0 : i + 1;
     }
     __syncthreads();
