@@ -98,6 +98,10 @@ def parse_args():
     ap.add_argument("--regroup", default="", help="phase regrouping 'every,shift' (default: the library's choice for the table)")
     ap.add_argument("--light-bulk", action="store_true",
                     help="A/B: header-only launches fetch their tiles with cp.async.bulk + mbarrier (ge_batch_set_option)")
+    ap.add_argument("--store", default="packed", choices=["canonical", "packed"],
+                    help="session store in HBM: packed (werewolf tables up to 8 players keep a 32-byte record in two 16-byte columns, "
+                         "the library's default for them; other tables are canonical either way) or canonical columns for every table "
+                         "(ge_batch_set_option GE_OPT_STORE_PACKED 0: the A/B)")
     ap.add_argument("--head-start-us", type=int, default=3000,
                     help="length of the spin kernel the timed launches are queued behind (host head start; 0 = none)")
     ap.add_argument("--seed", type=int, default=20261018)
@@ -401,6 +405,9 @@ def run_ours(a):
     cap = a.cap or game_cap(cg.family, a.players, cg.table.max_revotes)
     N, R = a.sessions, a.ring
     tab = Table(cg)
+    packable = cg.family == 1 and a.players <= 8
+    packed = a.store == "packed" and packable and a.kernel != "coop" and cg.table.max_revotes == 0
+    S_store = 32 if packed else S                    # bytes per session resident in HBM
     # the ring's batches are independent sessions: batch i runs on stream i % NS so that one batch's launch
     # ramp / tail and near-empty late-game launches overlap with another batch's work
     merged = a.launch == "ring" and a.kernel != "coop"
@@ -419,6 +426,8 @@ def run_ours(a):
         b.set_grid((a.ring_ctas if NS > 1 else 0) if merged else a.ctas_per_sm)
         if a.light_bulk:
             b.set_option("light_bulk", 1)
+        if packable:
+            b.set_option("store_packed", 1 if packed else 0)
         if a.regroup:
             b.set_regroup(*[int(x) for x in a.regroup.split(",")])
         if a.compaction:
@@ -564,6 +573,8 @@ def run_ours(a):
               for j in range(4)]
         for j, b in enumerate(fb):
             b.set_stream(streams[j % NS].cuda_stream)
+            if packable:
+                b.set_option("store_packed", 1 if packed else 0)
             b.run_fused(cap)
         torch.cuda.synchronize()
         f0 = sum(b.counted_steps() for b in fb)
@@ -602,6 +613,8 @@ def run_ours(a):
                 for j in range(NSUB)]
         for sb in subs:
             sb.set_wire(a.wire)
+            if packable:
+                sb.set_option("store_packed", 1 if packed else 0)
         W = subs[0].wire_record_size                          # bytes per session on the wire
         pin_in, pin_out, pin_st = PinnedBuffer(NE * W), PinnedBuffer(NE * W), PinnedBuffer(NSUB * 560 * 8)
         rin = pin_in.array.reshape(NSUB, sub, W)
@@ -673,8 +686,8 @@ def run_ours(a):
     step_launches = a.steps * (NS if merged else R)                       # step-kernel launches per GPU in the timed region
     # physical DRAM traffic: bytes per counted step from the committed ncu capture of THIS workload (same table, players,
     # kernel and batch size; anything else is refused), times the live step rate
-    tr = ncu_traffic(a.game, a.players, kern, N, R, S)
-    nec = tab.necessary_bytes_per_step(stats)                             # visit-weighted columns that must move (ge_table_phase_io)
+    tr = ncu_traffic(a.game, a.players, kern + ("+packed" if packed else ""), N, R, S_store)
+    nec = tab.necessary_bytes_per_step(stats, packed)                             # visit-weighted columns that must move (ge_table_phase_io)
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": (tr["bytes_per_step"] * counted_all / world / step_launches) if tr else None, "peak_source": peak_src,
             "frac_of_nominal_8000": achieved / 8000.0,         # BASELINE.md section 2 asks for the nominal figure too
@@ -701,7 +714,7 @@ def run_ours(a):
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
             "baseline_config": a.config,
             "light_path": "cp.async.bulk + mbarrier" if a.light_bulk else "LDG.128", "kernel": kern, "launch": ("%d ring launch(es) per pass (ge_step_ring)" % NS) if merged else "one launch per batch", "streams": NS,
-            "ctas_per_sm": "occupancy limit" if merged else a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S, "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
+            "ctas_per_sm": "occupancy limit" if merged else a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S_store, "store": "packed (32 bytes per session in HBM)" if packed else "canonical columns", "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
             "steps_before_reinit": "when every game of the batch is over (device-side auto-reset, checked every 8 steps)" if auto else cap,
             "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
             "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,

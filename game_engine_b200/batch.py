@@ -28,19 +28,21 @@ class Table:
         self.record_size = int(L.ge_table_record_size(self._h))
         assert self.record_size == game.record_size
 
-    def phase_io(self):
-        """[(read_bytes, write_bytes)] per phase index: what a step starting there must move per session."""
+    def phase_io(self, packed: bool = False):
+        """[(read_bytes, write_bytes)] per phase index: what a step starting there must move per session (packed: with
+        the packed session store, GE_OPT_STORE_PACKED)."""
         out = []
+        fn = capi.lib().ge_table_phase_io_packed if packed else capi.lib().ge_table_phase_io
         for i in range(len(self.game.phase_ids)):
             r, w = ctypes.c_uint32(), ctypes.c_uint32()
-            capi.check(capi.lib().ge_table_phase_io(self._h, i, ctypes.byref(r), ctypes.byref(w)))
+            capi.check(fn(self._h, i, ctypes.byref(r), ctypes.byref(w)))
             out.append((int(r.value), int(w.value)))
         return out
 
-    def necessary_bytes_per_step(self, stats) -> float:
+    def necessary_bytes_per_step(self, stats, packed: bool = False) -> float:
         """Visit-weighted necessary DRAM bytes per session-phase-step (stats = the u64[560] statistics: words
         260.. are visits per phase index; a visit to a non-terminal phase is followed by one step that starts there)."""
-        io = self.phase_io()
+        io = self.phase_io(packed)
         num = den = 0.0
         for i, (r, w) in enumerate(io):
             if r + w == 0:
@@ -130,8 +132,9 @@ class SessionBatch:
         capi.check(capi.lib().ge_batch_set_compaction(self._h, int(every_n_steps), int(min_dead_shift)))
 
     def set_option(self, option: str, value: int) -> None:
-        """Tuning options: "light_bulk" (header-only launches fetch their tiles with cp.async.bulk + mbarrier)."""
-        capi.check(capi.lib().ge_batch_set_option(self._h, {"light_bulk": capi.OPT_LIGHT_BULK}[option], int(value)))
+        """Tuning options: "light_bulk" (header-only launches fetch their tiles with cp.async.bulk + mbarrier);
+        "store_packed" (werewolf tables up to 8 players: 32-byte records in HBM, two 16-byte columns)."""
+        capi.check(capi.lib().ge_batch_set_option(self._h, {"light_bulk": capi.OPT_LIGHT_BULK, "store_packed": capi.OPT_STORE_PACKED}[option], int(value)))
 
     def set_grid(self, ctas_per_sm: int) -> None:
         """Persistent grid of the step launches = SMs x ctas_per_sm (0 = as many as fit).  Smaller grids let the

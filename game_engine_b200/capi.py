@@ -17,6 +17,7 @@ STATS_LEN = 560
 GE_OK, GE_ERR_ARG, GE_ERR_CUDA, GE_ERR_UNSUPPORTED, GE_ERR_NOMEM = 0, -1, -2, -3, -4
 KERNEL_AUTO, KERNEL_COOP, KERNEL_TPS, KERNEL_TPS_GENERIC = 0, 1, 2, 3
 OPT_LIGHT_BULK = 1
+OPT_STORE_PACKED = 2
 WIRE_CANONICAL, WIRE_DENSE = 0, 1
 WIRE_NAMES = {"canonical": WIRE_CANONICAL, "dense": WIRE_DENSE}
 KERNEL_NAMES = {"auto": KERNEL_AUTO, "coop": KERNEL_COOP, "tps": KERNEL_TPS, "tps_generic": KERNEL_TPS_GENERIC}
@@ -29,6 +30,7 @@ SYMBOLS = [
     ("ge_table_record_size", _sz, [_vp]),
     ("ge_table_n_players", _int, [_vp]),
     ("ge_table_phase_io", _int, [_vp, _int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
+    ("ge_table_phase_io_packed", _int, [_vp, _int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
     ("ge_batch_create", _int, [_vp, _int, _u64, _u64, _u64, ctypes.POINTER(_vp)]),
     ("ge_batch_reset", _int, [_vp, _u64, _u64]),
     ("ge_batch_clear_stats", _int, [_vp]),

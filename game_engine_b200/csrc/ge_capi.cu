@@ -47,6 +47,7 @@ struct ge_table {
     int family, P, bucket;       // bucket: werewolf P8 (8/16/24/32), TTL PB (4/8/16/32)
     size_t rec_canon, rec_dev;   // canonical / device record bytes
     uint16_t io_read[GE_MAX_PHASES], io_write[GE_MAX_PHASES];   // bytes a step that starts in phase i must read / write (ge_table_phase_io)
+    uint16_t io_read_pk[GE_MAX_PHASES], io_write_pk[GE_MAX_PHASES];   // the same for the packed store (0 = table not packable)
     uint32_t init_words[40];     // initial device record
     KernelSet ks;                // the run-time-table kernels of this (family, bucket)  (ge_kernels.h)
     SpecKernels spec;            // build-time specialised twins for this exact table (all NULL when it is not a shipped one)
@@ -103,6 +104,13 @@ struct ge_batch {
     uint32_t* h_err;              // import validation: [0] rejected records, [1] max(~index): pinned host words that k_import
     uint32_t* d_err;              //   bumps THROUGH THE MAPPING (d_err) only when it finds a bad record — no memset, no copy
     cudaEvent_t fence;            // orders a caller-supplied stream against the batch's own (ge_step / ge_run_fused / ge_stats_refresh)
+    // Store format (GE_OPT_STORE_PACKED): werewolf tables up to 8 players can keep their records PACKED — the 32 bytes of
+    // the dense wire record in two 16-byte columns instead of 56 bytes in 3.5 — for the all-bot thread-per-session
+    // kernels.  want_packed = the option; packed = how d_tiles is laid out right now; rec_store = its record bytes.
+    // Everything that does not speak the packed layout (lane-per-player kernels, human seats, regrouping, audience
+    // masks) converts the store back first (ensure_store).
+    bool want_packed, packed;
+    size_t rec_store;
 };
 
 static int restore_order(ge_batch* b, bool keep_records);
@@ -114,6 +122,7 @@ static int sync_and_check(ge_batch* b);
 static int lanes_per_session(const ge_table* t);
 extern "C" int ge_batch_set_regroup(ge_batch* b, int every_n_steps, int min_mixed_shift);
 static int ensure_stage(ge_batch* b, size_t bytes);
+static int ensure_store(ge_batch* b, bool packed, cudaStream_t st);
 extern "C" size_t ge_table_wire_size(const ge_table* t, int wire);
 
 static int sync_and_check(ge_batch* b) {
@@ -242,6 +251,35 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             need |= entry_need(t->dev.phase[br.next].entry_op);
             if (t->dev.phase[br.next].entry_op == EN_ASSIGN_ROLES) need |= 8;
         }
+        // bit 4: column D1 of the PACKED store (role_lo / role_hi bytes + target bytes; ge_step_tps.cuh) must be read:
+        // a predicate names a role field (8-11), anything touches the target bytes, or an entry effect rewrites part of
+        // the column (ASSIGN_ROLES the role bytes, NIGHT_RESET the target bytes)
+        {
+            auto pred_roles = [&](int pi) -> bool {
+                for (; pi >= 0 && pi < h.n_preds; ++pi) {
+                    const ge_pred_t& p = t->dev.pred[pi];
+                    const uint16_t lits[4] = {p.pos0, p.neg0, p.pos1, p.neg1};
+                    for (int c = 0; c < 2; ++c)
+                        if (!(lits[2 * c + 1] & 0x8000u) && ((lits[2 * c] | lits[2 * c + 1]) & 0x0F00u)) return true;
+                    if (!(p.pos0 & GE_PRED_CONTINUED)) break;
+                }
+                return false;
+            };
+            bool d1 = (need & 4) != 0;
+            if (ph.kind == KIND_ACTION) {
+                d1 |= pred_roles(ph.actor_pred);
+                if (ph.action_op == ACT_PICK_PLAYER) d1 |= pred_roles(ph.action_arg);
+                if (ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE) d1 = true;      // recorded targets
+            }
+            for (int b = 0; b < ph.n_branches; ++b) {
+                const ge_branch_t& br = ph.br[b];
+                if (br.op == BR_COUNT_EQ0 || br.op == BR_COUNT_GE) d1 |= pred_roles(br.a);
+                if (br.op == BR_COUNT_GE) d1 |= pred_roles((int)br.arg);
+                const int en = t->dev.phase[br.next].entry_op;
+                if (en == EN_ASSIGN_ROLES || en == EN_NIGHT_RESET) d1 = true;
+            }
+            if (d1) need |= 16;
+        }
         t->dev.need[i] = need;
     }
     // NECESSARY bytes per session of a step that starts in phase i (ge_table_phase_io): the columns `need` proves it
@@ -250,6 +288,7 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
     // figure 2·S assumes every byte of the record moves on every step.
     for (int i = 0; i < h.n_phases; ++i) {
         const ge_phase_t& ph = t->dev.phase[i];
+        t->io_read_pk[i] = t->io_write_pk[i] = 0;
         if (ph.kind == KIND_TERMINAL) { t->io_read[i] = t->io_write[i] = 0; continue; }
         const uint8_t need = t->dev.need[i];
         bool en_assign = false, en_reset = false, en_any = false;
@@ -267,6 +306,10 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             if (en_reset || (records && (ph.exit_op == EX_DAY_VOTE || h.n_players <= 8))) wr += P8;
             else if (records) wr += ph.exit_op == EX_VOTE_KILL ? h.n_wolves : 1;   // one target byte per actor, stored directly
             t->io_read[i] = (uint16_t)rd; t->io_write[i] = (uint16_t)wr;
+            // packed store (up to 8 players): D0 both ways on every step, D1 when `need` bit 4 says so / when the role or
+            // target bytes change
+            t->io_read_pk[i] = (uint16_t)(P8 == 8 ? 16 + ((need & 16) ? 16 : 0) : 0);
+            t->io_write_pk[i] = (uint16_t)(P8 == 8 ? 16 + ((records || en_assign || en_reset) ? 16 : 0) : 0);
         } else {
             const int bucket = h.n_players <= 4 ? 4 : h.n_players <= 8 ? 8 : h.n_players <= 16 ? 16 : 32;
             const int S = 8 + 4 * bucket;
@@ -347,6 +390,13 @@ extern "C" int ge_table_phase_io(const ge_table* t, int phase_index, uint32_t* r
     if (write_bytes) *write_bytes = t->io_write[phase_index];
     return GE_OK;
 }
+extern "C" int ge_table_phase_io_packed(const ge_table* t, int phase_index, uint32_t* read_bytes, uint32_t* write_bytes) {
+    if (!t || phase_index < 0 || phase_index >= t->dev.h.n_phases) return fail(GE_ERR_ARG, "bad arguments to ge_table_phase_io_packed");
+    if (!(t->family == FAM_WEREWOLF && t->bucket == 8)) return fail(GE_ERR_UNSUPPORTED, "the packed store covers werewolf-family tables up to 8 players");
+    if (read_bytes) *read_bytes = t->io_read_pk[phase_index];
+    if (write_bytes) *write_bytes = t->io_write_pk[phase_index];
+    return GE_OK;
+}
 // dense wire records exist for werewolf tables up to 16 players (SPEC.md section 5b); everything else travels canonical
 static bool has_dense(const ge_table* t) { return t->family == FAM_WEREWOLF && t->bucket <= 16; }
 extern "C" size_t ge_table_wire_size(const ge_table* t, int wire) {
@@ -376,12 +426,35 @@ static int glue_grid(const ge_batch* b, uint64_t items, int block) {
 }
 
 // ------------------------------------------------------------------------------------ batch
+// the initial record in the batch's CURRENT store format (canonical words, or the packed words of SPEC 5b)
+static InitRec init_rec(const ge_batch* b) {
+    InitRec rec;
+    memset(&rec, 0, sizeof rec);
+    const uint32_t* w = b->tab->init_words;
+    if (!b->packed) { memcpy(rec.w, w, sizeof rec.w); return rec; }
+    rec.w[0] = w[0]; rec.w[1] = w[1];
+    rec.w[2] = (w[2] & 0xFFu) | ((w[3] & 0xFFu) << 8) | ((w[4] & 0xFFu) << 16) | ((w[5] & 0xFFu) << 24);
+    rec.w[3] = (w[6] & 0xFFu) | ((w[7] & 0xFFu) << 8) | ((w[8] & 0xFFu) << 16) | ((w[9] & 0xFFu) << 24);
+    rec.w[4] = (w[10] & 0xFFu) | ((w[11] & 0xFFu) << 8);
+    rec.w[5] = w[12]; rec.w[6] = w[13]; rec.w[7] = 0;
+    return rec;
+}
+static InitRec init_rec_canon(const ge_batch* b) {
+    InitRec rec;
+    memcpy(rec.w, b->tab->init_words, sizeof rec.w);
+    return rec;
+}
+static bool packable(const ge_table* t) { return t->family == FAM_WEREWOLF && t->bucket == 8 && t->ks.tps_pk != nullptr; }
+// the layout the batch's next step launch wants
+static bool store_should_be_packed(const ge_batch* b) {
+    return b->want_packed && packable(b->tab) && b->kernel != GE_KERNEL_COOP && !b->d_hmask && b->regroup_every == 0;
+}
+
 static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) {
     b->first_sid = first_session_id;
     b->seed = seed;
-    InitRec rec;
-    memcpy(rec.w, b->tab->init_words, sizeof rec.w);
-    k_init<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, b->stream>>>(b->d_tiles, b->n_tiles, (uint32_t)b->tab->rec_dev, rec);
+    const InitRec rec = init_rec(b);
+    k_init<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, b->stream>>>(b->d_tiles, b->n_tiles, (uint32_t)b->rec_store, rec);
     CU(cudaGetLastError());
     b->launches++;
     CU(cudaMemsetAsync(b->d_presence, 0, 3 * sizeof(uint32_t), b->stream));
@@ -401,7 +474,7 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
 extern "C" int ge_batch_reset(ge_batch* b, uint64_t first_session_id, uint64_t seed) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     CU(cudaSetDevice(b->device));
-    k_stats<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, b->d_tiles, (uint32_t)b->tab->rec_dev, b->n, b->d_stats);
+    k_stats<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->d_stats, b->packed ? 1u : 0u);
     CU(cudaGetLastError());
     b->launches++;
     return init_sessions(b, first_session_id, seed);
@@ -425,7 +498,8 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (!b) return fail(GE_ERR_NOMEM, "out of host memory");
     memset(b, 0, sizeof *b);
     b->tab = t; b->device = device; b->n = n_sessions; b->n_tiles = (n_sessions + 31) / 32;
-    b->tiles_bytes = (size_t)b->n_tiles * 32 * t->rec_dev;
+    b->tiles_bytes = (size_t)b->n_tiles * 32 * t->rec_dev;      // allocated for the canonical columns; the packed store uses a prefix
+    b->rec_store = t->rec_dev;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { delete b; return fail(GE_ERR_CUDA, cudaGetErrorString(e)); }
@@ -480,13 +554,18 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     }
     b->kernel = GE_KERNEL_TPS;
     b->wire = GE_WIRE_CANONICAL; b->rec_wire = t->rec_canon;
-    int rc = ge_batch_clear_stats(b);
-    if (rc == GE_OK) rc = init_sessions(b, first_session_id, seed);
     // tables with a tie -> re-vote loop de-synchronise their sessions: regroup them by phase (k_regroup_*)
     bool desync = false;
     for (int i = 0; i < t->dev.h.n_phases; ++i)
         for (int k = 0; k < t->dev.phase[i].n_branches; ++k)
             if (t->dev.phase[i].br[k].op == BR_TIE_PENDING) desync = true;
+    // tables up to 8 players keep their records packed (32 bytes in two columns; +10 % on the headline workload, DESIGN
+    // section 6) unless something the packed layout does not serve is switched on (GE_OPT_STORE_PACKED 0 = canonical)
+    b->want_packed = packable(t);
+    b->packed = b->want_packed && !(desync && t->family == FAM_WEREWOLF && b->n <= (1ull << 31));
+    b->rec_store = b->packed ? 32 : t->rec_dev;
+    int rc = ge_batch_clear_stats(b);
+    if (rc == GE_OK) rc = init_sessions(b, first_session_id, seed);
     if (rc == GE_OK && desync && t->family == FAM_WEREWOLF && b->n <= (1ull << 31)) rc = ge_batch_set_regroup(b, 5, 3);
     if (rc != GE_OK) { ge_batch_destroy(b); return rc; }
     *out = b;
@@ -570,6 +649,12 @@ extern "C" int ge_batch_set_option(ge_batch* b, int option, int value) {
     if (option == GE_OPT_LIGHT_BULK) {
         b->step_flags = value ? (b->step_flags | STEP_LIGHT_BULK) : (b->step_flags & ~(uint32_t)STEP_LIGHT_BULK);
         return GE_OK;
+    }
+    if (option == GE_OPT_STORE_PACKED) {
+        if (value && !packable(b->tab)) return fail(GE_ERR_UNSUPPORTED, "the packed store covers werewolf-family tables up to 8 players");
+        b->want_packed = value != 0;
+        CU(cudaSetDevice(b->device));
+        return ensure_store(b, store_should_be_packed(b), b->stream);
     }
     return fail(GE_ERR_ARG, "unknown option");
 }
@@ -687,7 +772,7 @@ static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st) {
     CompactArgs ca;
     memset(&ca, 0, sizeof ca);
     ca.n = n;
-    ca.S = (uint32_t)list[0]->tab->rec_dev;
+    ca.S = (uint32_t)list[0]->rec_store;
     ca.dead_shift = (uint32_t)list[0]->dead_shift;
     int max_scan = 1;
     uint64_t max_tiles = 1;
@@ -715,7 +800,7 @@ static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st) {
 
 // plan -> scatter -> copy back on the histogram of the counted step that just ran (all asynchronous, no host sync)
 static int enqueue_regroup(ge_batch* b, cudaStream_t st) {
-    const uint32_t S = (uint32_t)b->tab->rec_dev;
+    const uint32_t S = (uint32_t)b->rec_store;
     k_regroup_plan<<<1, 32, 0, st>>>(b->d_cstate, b->d_rg, b->tab->dev.nonterm, (uint32_t)b->rg_mixed_shift, (uint32_t)b->dead_shift);
     uint64_t g = (b->n + 1023) / 1024;
     if (g > (uint64_t)b->sm_count * 2) g = (uint64_t)b->sm_count * 2;
@@ -773,7 +858,12 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
     // a batch with people at the table runs the run-time-table kernel that carries the human-seat path
     const bool regroup_on = b->regroup_every > 0 && b->kernel != GE_KERNEL_COOP && steps_per_launch == 1;
     const bool tiled = regroup_on && b->sid_stride == 0 && !b->d_hmask && pick_tiled_fn(b->tab, b->kernel) != nullptr;
-    const step_fn fn = b->d_hmask ? pick_human_fn(b->tab) : tiled ? pick_tiled_fn(b->tab, b->kernel) : b->fn[b->kernel];
+    {
+        const int rc = ensure_store(b, store_should_be_packed(b), st);
+        if (rc != GE_OK) return rc;
+    }
+    const step_fn fn = b->packed ? ((b->kernel == GE_KERNEL_TPS && b->tab->spec.tps_pk) ? b->tab->spec.tps_pk : b->tab->ks.tps_pk)
+                     : b->d_hmask ? pick_human_fn(b->tab) : tiled ? pick_tiled_fn(b->tab, b->kernel) : b->fn[b->kernel];
     StepArgs a;
     fill_common(b, a, steps_per_launch);
     // phase regrouping replaces the swap compaction (it also moves finished games behind the live ones)
@@ -803,10 +893,9 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
             if (rc != GE_OK) return rc;
         }
         if ((regroup_after || compact_after) && b->sid_stride != 0) {      // every game over? start the next epoch on the device
-            InitRec rec;
-            memcpy(rec.w, b->tab->init_words, sizeof rec.w);
+            const InitRec rec = init_rec(b);
             k_autoreset_apply<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(
-                b->tab->dev, b->d_tiles, (uint32_t)b->tab->rec_dev, b->n, b->n_tiles, rec, b->d_origin, b->d_stats, b->d_cstate);
+                b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->n_tiles, rec, b->d_origin, b->d_stats, b->d_cstate, b->packed ? 1u : 0u);
             k_autoreset_commit<<<1, 32, 0, st>>>(b->d_cstate, b->d_presence, regroup ? b->d_rg : nullptr, b->launch_idx, b->n);
             CU(cudaGetLastError());
             b->launches += 2;
@@ -834,7 +923,13 @@ extern "C" int ge_step_ring(ge_batch** batches, int n_batches, int n_rounds) {
             if (batches[j] == b) return fail(GE_ERR_ARG, "ge_step_ring: a batch appears twice");
     }
     CU(cudaSetDevice(b0->device));
-    const ring_fn fn = b0->rfn[b0->kernel];
+    for (int i = 0; i < n_batches; ++i) {
+        if (batches[i]->want_packed != b0->want_packed) return fail(GE_ERR_ARG, "ge_step_ring: the batches must share the store format (GE_OPT_STORE_PACKED)");
+        const int rc = ensure_store(batches[i], store_should_be_packed(batches[i]), b0->stream);
+        if (rc != GE_OK) return rc;
+    }
+    const ring_fn fn = b0->packed ? ((b0->kernel == GE_KERNEL_TPS && b0->tab->spec.ring_pk) ? b0->tab->spec.ring_pk : b0->tab->ks.ring_pk)
+                                  : b0->rfn[b0->kernel];
     if (!fn) return fail(GE_ERR_UNSUPPORTED, "no ring kernel for this table");
     StepArgs c;
     memset(&c, 0, sizeof c);
@@ -1038,20 +1133,42 @@ static int ensure_stage(ge_batch* b, size_t bytes) {
     return GE_OK;
 }
 
+// Bring the session store to the wanted layout (canonical columns <-> packed, ge_batch::packed).  Slot by slot, so the
+// slot order (compaction's origin map, the active prefix) is untouched; through the staging buffer, stream-ordered.
+static int ensure_store(ge_batch* b, bool packed, cudaStream_t st) {
+    if (b->packed == packed) return GE_OK;
+    const size_t S_dst = packed ? 32 : b->tab->rec_dev;
+    const size_t bytes = (size_t)b->n_tiles * 32 * S_dst;
+    if (st != b->stream) CU(cudaStreamSynchronize(b->stream));      // the staging buffer belongs to the batch's own stream
+    int rc = ensure_stage(b, bytes);
+    if (rc) return rc;
+    k_repack<8><<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_tiles, b->d_stage, b->n_tiles * 32, packed ? 1 : 0);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(b->d_tiles, b->d_stage, bytes, cudaMemcpyDeviceToDevice, st));
+    if (st != b->stream) CU(cudaStreamSynchronize(st));
+    b->launches++;
+    b->packed = packed;
+    b->rec_store = S_dst;
+    b->tile_valid = false;
+    return GE_OK;
+}
+
 static int export_async(ge_batch* b, uint64_t first, uint64_t count, void* host_buf, int wire) {
     const bool dense = wire == GE_WIRE_DENSE && has_dense(b->tab);
     const size_t S = dense ? ge_table_wire_size(b->tab, GE_WIRE_DENSE) : b->tab->rec_canon;
     int rc = ensure_stage(b, count * S);
     if (rc) return rc;
-    if (dense) {
+    if (dense || b->packed) {
         const uint32_t* org = b->compacted ? b->d_origin : nullptr;
         const int g = glue_grid(b, org ? b->n : count, 256);
-        if (b->tab->bucket == 8) k_export_dense<8><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
-        else k_export_dense<16><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        if (b->packed && dense) k_export_w<8, true, true><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        else if (b->packed) k_export_w<8, false, true><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        else if (b->tab->bucket == 8) k_export_w<8, true, false><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        else k_export_w<16, true, false><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
     } else if (b->compacted)
-        k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, b->d_origin, b->n, first, count, b->d_stage);
+        k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, b->d_origin, b->n, first, count, b->d_stage);
     else
-        k_export<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage);
+        k_export<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, first, count, b->d_stage);
     CU(cudaGetLastError());
     b->launches++;
     CU(cudaMemcpyAsync(host_buf, b->d_stage, count * S, cudaMemcpyDeviceToHost, b->stream));
@@ -1066,10 +1183,14 @@ static int restore_order(ge_batch* b, bool keep_records) {
         const size_t S = b->tab->rec_canon;
         int rc = ensure_stage(b, b->n * S);
         if (rc) return rc;
-        InitRec rec;
-        memcpy(rec.w, b->tab->init_words, sizeof rec.w);
-        k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, b->d_origin, b->n, 0, b->n, b->d_stage);
-        k_import<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, 0, b->n, b->d_stage, nullptr, ImportReset{nullptr, nullptr, 0, 0});
+        const InitRec rec = init_rec_canon(b);
+        if (b->packed) {
+            k_export_w<8, false, true><<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, b->d_origin, b->n, 0, b->n, b->d_stage);
+            k_import_w<8, false, true><<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, 0, b->n, b->d_stage, nullptr, ImportReset{nullptr, nullptr, 0, 0});
+        } else {
+        k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, b->d_origin, b->n, 0, b->n, b->d_stage);
+        k_import<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, 0, b->n, b->d_stage, nullptr, ImportReset{nullptr, nullptr, 0, 0});
+        }
         CU(cudaGetLastError());
         b->launches += 2;
     }
@@ -1106,12 +1227,14 @@ static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void*
     }
     int rc = ensure_stage(b, count * S);
     if (rc) return rc;
-    InitRec rec;
-    memcpy(rec.w, b->tab->init_words, sizeof rec.w);
+    const InitRec rec = init_rec_canon(b);
     CU(cudaMemcpyAsync(b->d_stage, host_buf, count * S, cudaMemcpyHostToDevice, b->stream));
-    if (dense && b->tab->bucket == 8) k_import_dense<8><<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
-    else if (dense) k_import_dense<16><<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
-    else k_import<<<glue_grid(b, count, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->tab->rec_dev, (uint32_t)S, first, count, b->d_stage, b->d_err, R);
+    const int g = glue_grid(b, count, 256);
+    if (b->packed && dense) k_import_w<8, true, true><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else if (b->packed) k_import_w<8, false, true><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else if (dense && b->tab->bucket == 8) k_import_w<8, true, false><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else if (dense) k_import_w<16, true, false><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else k_import<<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, first, count, b->d_stage, b->d_err, R);
     CU(cudaGetLastError());
     b->launches++;
     b->next_override = 0xFFFFFFFFu;   // imported sessions can be in any phase (the import kernel cleared the presence words)
@@ -1160,13 +1283,15 @@ extern "C" int ge_eval_preds(ge_batch* b, const ge_pred_t* preds, int n_preds, u
     if (count == 0) return GE_OK;
     CU(cudaSetDevice(b->device));
     const size_t bytes = count * (size_t)n_preds * sizeof(uint32_t);
-    int rc = ensure_stage(b, bytes);
+    int rc = ensure_store(b, false, b->stream);       // the audience-mask kernel reads the canonical columns (the next step re-packs)
+    if (rc) return rc;
+    rc = ensure_stage(b, bytes);
     if (rc) return rc;
     PredList pl;
     memset(&pl, 0, sizeof pl);
     memcpy(pl.p, preds, (size_t)n_preds * sizeof(ge_pred_t));
     pl.n = n_preds;
-    k_eval_preds<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, pl, b->d_tiles, (uint32_t)b->tab->rec_dev,
+    k_eval_preds<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, pl, b->d_tiles, (uint32_t)b->rec_store,
                                                                b->compacted ? b->d_origin : nullptr, b->n, first, count,
                                                                reinterpret_cast<uint32_t*>(b->d_stage));
     CU(cudaGetLastError());
@@ -1184,7 +1309,7 @@ extern "C" int ge_stats_refresh(ge_batch* b, void* cuda_stream) {
     if (rc != GE_OK) return rc;
     // snapshot = accumulator + histograms of the sessions currently resident
     CU(cudaMemcpyAsync(b->d_stats_out, b->d_stats, GE_STATS_LEN * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-    k_stats<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->tab->dev, b->d_tiles, (uint32_t)b->tab->rec_dev, b->n, b->d_stats_out);
+    k_stats<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->d_stats_out, b->packed ? 1u : 0u);
     CU(cudaGetLastError());
     b->launches++;
     return fence_out(b, st);
@@ -1249,5 +1374,5 @@ extern "C" int ge_host_alloc(void** p, size_t bytes) {
 extern "C" void ge_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" void* ge_state_device_ptr(ge_batch* b) { return b ? (void*)b->d_tiles : nullptr; }
-extern "C" size_t ge_state_device_bytes(const ge_batch* b) { return b ? b->tiles_bytes : 0; }
+extern "C" size_t ge_state_device_bytes(const ge_batch* b) { return b ? (size_t)b->n_tiles * 32 * b->rec_store : 0; }
 extern "C" uint64_t ge_launch_count(const ge_batch* b) { return b ? b->launches : 0; }

@@ -115,7 +115,8 @@ __global__ void k_import(const __grid_constant__ DevTable T, const __grid_consta
 //            | 4 role_lo,role_hi,0,0 | 5-6 selected_target_id[0..7] | 7 zero
 //   P8 = 16: 0-1 header | 2 alive,can_vote (u16 each) | 3 eligible,submitted | 4 revealed,investigated | 5 wolf,secret
 //            | 6 role_lo,role_hi | 7 zero | 8-11 selected_target_id[0..15]
-// The conversion happens in the import / export kernels; the session store in HBM keeps the canonical columns.
+// The conversion happens in the import / export kernels.  The session store in HBM keeps the canonical columns, or —
+// tables up to 8 players, GE_OPT_STORE_PACKED — exactly these 32 bytes in two 16-byte columns (the packed store).
 template <int P8> struct DenseW { static constexpr int WORDS = P8 == 8 ? 8 : 12; static constexpr int CW = 12 + P8 / 4; };
 
 template <int P8>
@@ -174,77 +175,136 @@ __device__ __forceinline__ int words_invalid_w(const DevTable& T, const uint32_t
     return 0;
 }
 
-// canonical words of one slot of the tiled store (werewolf) and back
-template <int P8>
+// canonical words of one slot of the tiled store (werewolf) and back.  PK: the slot lives in the PACKED store (two
+// 16-byte columns holding the dense wire record, ge_step_tps.cuh), otherwise in the canonical columns.
+template <int P8, bool PK = false>
 __device__ __forceinline__ void tile_load_words(const uint8_t* tiles, uint64_t slot, uint32_t (&w)[12 + P8 / 4]) {
-    constexpr int S = 48 + P8;
-    const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S);
     const uint32_t sl = (uint32_t)(slot & 31);
+    if constexpr (PK) {
+        static_assert(P8 == 8, "packed store: up to 8 players");
+        const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * 32);
+        const uint4 a = *reinterpret_cast<const uint4*>(base + sl * 16), b = *reinterpret_cast<const uint4*>(base + 512 + sl * 16);
+        const uint32_t d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        dense_unpack<8>(d, w);
+    } else {
+        constexpr int S = 48 + P8;
+        const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S);
 #pragma unroll
-    for (int c = 0; c < S / 16; ++c) {
-        const uint4 v = *reinterpret_cast<const uint4*>(base + c * 512 + sl * 16);
-        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
-    }
-    if (S % 16) {
-        const uint2 v = *reinterpret_cast<const uint2*>(base + (S / 16) * 512 + sl * 8);
-        w[4 * (S / 16)] = v.x; w[4 * (S / 16) + 1] = v.y;
+        for (int c = 0; c < S / 16; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + c * 512 + sl * 16);
+            w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+        }
+        if (S % 16) {
+            const uint2 v = *reinterpret_cast<const uint2*>(base + (S / 16) * 512 + sl * 8);
+            w[4 * (S / 16)] = v.x; w[4 * (S / 16) + 1] = v.y;
+        }
     }
 }
-template <int P8>
+template <int P8, bool PK = false>
 __device__ __forceinline__ void tile_store_words(uint8_t* tiles, uint64_t slot, const uint32_t (&w)[12 + P8 / 4]) {
-    constexpr int S = 48 + P8;
-    uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S);
     const uint32_t sl = (uint32_t)(slot & 31);
+    if constexpr (PK) {
+        uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * 32);
+        uint32_t d[8];
+        dense_pack<8>(w, d);
+        *reinterpret_cast<uint4*>(base + sl * 16) = make_uint4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<uint4*>(base + 512 + sl * 16) = make_uint4(d[4], d[5], d[6], d[7]);
+    } else {
+        constexpr int S = 48 + P8;
+        uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S);
 #pragma unroll
-    for (int c = 0; c < S / 16; ++c)
-        *reinterpret_cast<uint4*>(base + c * 512 + sl * 16) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-    if (S % 16)
-        *reinterpret_cast<uint2*>(base + (S / 16) * 512 + sl * 8) = make_uint2(w[4 * (S / 16)], w[4 * (S / 16) + 1]);
+        for (int c = 0; c < S / 16; ++c)
+            *reinterpret_cast<uint4*>(base + c * 512 + sl * 16) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        if (S % 16)
+            *reinterpret_cast<uint2*>(base + (S / 16) * 512 + sl * 8) = make_uint2(w[4 * (S / 16)], w[4 * (S / 16) + 1]);
+    }
 }
 
-// dense AoS records -> tiles (validated like k_import).  One thread per session, 128-bit accesses on both sides.
-template <int P8>
-__global__ void __launch_bounds__(256)
-k_import_dense(const __grid_constant__ DevTable T, const __grid_constant__ InitRec init, uint8_t* tiles, uint64_t first, uint64_t count,
-               const uint8_t* in, uint32_t* err, ImportReset R) {
-    constexpr int DW = DenseW<P8>::WORDS;
-    if (blockIdx.x == 0 && threadIdx.x == 0) import_reset(R);
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t d[DW], w[12 + P8 / 4];
+// AoS records of one wire format -> canonical words and back (WD: dense wire record, else the canonical record).
+// wire_load returns non-zero when the padding of a dense record is not zero.
+template <int P8, bool WD>
+__device__ __forceinline__ uint32_t wire_load(const uint8_t* in, uint64_t j, uint32_t (&w)[12 + P8 / 4]) {
+    if constexpr (WD) {
+        constexpr int DW = DenseW<P8>::WORDS;
+        uint32_t d[DW];
         const uint4* src = reinterpret_cast<const uint4*>(in + j * (4 * DW));
 #pragma unroll
         for (int k = 0; k < DW / 4; ++k) { const uint4 v = src[k]; d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w; }
-        const uint32_t pad = dense_unpack<P8>(d, w);
-        if (pad != 0 || words_invalid_w<P8>(T, w) != 0) {
+        return dense_unpack<P8>(d, w);
+    } else {
+        constexpr int CW = 12 + P8 / 4;                      // canonical records are 8-byte aligned (S % 8 == 0)
+        const uint2* src = reinterpret_cast<const uint2*>(in + j * (4 * CW));
+#pragma unroll
+        for (int k = 0; k < CW / 2; ++k) { const uint2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+        return 0u;
+    }
+}
+template <int P8, bool WD>
+__device__ __forceinline__ void wire_store(uint8_t* out, uint64_t j, const uint32_t (&w)[12 + P8 / 4]) {
+    if constexpr (WD) {
+        constexpr int DW = DenseW<P8>::WORDS;
+        uint32_t d[DW];
+        dense_pack<P8>(w, d);
+        uint4* dst = reinterpret_cast<uint4*>(out + j * (4 * DW));
+#pragma unroll
+        for (int k = 0; k < DW / 4; ++k) dst[k] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+    } else {
+        constexpr int CW = 12 + P8 / 4;
+        uint2* dst = reinterpret_cast<uint2*>(out + j * (4 * CW));
+#pragma unroll
+        for (int k = 0; k < CW / 2; ++k) dst[k] = make_uint2(w[2 * k], w[2 * k + 1]);
+    }
+}
+
+// AoS records -> tiles for the werewolf family, any wire format (WD) and any store format (PK), validated like k_import
+// (err == NULL: trusted records, no validation).  One thread per session, wide accesses on both sides.  `init` holds
+// the CANONICAL words of the initial record.
+template <int P8, bool WD, bool PK>
+__global__ void __launch_bounds__(256)
+k_import_w(const __grid_constant__ DevTable T, const __grid_constant__ InitRec init, uint8_t* tiles, uint64_t first, uint64_t count,
+           const uint8_t* in, uint32_t* err, ImportReset R) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) import_reset(R);
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w[12 + P8 / 4];
+        const uint32_t pad = wire_load<P8, WD>(in, j, w);
+        if (err != nullptr && (pad != 0 || words_invalid_w<P8>(T, w) != 0)) {
             atomicAdd_system(&err[0], 1u);
             atomicMax_system(&err[1], ~(uint32_t)(j > 0xFFFFFFFEull ? 0xFFFFFFFEull : j));
 #pragma unroll
             for (int k = 0; k < 12 + P8 / 4; ++k) w[k] = init.w[k];
         }
-        tile_store_words<P8>(tiles, first + j, w);
+        tile_store_words<P8, PK>(tiles, first + j, w);
     }
 }
 
-// tiles -> dense AoS records; origin != NULL: slots are permuted (compaction), records leave in original order
-template <int P8>
+// tiles -> AoS records; origin != NULL: slots are permuted (compaction), records leave in original order
+template <int P8, bool WD, bool PK>
 __global__ void __launch_bounds__(256)
-k_export_dense(const uint8_t* tiles, const uint32_t* __restrict__ origin, uint64_t n, uint64_t first, uint64_t count, uint8_t* out) {
-    constexpr int DW = DenseW<P8>::WORDS;
+k_export_w(const uint8_t* tiles, const uint32_t* __restrict__ origin, uint64_t n, uint64_t first, uint64_t count, uint8_t* out) {
     const uint64_t lo = origin ? 0 : first, hi = origin ? n : first + count;
     for (uint64_t slot = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < hi; slot += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t o = origin ? origin[slot] : slot;
         if (o < first || o >= first + count) continue;
-        uint32_t d[DW], w[12 + P8 / 4];
-        tile_load_words<P8>(tiles, slot, w);
-        dense_pack<P8>(w, d);
-        uint4* dst = reinterpret_cast<uint4*>(out + (o - first) * (4 * DW));
-#pragma unroll
-        for (int k = 0; k < DW / 4; ++k) dst[k] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+        uint32_t w[12 + P8 / 4];
+        tile_load_words<P8, PK>(tiles, slot, w);
+        wire_store<P8, WD>(out, o - first, w);
+    }
+}
+
+// canonical columns <-> packed store, slot by slot (slot order, and with it the origin map of compaction, is kept)
+template <int P8>
+__global__ void __launch_bounds__(256)
+k_repack(const uint8_t* src, uint8_t* dst, uint64_t slots, int to_packed) {
+    for (uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < slots; slot += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w[12 + P8 / 4];
+        if (to_packed) { tile_load_words<P8, false>(src, slot, w); tile_store_words<P8, true>(dst, slot, w); }
+        else { tile_load_words<P8, true>(src, slot, w); tile_store_words<P8, false>(dst, slot, w); }
     }
 }
 
 // final-state histograms (SPEC.md section 6): winner, length, survivors / scores.  sh = 515 shared counters.
-__device__ __forceinline__ void stats_one(const DevTable& T, const uint8_t* tiles, uint32_t S_dev, uint64_t i, uint32_t* sh) {
+// pk: the packed store keeps is_alive in the low byte of word 2
+__device__ __forceinline__ void stats_one(const DevTable& T, const uint8_t* tiles, uint32_t S_dev, uint64_t i, uint32_t* sh, uint32_t pk) {
     const uint32_t n16 = S_dev / 16;
     const int P = T.h.n_players;
     const uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
@@ -255,7 +315,7 @@ __device__ __forceinline__ void stats_one(const DevTable& T, const uint8_t* tile
     if (T.h.family == FAM_WEREWOLF) {
         const uint32_t w = c0.y & 0xFF;
         atomicAdd(&sh[w <= 2 ? w : 0], 1u);
-        if (terminal) atomicAdd(&sh[3 + 256 + __popc(c0.z)], 1u);
+        if (terminal) atomicAdd(&sh[3 + 256 + __popc(pk ? c0.z & 0xFFu : c0.z)], 1u);
     } else {
         atomicAdd(&sh[terminal ? 1 : 0], 1u);
         if (terminal)
@@ -276,12 +336,12 @@ __device__ __forceinline__ void stats_flush(const uint32_t* sh, unsigned long lo
 }
 
 __global__ void __launch_bounds__(256)
-k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev, uint64_t n, unsigned long long* stats) {
+k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev, uint64_t n, unsigned long long* stats, uint32_t pk) {
     __shared__ uint32_t sh[3 + 256 + 256];
     for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        stats_one(T, tiles, S_dev, i, sh);
+        stats_one(T, tiles, S_dev, i, sh, pk);
     __syncthreads();
     stats_flush(sh, stats);
 }
@@ -294,7 +354,7 @@ k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev
 // Both are no-ops (one uniform load) while games are still running.
 __global__ void __launch_bounds__(256)
 k_autoreset_apply(const __grid_constant__ DevTable T, uint8_t* tiles, uint32_t S_dev, uint64_t n, uint64_t n_tiles,
-                  const __grid_constant__ InitRec rec, uint32_t* origin, unsigned long long* stats, const unsigned long long* cstate) {
+                  const __grid_constant__ InitRec rec, uint32_t* origin, unsigned long long* stats, const unsigned long long* cstate, uint32_t pk) {
     __shared__ uint32_t sh[3 + 256 + 256];
     if (cstate[0] != 0) return;
     for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
@@ -302,7 +362,7 @@ k_autoreset_apply(const __grid_constant__ DevTable T, uint8_t* tiles, uint32_t S
     const uint32_t n16 = S_dev / 16;
     const uint64_t total = n_tiles * 32;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (i < n) stats_one(T, tiles, S_dev, i, sh);            // read the finished game first ...
+        if (i < n) stats_one(T, tiles, S_dev, i, sh, pk);        // read the finished game first ...
         uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
         const uint32_t sl = (uint32_t)(i & 31);
         for (uint32_t k = 0; k < S_dev / 8; ++k)                   // ... then overwrite the same slot

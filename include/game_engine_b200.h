@@ -93,6 +93,10 @@ int ge_table_n_players(const ge_table *t);
  * predicate or effect of the phase touches them).  Weighted by the visit histogram of the statistics this gives the
  * necessary DRAM traffic per session-phase-step, the honest lower bound next to the 2*S "algorithmic" figure. */
 int ge_table_phase_io(const ge_table *t, int phase_index, uint32_t *read_bytes, uint32_t *write_bytes);
+/* The same for the packed session store (GE_OPT_STORE_PACKED; werewolf-family tables up to 8 players, else
+ * GE_ERR_UNSUPPORTED): column D0 (16 bytes) both ways on every step, column D1 (16 bytes) only when the phase reads or
+ * changes the role bytes or the target bytes. */
+int ge_table_phase_io_packed(const ge_table *t, int phase_index, uint32_t *read_bytes, uint32_t *write_bytes);
 
 /* Allocate n_sessions sessions on `device` and initialise them from the DSL template.
  * Session i has id first_session_id + i.  Replaces initialize_player_states_from_dsl
@@ -147,8 +151,16 @@ int ge_batch_get_kernel(const ge_batch *b);
 /* Tuning options of a batch.  GE_OPT_LIGHT_BULK (werewolf family, specialised / interpreter single-batch kernels):
  * launches whose sessions are all in header-only phases fetch their 512-byte columns with cp.async.bulk into shared
  * memory, completion counted by an mbarrier, double-buffered one group of four tiles ahead, instead of warp-wide
- * 128-bit loads.  Off by default (measured: DESIGN section 6). */
+ * 128-bit loads.  Off by default (measured: DESIGN section 6).
+ * GE_OPT_STORE_PACKED (werewolf-family tables up to 8 players): the session store in HBM keeps a record as the 32 bytes of
+ * the dense wire format (two 16-byte columns: header + eight mask bytes | role bytes + target bytes) instead of the
+ * canonical 56 bytes in 3.5 columns whose mask words are three-quarters zeros; the all-bot thread-per-session kernels
+ * run on it directly.  Records at the ABI are unchanged (canonical or dense wire, as ge_batch_set_wire says); callers
+ * the packed layout does not serve (lane-per-player kernels, human seats, phase regrouping, ge_eval_preds) convert the
+ * store back transparently.  ON by default for the tables it covers (value 0 = keep the canonical columns);
+ * GE_ERR_UNSUPPORTED when switched on for other tables. */
 #define GE_OPT_LIGHT_BULK 1
+#define GE_OPT_STORE_PACKED 2
 int ge_batch_set_option(ge_batch *b, int option, int value);
 
 /* Record format of the host-buffer calls of this batch (ge_export_state, ge_import_state, ge_run_host[_async]):

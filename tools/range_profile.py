@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--cap", type=int, default=0)
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--launch", default="streams", choices=["streams", "ring"], help="one launch per batch on --streams streams, or one ring launch per pass")
+    ap.add_argument("--store", default="packed", choices=["canonical", "packed"])
     a = ap.parse_args()
     from bench import game_cap
     dev = torch.device("cuda", 0)
@@ -57,6 +58,8 @@ def main():
     for i, b in enumerate(ring):
         b.set_stream(streams[i % NS].cuda_stream)
         b.set_grid(0 if merged else a.ctas_per_sm)
+        if cg.family == 1 and a.players <= 8:
+            b.set_option("store_packed", 1 if a.store == "packed" else 0)
     age, epoch = [0] * R, [0] * R
     for i, b in enumerate(ring):
         pre = (i * cap) // R
@@ -99,7 +102,8 @@ def main():
     S = cg.record_size
     print(json.dumps({"game": a.game, "players": a.players, "sessions_per_batch": N, "ring": R, "launch": a.launch, "streams": NS,
                       "ctas_per_sm": a.ctas_per_sm, "passes": a.steps, "region_ms": ms, "counted_steps": counted,
-                      "launches": launches, "steps_per_s": counted / (ms * 1e-3), "record_bytes": S,
+                      "launches": launches, "steps_per_s": counted / (ms * 1e-3),
+                      "record_bytes": ring[0].state_device_bytes() // (((N + 31) // 32) * 32), "store": a.store,
                       "algorithmic_bytes": counted * 2 * S}), flush=True)
     for b in ring:
         b.close()
