@@ -15,7 +15,9 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
-LIB = os.path.join(_HERE, "libgame_engine_b200.so")
+# GE_LIB_OUT: build a variant library (A/B of compile-time knobs with GE_EXTRA_NVCC) next to the product one; GE_LIB makes
+# capi.py load it
+LIB = os.environ.get("GE_LIB_OUT") or os.path.join(_HERE, "libgame_engine_b200.so")
 PUBLIC_H = os.path.join("..", "..", "include", "game_engine_b200.h")
 KERNEL_HEADERS = ["ge_common.cuh", "ge_step_tps.cuh", "ge_step_coop.cuh", "ge_spec_gen.cuh", "ge_kernels.h", PUBLIC_H]
 KERNEL_SETS = [(1, 8), (1, 16), (1, 24), (1, 32), (2, 4), (2, 8), (2, 16), (2, 32)]      # ge_kernels.h GE_KERNEL_SETS

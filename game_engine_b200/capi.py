@@ -104,7 +104,7 @@ _lib = None
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        _lib = load()
+        _lib = load(os.environ.get("GE_LIB") or LIB_PATH)       # GE_LIB: an A/B build of the same library (build.py GE_LIB_OUT)
     return _lib
 
 

@@ -23,6 +23,21 @@ struct WState {
     uint32_t eligible, submitted, revealed, investigated;   // column 1
     uint32_t wolf, secret, role_lo, role_hi;           // column 2
     uint32_t tw[P8 / 4];                               // selected_target_id bytes
+    // Packed store (up to 8 players): the ten masks as they sit in HBM — pk0 = alive | can_vote << 8 | eligible << 16 |
+    // submitted << 24, pk1 = revealed | investigated << 8 | wolf << 16 | secret << 24, pk2 = role_lo | role_hi << 8.  A step
+    // unpacks them INSIDE its per-phase body and packs them again at its end, so that with a build-time table every phase
+    // extracts only the fields it reads and re-inserts only the ones it writes (pack(unpack(x)) folds to x).
+    uint32_t pk0, pk1, pk2;
+    __device__ __forceinline__ void unpack() {
+        alive = pk0 & 0xFFu; can_vote = (pk0 >> 8) & 0xFFu; eligible = (pk0 >> 16) & 0xFFu; submitted = pk0 >> 24;
+        revealed = pk1 & 0xFFu; investigated = (pk1 >> 8) & 0xFFu; wolf = (pk1 >> 16) & 0xFFu; secret = pk1 >> 24;
+        role_lo = pk2 & 0xFFu; role_hi = (pk2 >> 8) & 0xFFu;
+    }
+    __device__ __forceinline__ void repack() {
+        pk0 = (alive & 0xFFu) | ((can_vote & 0xFFu) << 8) | ((eligible & 0xFFu) << 16) | (submitted << 24);
+        pk1 = (revealed & 0xFFu) | ((investigated & 0xFFu) << 8) | ((wolf & 0xFFu) << 16) | (secret << 24);
+        pk2 = (role_lo & 0xFFu) | ((role_hi & 0xFFu) << 8);
+    }
 };
 
 constexpr int TPS_THREADS = 128;
@@ -503,34 +518,74 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
 }
 
 // Generic entry: interpret the run-time table.  Returns the phase entered or -1 for a terminal session.
-template <int P8>
+template <int P8, bool PK = false>
 __device__ __forceinline__ int w_step(const DevTable& T, WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
                                       const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     const int X = s.h0 & 0xFF;
     if (T.phase[X].kind == KIND_TERMINAL) return -1;
     dirty |= DIRTY_C0;
     if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }    // SPEC D11
-    return w_step_body<P8>(RtView(T, X), X, s, F, K, sid_lo, sid_hi, A, dirty, H);
+    if constexpr (PK) s.unpack();
+    const int y = w_step_body<P8>(RtView(T, X), X, s, F, K, sid_lo, sid_hi, A, dirty, H);
+    if constexpr (PK) s.repack();
+    return y;
 }
 
-// Specialised entry: a warp-uniform switch over the phases of a build-time table.
-template <int P8, class Spec, int X>
+// Specialised entry: one compiled body per phase of a build-time table.
+template <int P8, class Spec, int X, bool PK>
 __device__ __forceinline__ int w_step_spec_case(WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
                                                 const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
-    if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
-    dirty |= DIRTY_C0;
-    if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
-    return w_step_body<P8>(CtView<Spec, X>{}, X, s, F, K, sid_lo, sid_hi, A, dirty, H);
-}
-
-template <int P8, class Spec, int X = 0>
-__device__ __forceinline__ int w_step_spec(WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
-                                           const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
     if constexpr (X >= Spec::n_phases) {
         return -1;
     } else {
-        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X>(s, F, K, sid_lo, sid_hi, A, dirty, H);
-        return w_step_spec<P8, Spec, X + 1>(s, F, K, sid_lo, sid_hi, A, dirty, H);
+        if (Spec::phase(X).kind == KIND_TERMINAL) return -1;
+        dirty |= DIRTY_C0;
+        if ((s.h0 >> 16) == 0) { s.h0 = (s.h0 & 0xFFFFu) | (1u << 16); return X; }
+        if constexpr (PK) s.unpack();
+        const int y = w_step_body<P8>(CtView<Spec, X>{}, X, s, F, K, sid_lo, sid_hi, A, dirty, H);
+        if constexpr (PK) s.repack();
+        return y;
+    }
+}
+
+// The body of phase X0.  The caller (w_tps_tiles) makes X0 uniform over the lanes that get here — the sessions of a batch
+// move in lockstep, so a tile's live sessions are nearly always in ONE phase — which turns the dispatch into one indexed
+// branch instead of a chain of up to n_phases compare-and-branch pairs per tile (4-7 % of the step's instructions, ncu).
+template <int P8, class Spec, bool PK>
+__device__ __forceinline__ int w_step_spec(const int X0, WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
+                                           const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
+#define GE_W_CASE(X) case X: return w_step_spec_case<P8, Spec, X, PK>(s, F, K, sid_lo, sid_hi, A, dirty, H);
+    switch (X0) {
+        GE_W_CASE(0) GE_W_CASE(1) GE_W_CASE(2) GE_W_CASE(3) GE_W_CASE(4) GE_W_CASE(5) GE_W_CASE(6) GE_W_CASE(7)
+        GE_W_CASE(8) GE_W_CASE(9) GE_W_CASE(10) GE_W_CASE(11) GE_W_CASE(12) GE_W_CASE(13) GE_W_CASE(14) GE_W_CASE(15)
+        GE_W_CASE(16) GE_W_CASE(17) GE_W_CASE(18) GE_W_CASE(19) GE_W_CASE(20) GE_W_CASE(21) GE_W_CASE(22) GE_W_CASE(23)
+        GE_W_CASE(24) GE_W_CASE(25) GE_W_CASE(26) GE_W_CASE(27) GE_W_CASE(28) GE_W_CASE(29) GE_W_CASE(30) GE_W_CASE(31)
+    default: return -1;
+    }
+#undef GE_W_CASE
+}
+// Per-lane dispatch as a balanced tree of compares over the phase index: ceil(log2(n_phases)) compare-and-branch pairs
+// instead of up to n_phases (the chain below); lanes of a tile that sit in different phases simply diverge.
+template <int P8, class Spec, bool PK, int LO = 0, int HI = Spec::n_phases>
+__device__ __forceinline__ int w_step_spec_tree(WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
+                                                const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
+    if constexpr (HI - LO <= 1) {
+        return w_step_spec_case<P8, Spec, LO, PK>(s, F, K, sid_lo, sid_hi, A, dirty, H);
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        if ((int)(s.h0 & 0xFF) < MID) return w_step_spec_tree<P8, Spec, PK, LO, MID>(s, F, K, sid_lo, sid_hi, A, dirty, H);
+        return w_step_spec_tree<P8, Spec, PK, MID, HI>(s, F, K, sid_lo, sid_hi, A, dirty, H);
+    }
+}
+// A/B twin (-DGE_CHAIN_DISPATCH): the per-lane chain of compare-and-branch pairs over the phases
+template <int P8, class Spec, bool PK, int X = 0>
+__device__ __forceinline__ int w_step_spec_chain(WState<P8>& s, const FieldTable& F, const PlSink& K, uint32_t sid_lo, uint32_t sid_hi,
+                                                 const StepArgs& A, uint32_t& dirty, const HumanIn& H) {
+    if constexpr (X >= Spec::n_phases) {
+        return -1;
+    } else {
+        if ((int)(s.h0 & 0xFF) == X) return w_step_spec_case<P8, Spec, X, PK>(s, F, K, sid_lo, sid_hi, A, dirty, H);
+        return w_step_spec_chain<P8, Spec, PK, X + 1>(s, F, K, sid_lo, sid_hi, A, dirty, H);
     }
 }
 
@@ -792,9 +847,7 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
                     if (need_next & 16) prefetch_l1(base + tile_stride + 512);
                 }
                 s.h0 = d0.x; s.h1 = d0.y;
-                s.alive = d0.z & 0xFFu; s.can_vote = (d0.z >> 8) & 0xFFu; s.eligible = (d0.z >> 16) & 0xFFu; s.submitted = d0.z >> 24;
-                s.revealed = d0.w & 0xFFu; s.investigated = (d0.w >> 8) & 0xFFu; s.wolf = (d0.w >> 16) & 0xFFu; s.secret = d0.w >> 24;
-                s.role_lo = d1.x & 0xFFu; s.role_hi = (d1.x >> 8) & 0xFFu;
+                s.pk0 = d0.z; s.pk1 = d0.w; s.pk2 = d1.x;             // unpacked inside the step (WState::unpack)
                 s.tw[0] = d1.y; s.tw[1] = d1.z;
             } else {
             const uint4 c0 = ld128(base);
@@ -845,13 +898,28 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             }
             for (int it = 0; it < C.n_steps; ++it) {
                 int np = -1;
-                if (live) {
-                    if constexpr (std::is_void<Spec>::value)
-                        np = w_step<P8>(T, s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
-                    else
-                        np = w_step_spec<P8, Spec>(s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
-                    if (np < 0) live = false;
+                if constexpr (std::is_void<Spec>::value) {
+                    if (live) np = w_step<P8, PK>(T, s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
+                } else {
+                    // phase dispatch: a per-lane compare tree (default); A/B twins: the linear chain (-DGE_CHAIN_DISPATCH)
+                    // and the warp-uniform switch loop (-DGE_LOOP_DISPATCH) — measured in DESIGN section 6
+#if defined(GE_CHAIN_DISPATCH)
+                    if (live) np = w_step_spec_chain<P8, Spec, PK>(s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
+#elif !defined(GE_LOOP_DISPATCH)
+                    if (live) np = w_step_spec_tree<P8, Spec, PK>(s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
+#else
+                    // one iteration per distinct phase among the tile's live sessions (nearly always one): the phase is
+                    // uniform over the lanes that enter the switch
+                    uint32_t todo = __ballot_sync(0xFFFFFFFFu, live);
+                    while (todo) {
+                        const int X0 = __shfl_sync(0xFFFFFFFFu, (int)(s.h0 & 0xFFu), __ffs(todo) - 1);
+                        const bool mine = ((todo >> lane) & 1u) && (int)(s.h0 & 0xFFu) == X0;
+                        if (mine) np = w_step_spec<P8, Spec, PK>(X0, s, F, K, (uint32_t)sid, (uint32_t)(sid >> 32), C, dirty, H);
+                        todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
+                    }
+#endif
                 }
+                if (live && np < 0) live = false;
                 mixed += visits.add(s_visits, np, lane) > 1;
             }
             if (in_range) present_out |= 1u << (s.h0 & 31);
@@ -863,10 +931,8 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             }
             live_cnt += __popc(lm);
             if constexpr (PK) {
-                if (dirty & (DIRTY_C0 | DIRTY_C1 | DIRTY_C2))
-                    st128(base, make_uint4(s.h0, s.h1, s.alive | (s.can_vote << 8) | (s.eligible << 16) | (s.submitted << 24),
-                                           s.revealed | (s.investigated << 8) | (s.wolf << 16) | (s.secret << 24)));
-                if (dirty & (DIRTY_C2 | DIRTY_PL)) st128(base + 512, make_uint4(s.role_lo | (s.role_hi << 8), s.tw[0], s.tw[1], 0u));
+                if (dirty & (DIRTY_C0 | DIRTY_C1 | DIRTY_C2)) st128(base, make_uint4(s.h0, s.h1, s.pk0, s.pk1));
+                if (dirty & (DIRTY_C2 | DIRTY_PL)) st128(base + 512, make_uint4(s.pk2, s.tw[0], s.tw[1], 0u));
             } else {
             if (dirty & DIRTY_C0) st128(base, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
             if (dirty & DIRTY_C1) st128(base + 512, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
