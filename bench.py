@@ -98,6 +98,7 @@ def parse_args():
     ap.add_argument("--regroup", default="", help="phase regrouping 'every,shift' (default: the library's choice for the table)")
     ap.add_argument("--light-bulk", action="store_true",
                     help="A/B: header-only launches fetch their tiles with cp.async.bulk + mbarrier (ge_batch_set_option)")
+    ap.add_argument("--no-pdl", action="store_true", help="A/B: plain stream-ordered step launches instead of programmatic dependent launches (GE_OPT_PDL 0)")
     ap.add_argument("--store", default="packed", choices=["canonical", "packed"],
                     help="session store in HBM: packed (werewolf tables up to 8 players keep a 32-byte record in two 16-byte columns, "
                          "the library's default for them; other tables are canonical either way) or canonical columns for every table "
@@ -405,9 +406,9 @@ def run_ours(a):
     cap = a.cap or game_cap(cg.family, a.players, cg.table.max_revotes)
     N, R = a.sessions, a.ring
     tab = Table(cg)
-    packable = cg.family == 1 and a.players <= 8
+    packable = cg.family == 1 and a.players <= 16
     packed = a.store == "packed" and packable and a.kernel != "coop" and cg.table.max_revotes == 0
-    S_store = 32 if packed else S                    # bytes per session resident in HBM
+    S_store = (32 if a.players <= 8 else 48) if packed else S                    # bytes per session resident in HBM
     # the ring's batches are independent sessions: batch i runs on stream i % NS so that one batch's launch
     # ramp / tail and near-empty late-game launches overlap with another batch's work
     merged = a.launch == "ring" and a.kernel != "coop"
@@ -428,6 +429,8 @@ def run_ours(a):
             b.set_option("light_bulk", 1)
         if packable:
             b.set_option("store_packed", 1 if packed else 0)
+        if a.no_pdl:
+            b.set_option("pdl", 0)
         if a.regroup:
             b.set_regroup(*[int(x) for x in a.regroup.split(",")])
         if a.compaction:
@@ -714,7 +717,7 @@ def run_ours(a):
             "workload": "%s.yaml, %d players, %d sessions per batch per GPU, Philox bots" % (a.game, a.players, N),
             "baseline_config": a.config,
             "light_path": "cp.async.bulk + mbarrier" if a.light_bulk else "LDG.128", "kernel": kern, "launch": ("%d ring launch(es) per pass (ge_step_ring)" % NS) if merged else "one launch per batch", "streams": NS,
-            "ctas_per_sm": "occupancy limit" if merged else a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S_store, "store": "packed (32 bytes per session in HBM)" if packed else "canonical columns", "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
+            "ctas_per_sm": "occupancy limit" if merged else a.ctas_per_sm, "ring_batches": R, "ring_bytes": R * N * S_store, "store": ("packed (%d bytes per session in HBM)" % S_store) if packed else "canonical columns", "l2_policy": "inputs larger than L2 (ring of batches, round-robin)",
             "steps_before_reinit": "when every game of the batch is over (device-side auto-reset, checked every 8 steps)" if auto else cap,
             "reinits_in_timed_region": resets, "record_bytes": S, "seed": a.seed,
             "parallelism": "dp%d (independent session shards, one NCCL all-reduce of the statistics)" % world,

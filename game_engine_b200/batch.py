@@ -134,7 +134,7 @@ class SessionBatch:
     def set_option(self, option: str, value: int) -> None:
         """Tuning options: "light_bulk" (header-only launches fetch their tiles with cp.async.bulk + mbarrier);
         "store_packed" (werewolf tables up to 8 players: 32-byte records in HBM, two 16-byte columns)."""
-        capi.check(capi.lib().ge_batch_set_option(self._h, {"light_bulk": capi.OPT_LIGHT_BULK, "store_packed": capi.OPT_STORE_PACKED}[option], int(value)))
+        capi.check(capi.lib().ge_batch_set_option(self._h, {"light_bulk": capi.OPT_LIGHT_BULK, "store_packed": capi.OPT_STORE_PACKED, "pdl": capi.OPT_PDL}[option], int(value)))
 
     def set_grid(self, ctas_per_sm: int) -> None:
         """Persistent grid of the step launches = SMs x ctas_per_sm (0 = as many as fit).  Smaller grids let the

@@ -18,6 +18,7 @@ GE_OK, GE_ERR_ARG, GE_ERR_CUDA, GE_ERR_UNSUPPORTED, GE_ERR_NOMEM = 0, -1, -2, -3
 KERNEL_AUTO, KERNEL_COOP, KERNEL_TPS, KERNEL_TPS_GENERIC = 0, 1, 2, 3
 OPT_LIGHT_BULK = 1
 OPT_STORE_PACKED = 2
+OPT_PDL = 3
 WIRE_CANONICAL, WIRE_DENSE = 0, 1
 WIRE_NAMES = {"canonical": WIRE_CANONICAL, "dense": WIRE_DENSE}
 KERNEL_NAMES = {"auto": KERNEL_AUTO, "coop": KERNEL_COOP, "tps": KERNEL_TPS, "tps_generic": KERNEL_TPS_GENERIC}

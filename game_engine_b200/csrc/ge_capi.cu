@@ -111,6 +111,7 @@ struct ge_batch {
     // masks) converts the store back first (ensure_store).
     bool want_packed, packed;
     size_t rec_store;
+    bool pdl;                     // GE_OPT_PDL: step launches carry the programmatic-stream-serialization attribute
 };
 
 static int restore_order(ge_batch* b, bool keep_records);
@@ -260,23 +261,28 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
                     const ge_pred_t& p = t->dev.pred[pi];
                     const uint16_t lits[4] = {p.pos0, p.neg0, p.pos1, p.neg1};
                     for (int c = 0; c < 2; ++c)
-                        if (!(lits[2 * c + 1] & 0x8000u) && ((lits[2 * c] | lits[2 * c + 1]) & 0x0F00u)) return true;
+                        if (!(lits[2 * c + 1] & 0x8000u) && ((lits[2 * c] | lits[2 * c + 1]) & (h.n_players > 8 ? 0x1FF0u : 0x0F00u))) return true;
                     if (!(p.pos0 & GE_PRED_CONTINUED)) break;
                 }
                 return false;
             };
-            bool d1 = (need & 4) != 0;
+            // (up to 16 players the packed store has three columns: D1 = role_revealed, investigated, team, secret and role
+            // masks — fields 4..12 —, read when a predicate names one or an effect changes part of it (INVESTIGATE_RESOLVE,
+            // DAY_VOTE's reveal, ASSIGN_ROLES); the target bytes are D2, governed by bit 2 as in the canonical store)
+            const bool wide = h.n_players > 8;
+            bool d1 = !wide && (need & 4) != 0;
             if (ph.kind == KIND_ACTION) {
                 d1 |= pred_roles(ph.actor_pred);
                 if (ph.action_op == ACT_PICK_PLAYER) d1 |= pred_roles(ph.action_arg);
-                if (ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE) d1 = true;      // recorded targets
+                if (!wide && ph.exit_op >= EX_VOTE_KILL && ph.exit_op <= EX_DAY_VOTE) d1 = true;      // recorded targets
+                if (wide && (ph.exit_op == EX_INVESTIGATE_RESOLVE || ph.exit_op == EX_DAY_VOTE)) d1 = true;
             }
             for (int b = 0; b < ph.n_branches; ++b) {
                 const ge_branch_t& br = ph.br[b];
                 if (br.op == BR_COUNT_EQ0 || br.op == BR_COUNT_GE) d1 |= pred_roles(br.a);
                 if (br.op == BR_COUNT_GE) d1 |= pred_roles((int)br.arg);
                 const int en = t->dev.phase[br.next].entry_op;
-                if (en == EN_ASSIGN_ROLES || en == EN_NIGHT_RESET) d1 = true;
+                if (en == EN_ASSIGN_ROLES || (!wide && en == EN_NIGHT_RESET)) d1 = true;
             }
             if (d1) need |= 16;
         }
@@ -308,8 +314,17 @@ static int validate_and_build(const uint8_t* blob, size_t n, ge_table* t) {
             t->io_read[i] = (uint16_t)rd; t->io_write[i] = (uint16_t)wr;
             // packed store (up to 8 players): D0 both ways on every step, D1 when `need` bit 4 says so / when the role or
             // target bytes change
-            t->io_read_pk[i] = (uint16_t)(P8 == 8 ? 16 + ((need & 16) ? 16 : 0) : 0);
-            t->io_write_pk[i] = (uint16_t)(P8 == 8 ? 16 + ((records || en_assign || en_reset) ? 16 : 0) : 0);
+            if (P8 == 8) {
+                t->io_read_pk[i] = (uint16_t)(16 + ((need & 16) ? 16 : 0));
+                t->io_write_pk[i] = (uint16_t)(16 + ((records || en_assign || en_reset) ? 16 : 0));
+            } else if (P8 == 16) {
+                const bool d1w = en_assign || (ph.kind == KIND_ACTION && (ph.exit_op == EX_INVESTIGATE_RESOLVE || ph.exit_op == EX_DAY_VOTE));
+                int wr_pk = 16 + (d1w ? 16 : 0);
+                if (en_reset || (records && ph.exit_op == EX_DAY_VOTE)) wr_pk += 16;
+                else if (records) wr_pk += ph.exit_op == EX_VOTE_KILL ? h.n_wolves : 1;
+                t->io_read_pk[i] = (uint16_t)(16 + ((need & 16) ? 16 : 0) + ((need & 4) ? 16 : 0));
+                t->io_write_pk[i] = (uint16_t)wr_pk;
+            }
         } else {
             const int bucket = h.n_players <= 4 ? 4 : h.n_players <= 8 ? 8 : h.n_players <= 16 ? 16 : 32;
             const int S = 8 + 4 * bucket;
@@ -392,7 +407,7 @@ extern "C" int ge_table_phase_io(const ge_table* t, int phase_index, uint32_t* r
 }
 extern "C" int ge_table_phase_io_packed(const ge_table* t, int phase_index, uint32_t* read_bytes, uint32_t* write_bytes) {
     if (!t || phase_index < 0 || phase_index >= t->dev.h.n_phases) return fail(GE_ERR_ARG, "bad arguments to ge_table_phase_io_packed");
-    if (!(t->family == FAM_WEREWOLF && t->bucket == 8)) return fail(GE_ERR_UNSUPPORTED, "the packed store covers werewolf-family tables up to 8 players");
+    if (!(t->family == FAM_WEREWOLF && t->bucket <= 16)) return fail(GE_ERR_UNSUPPORTED, "the packed store covers werewolf-family tables up to 16 players");
     if (read_bytes) *read_bytes = t->io_read_pk[phase_index];
     if (write_bytes) *write_bytes = t->io_write_pk[phase_index];
     return GE_OK;
@@ -433,10 +448,16 @@ static InitRec init_rec(const ge_batch* b) {
     const uint32_t* w = b->tab->init_words;
     if (!b->packed) { memcpy(rec.w, w, sizeof rec.w); return rec; }
     rec.w[0] = w[0]; rec.w[1] = w[1];
-    rec.w[2] = (w[2] & 0xFFu) | ((w[3] & 0xFFu) << 8) | ((w[4] & 0xFFu) << 16) | ((w[5] & 0xFFu) << 24);
-    rec.w[3] = (w[6] & 0xFFu) | ((w[7] & 0xFFu) << 8) | ((w[8] & 0xFFu) << 16) | ((w[9] & 0xFFu) << 24);
-    rec.w[4] = (w[10] & 0xFFu) | ((w[11] & 0xFFu) << 8);
-    rec.w[5] = w[12]; rec.w[6] = w[13]; rec.w[7] = 0;
+    if (b->tab->bucket == 8) {
+        rec.w[2] = (w[2] & 0xFFu) | ((w[3] & 0xFFu) << 8) | ((w[4] & 0xFFu) << 16) | ((w[5] & 0xFFu) << 24);
+        rec.w[3] = (w[6] & 0xFFu) | ((w[7] & 0xFFu) << 8) | ((w[8] & 0xFFu) << 16) | ((w[9] & 0xFFu) << 24);
+        rec.w[4] = (w[10] & 0xFFu) | ((w[11] & 0xFFu) << 8);
+        rec.w[5] = w[12]; rec.w[6] = w[13]; rec.w[7] = 0;
+    } else {
+        for (int k = 0; k < 5; ++k) rec.w[2 + k] = (w[2 + 2 * k] & 0xFFFFu) | ((w[3 + 2 * k] & 0xFFFFu) << 16);
+        rec.w[7] = 0;
+        for (int k = 0; k < 4; ++k) rec.w[8 + k] = w[12 + k];
+    }
     return rec;
 }
 static InitRec init_rec_canon(const ge_batch* b) {
@@ -444,7 +465,10 @@ static InitRec init_rec_canon(const ge_batch* b) {
     memcpy(rec.w, b->tab->init_words, sizeof rec.w);
     return rec;
 }
-static bool packable(const ge_table* t) { return t->family == FAM_WEREWOLF && t->bucket == 8 && t->ks.tps_pk != nullptr; }
+static bool packable(const ge_table* t) { return t->family == FAM_WEREWOLF && t->bucket <= 16 && t->ks.tps_pk != nullptr; }
+static size_t packed_record(const ge_table* t) { return t->bucket == 8 ? 32 : 48; }
+// where is_alive sits in word 2 of the stored record (k_stats)
+static uint32_t alive_mask_of(const ge_batch* b) { return !b->packed ? 0xFFFFFFFFu : b->tab->bucket == 8 ? 0xFFu : 0xFFFFu; }
 // the layout the batch's next step launch wants
 static bool store_should_be_packed(const ge_batch* b) {
     return b->want_packed && packable(b->tab) && b->kernel != GE_KERNEL_COOP && !b->d_hmask && b->regroup_every == 0;
@@ -474,7 +498,7 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
 extern "C" int ge_batch_reset(ge_batch* b, uint64_t first_session_id, uint64_t seed) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     CU(cudaSetDevice(b->device));
-    k_stats<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->d_stats, b->packed ? 1u : 0u);
+    k_stats<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->d_stats, alive_mask_of(b));
     CU(cudaGetLastError());
     b->launches++;
     return init_sessions(b, first_session_id, seed);
@@ -561,9 +585,10 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
             if (t->dev.phase[i].br[k].op == BR_TIE_PENDING) desync = true;
     // tables up to 8 players keep their records packed (32 bytes in two columns; +10 % on the headline workload, DESIGN
     // section 6) unless something the packed layout does not serve is switched on (GE_OPT_STORE_PACKED 0 = canonical)
+    b->pdl = true;                // programmatic dependent launches: never slower, +16 % on a single stream
     b->want_packed = packable(t);
     b->packed = b->want_packed && !(desync && t->family == FAM_WEREWOLF && b->n <= (1ull << 31));
-    b->rec_store = b->packed ? 32 : t->rec_dev;
+    b->rec_store = b->packed ? packed_record(t) : t->rec_dev;
     int rc = ge_batch_clear_stats(b);
     if (rc == GE_OK) rc = init_sessions(b, first_session_id, seed);
     if (rc == GE_OK && desync && t->family == FAM_WEREWOLF && b->n <= (1ull << 31)) rc = ge_batch_set_regroup(b, 5, 3);
@@ -650,8 +675,9 @@ extern "C" int ge_batch_set_option(ge_batch* b, int option, int value) {
         b->step_flags = value ? (b->step_flags | STEP_LIGHT_BULK) : (b->step_flags & ~(uint32_t)STEP_LIGHT_BULK);
         return GE_OK;
     }
+    if (option == GE_OPT_PDL) { b->pdl = value != 0; return GE_OK; }
     if (option == GE_OPT_STORE_PACKED) {
-        if (value && !packable(b->tab)) return fail(GE_ERR_UNSUPPORTED, "the packed store covers werewolf-family tables up to 8 players");
+        if (value && !packable(b->tab)) return fail(GE_ERR_UNSUPPORTED, "the packed store covers werewolf-family tables up to 16 players");
         b->want_packed = value != 0;
         CU(cudaSetDevice(b->device));
         return ensure_store(b, store_should_be_packed(b), b->stream);
@@ -881,7 +907,21 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
         // the bulk-copy variant of the light path stages its tiles in dynamic shared memory (werewolf single-batch kernels)
         const bool bulk = (a.flags & STEP_LIGHT_BULK) && b->tab->family == FAM_WEREWOLF && !b->d_hmask && b->kernel != GE_KERNEL_COOP;
         if (!bulk) a.flags &= ~(uint32_t)STEP_LIGHT_BULK;
-        fn<<<b->grid[b->kernel], 128, bulk ? sizeof(LightBulk) : 0, st>>>(b->tab->dev, a);
+        if (b->pdl && b->kernel != GE_KERNEL_COOP) {        // (the lane-per-player kernels have no device-side wait)
+            // the launch may begin while the previous kernel of the stream drains; it waits (griddepcontrol.wait) before
+            // it reads anything that kernel wrote
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3((unsigned)b->grid[b->kernel]); cfg.blockDim = dim3(128);
+            cfg.dynamicSmemBytes = bulk ? sizeof(LightBulk) : 0; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&cfg, fn, b->tab->dev, a));
+        } else {
+            fn<<<b->grid[b->kernel], 128, bulk ? sizeof(LightBulk) : 0, st>>>(b->tab->dev, a);
+        }
         b->launches++;
         b->since_compact++;
         if (b->hchoice_set) { const int rc = consume_human_inputs(b, st); if (rc != GE_OK) return rc; }
@@ -895,7 +935,7 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
         if ((regroup_after || compact_after) && b->sid_stride != 0) {      // every game over? start the next epoch on the device
             const InitRec rec = init_rec(b);
             k_autoreset_apply<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(
-                b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->n_tiles, rec, b->d_origin, b->d_stats, b->d_cstate, b->packed ? 1u : 0u);
+                b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->n_tiles, rec, b->d_origin, b->d_stats, b->d_cstate, alive_mask_of(b));
             k_autoreset_commit<<<1, 32, 0, st>>>(b->d_cstate, b->d_presence, regroup ? b->d_rg : nullptr, b->launch_idx, b->n);
             CU(cudaGetLastError());
             b->launches += 2;
@@ -959,7 +999,18 @@ extern "C" int ge_step_ring(ge_batch** batches, int n_batches, int n_rounds) {
             b->since_compact++;
             if (compact_after) due[n_due++] = b;
         }
-        fn<<<(unsigned)(g < 1 ? 1 : g), 128, 0, b0->stream>>>(b0->tab->dev, c, ra);
+        if (b0->pdl) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3((unsigned)(g < 1 ? 1 : g)); cfg.blockDim = dim3(128); cfg.stream = b0->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&cfg, fn, b0->tab->dev, c, ra));
+        } else {
+            fn<<<(unsigned)(g < 1 ? 1 : g), 128, 0, b0->stream>>>(b0->tab->dev, c, ra);
+        }
         b0->launches++;                               // ONE launch for the whole ring
         if (n_due) {
             const int rc = enqueue_compaction(due, n_due, b0->stream);
@@ -1137,12 +1188,13 @@ static int ensure_stage(ge_batch* b, size_t bytes) {
 // slot order (compaction's origin map, the active prefix) is untouched; through the staging buffer, stream-ordered.
 static int ensure_store(ge_batch* b, bool packed, cudaStream_t st) {
     if (b->packed == packed) return GE_OK;
-    const size_t S_dst = packed ? 32 : b->tab->rec_dev;
+    const size_t S_dst = packed ? packed_record(b->tab) : b->tab->rec_dev;
     const size_t bytes = (size_t)b->n_tiles * 32 * S_dst;
     if (st != b->stream) CU(cudaStreamSynchronize(b->stream));      // the staging buffer belongs to the batch's own stream
     int rc = ensure_stage(b, bytes);
     if (rc) return rc;
-    k_repack<8><<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_tiles, b->d_stage, b->n_tiles * 32, packed ? 1 : 0);
+    if (b->tab->bucket == 8) k_repack<8><<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_tiles, b->d_stage, b->n_tiles * 32, packed ? 1 : 0);
+    else k_repack<16><<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_tiles, b->d_stage, b->n_tiles * 32, packed ? 1 : 0);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(b->d_tiles, b->d_stage, bytes, cudaMemcpyDeviceToDevice, st));
     if (st != b->stream) CU(cudaStreamSynchronize(st));
@@ -1161,9 +1213,12 @@ static int export_async(ge_batch* b, uint64_t first, uint64_t count, void* host_
     if (dense || b->packed) {
         const uint32_t* org = b->compacted ? b->d_origin : nullptr;
         const int g = glue_grid(b, org ? b->n : count, 256);
-        if (b->packed && dense) k_export_w<8, true, true><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
-        else if (b->packed) k_export_w<8, false, true><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
-        else if (b->tab->bucket == 8) k_export_w<8, true, false><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        const bool p8 = b->tab->bucket == 8;
+        if (b->packed && dense && p8) k_export_w<8, true, true><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        else if (b->packed && dense) k_export_w<16, true, true><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        else if (b->packed && p8) k_export_w<8, false, true><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        else if (b->packed) k_export_w<16, false, true><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
+        else if (p8) k_export_w<8, true, false><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
         else k_export_w<16, true, false><<<g, 256, 0, b->stream>>>(b->d_tiles, org, b->n, first, count, b->d_stage);
     } else if (b->compacted)
         k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, b->d_origin, b->n, first, count, b->d_stage);
@@ -1184,9 +1239,12 @@ static int restore_order(ge_batch* b, bool keep_records) {
         int rc = ensure_stage(b, b->n * S);
         if (rc) return rc;
         const InitRec rec = init_rec_canon(b);
-        if (b->packed) {
+        if (b->packed && b->tab->bucket == 8) {
             k_export_w<8, false, true><<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, b->d_origin, b->n, 0, b->n, b->d_stage);
             k_import_w<8, false, true><<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, 0, b->n, b->d_stage, nullptr, ImportReset{nullptr, nullptr, 0, 0});
+        } else if (b->packed) {
+            k_export_w<16, false, true><<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, b->d_origin, b->n, 0, b->n, b->d_stage);
+            k_import_w<16, false, true><<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, 0, b->n, b->d_stage, nullptr, ImportReset{nullptr, nullptr, 0, 0});
         } else {
         k_export_perm<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, b->d_origin, b->n, 0, b->n, b->d_stage);
         k_import<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, 0, b->n, b->d_stage, nullptr, ImportReset{nullptr, nullptr, 0, 0});
@@ -1230,8 +1288,11 @@ static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void*
     const InitRec rec = init_rec_canon(b);
     CU(cudaMemcpyAsync(b->d_stage, host_buf, count * S, cudaMemcpyHostToDevice, b->stream));
     const int g = glue_grid(b, count, 256);
-    if (b->packed && dense) k_import_w<8, true, true><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
-    else if (b->packed) k_import_w<8, false, true><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    const bool p8 = b->tab->bucket == 8;
+    if (b->packed && dense && p8) k_import_w<8, true, true><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else if (b->packed && dense) k_import_w<16, true, true><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else if (b->packed && p8) k_import_w<8, false, true><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
+    else if (b->packed) k_import_w<16, false, true><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
     else if (dense && b->tab->bucket == 8) k_import_w<8, true, false><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
     else if (dense) k_import_w<16, true, false><<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, first, count, b->d_stage, b->d_err, R);
     else k_import<<<g, 256, 0, b->stream>>>(b->tab->dev, rec, b->d_tiles, (uint32_t)b->rec_store, (uint32_t)S, first, count, b->d_stage, b->d_err, R);
@@ -1309,7 +1370,7 @@ extern "C" int ge_stats_refresh(ge_batch* b, void* cuda_stream) {
     if (rc != GE_OK) return rc;
     // snapshot = accumulator + histograms of the sessions currently resident
     CU(cudaMemcpyAsync(b->d_stats_out, b->d_stats, GE_STATS_LEN * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-    k_stats<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->d_stats_out, b->packed ? 1u : 0u);
+    k_stats<<<glue_grid(b, b->n, 256), 256, 0, st>>>(b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->d_stats_out, alive_mask_of(b));
     CU(cudaGetLastError());
     b->launches++;
     return fence_out(b, st);

@@ -218,6 +218,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     } while (!ok);
 }
 
+// programmatic dependent launch (sm_90+): see counters_init in ge_step_tps.cuh
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // L1 prefetch of the 128-byte line that holds p (one warp instruction covers a 512-byte column of a tile)
 __device__ __forceinline__ void prefetch_l1(const uint8_t* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 ld128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }

@@ -116,7 +116,7 @@ __global__ void k_import(const __grid_constant__ DevTable T, const __grid_consta
 //   P8 = 16: 0-1 header | 2 alive,can_vote (u16 each) | 3 eligible,submitted | 4 revealed,investigated | 5 wolf,secret
 //            | 6 role_lo,role_hi | 7 zero | 8-11 selected_target_id[0..15]
 // The conversion happens in the import / export kernels.  The session store in HBM keeps the canonical columns, or —
-// tables up to 8 players, GE_OPT_STORE_PACKED — exactly these 32 bytes in two 16-byte columns (the packed store).
+// GE_OPT_STORE_PACKED — exactly these 32 / 48 bytes in two / three 16-byte columns (the packed store).
 template <int P8> struct DenseW { static constexpr int WORDS = P8 == 8 ? 8 : 12; static constexpr int CW = 12 + P8 / 4; };
 
 template <int P8>
@@ -181,11 +181,16 @@ template <int P8, bool PK = false>
 __device__ __forceinline__ void tile_load_words(const uint8_t* tiles, uint64_t slot, uint32_t (&w)[12 + P8 / 4]) {
     const uint32_t sl = (uint32_t)(slot & 31);
     if constexpr (PK) {
-        static_assert(P8 == 8, "packed store: up to 8 players");
-        const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * 32);
-        const uint4 a = *reinterpret_cast<const uint4*>(base + sl * 16), b = *reinterpret_cast<const uint4*>(base + 512 + sl * 16);
-        const uint32_t d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        dense_unpack<8>(d, w);
+        static_assert(P8 == 8 || P8 == 16, "packed store: up to 16 players");
+        constexpr int DW = DenseW<P8>::WORDS;
+        const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * 4 * DW);
+        uint32_t d[DW];
+#pragma unroll
+        for (int c = 0; c < DW / 4; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + c * 512 + sl * 16);
+            d[4 * c] = v.x; d[4 * c + 1] = v.y; d[4 * c + 2] = v.z; d[4 * c + 3] = v.w;
+        }
+        dense_unpack<P8>(d, w);
     } else {
         constexpr int S = 48 + P8;
         const uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S);
@@ -204,11 +209,13 @@ template <int P8, bool PK = false>
 __device__ __forceinline__ void tile_store_words(uint8_t* tiles, uint64_t slot, const uint32_t (&w)[12 + P8 / 4]) {
     const uint32_t sl = (uint32_t)(slot & 31);
     if constexpr (PK) {
-        uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * 32);
-        uint32_t d[8];
-        dense_pack<8>(w, d);
-        *reinterpret_cast<uint4*>(base + sl * 16) = make_uint4(d[0], d[1], d[2], d[3]);
-        *reinterpret_cast<uint4*>(base + 512 + sl * 16) = make_uint4(d[4], d[5], d[6], d[7]);
+        constexpr int DW = DenseW<P8>::WORDS;
+        uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * 4 * DW);
+        uint32_t d[DW];
+        dense_pack<P8>(w, d);
+#pragma unroll
+        for (int c = 0; c < DW / 4; ++c)
+            *reinterpret_cast<uint4*>(base + c * 512 + sl * 16) = make_uint4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
     } else {
         constexpr int S = 48 + P8;
         uint8_t* base = tiles + (slot >> 5) * (uint64_t)(32 * S);
@@ -303,8 +310,8 @@ k_repack(const uint8_t* src, uint8_t* dst, uint64_t slots, int to_packed) {
 }
 
 // final-state histograms (SPEC.md section 6): winner, length, survivors / scores.  sh = 515 shared counters.
-// pk: the packed store keeps is_alive in the low byte of word 2
-__device__ __forceinline__ void stats_one(const DevTable& T, const uint8_t* tiles, uint32_t S_dev, uint64_t i, uint32_t* sh, uint32_t pk) {
+// alive_mask: where is_alive sits in word 2 (canonical: the whole word; packed store: its low byte / half)
+__device__ __forceinline__ void stats_one(const DevTable& T, const uint8_t* tiles, uint32_t S_dev, uint64_t i, uint32_t* sh, uint32_t alive_mask) {
     const uint32_t n16 = S_dev / 16;
     const int P = T.h.n_players;
     const uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
@@ -315,7 +322,7 @@ __device__ __forceinline__ void stats_one(const DevTable& T, const uint8_t* tile
     if (T.h.family == FAM_WEREWOLF) {
         const uint32_t w = c0.y & 0xFF;
         atomicAdd(&sh[w <= 2 ? w : 0], 1u);
-        if (terminal) atomicAdd(&sh[3 + 256 + __popc(pk ? c0.z & 0xFFu : c0.z)], 1u);
+        if (terminal) atomicAdd(&sh[3 + 256 + __popc(c0.z & alive_mask)], 1u);
     } else {
         atomicAdd(&sh[terminal ? 1 : 0], 1u);
         if (terminal)
@@ -336,12 +343,12 @@ __device__ __forceinline__ void stats_flush(const uint32_t* sh, unsigned long lo
 }
 
 __global__ void __launch_bounds__(256)
-k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev, uint64_t n, unsigned long long* stats, uint32_t pk) {
+k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev, uint64_t n, unsigned long long* stats, uint32_t alive_mask) {
     __shared__ uint32_t sh[3 + 256 + 256];
     for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        stats_one(T, tiles, S_dev, i, sh, pk);
+        stats_one(T, tiles, S_dev, i, sh, alive_mask);
     __syncthreads();
     stats_flush(sh, stats);
 }
@@ -354,7 +361,7 @@ k_stats(const __grid_constant__ DevTable T, const uint8_t* tiles, uint32_t S_dev
 // Both are no-ops (one uniform load) while games are still running.
 __global__ void __launch_bounds__(256)
 k_autoreset_apply(const __grid_constant__ DevTable T, uint8_t* tiles, uint32_t S_dev, uint64_t n, uint64_t n_tiles,
-                  const __grid_constant__ InitRec rec, uint32_t* origin, unsigned long long* stats, const unsigned long long* cstate, uint32_t pk) {
+                  const __grid_constant__ InitRec rec, uint32_t* origin, unsigned long long* stats, const unsigned long long* cstate, uint32_t alive_mask) {
     __shared__ uint32_t sh[3 + 256 + 256];
     if (cstate[0] != 0) return;
     for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
@@ -362,7 +369,7 @@ k_autoreset_apply(const __grid_constant__ DevTable T, uint8_t* tiles, uint32_t S
     const uint32_t n16 = S_dev / 16;
     const uint64_t total = n_tiles * 32;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (i < n) stats_one(T, tiles, S_dev, i, sh, pk);        // read the finished game first ...
+        if (i < n) stats_one(T, tiles, S_dev, i, sh, alive_mask);        // read the finished game first ...
         uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
         const uint32_t sl = (uint32_t)(i & 31);
         for (uint32_t k = 0; k < S_dev / 8; ++k)                   // ... then overwrite the same slot

@@ -21,7 +21,7 @@ void GE_CAT3(ge_kernel_set_, GE_TU_FAM, GE_TU_BUCKET)(KernelSet* out) {
     k.tiled = (step_fn)k_step_w_tps_tiled<B>;
     k.human = (step_fn)k_step_w_tps_h<B>;
     k.ring = (ring_fn)k_ring_w_tps<B>;
-#if GE_TU_BUCKET == 8
+#if GE_TU_BUCKET == 8 || GE_TU_BUCKET == 16
     k.tps_pk = (step_fn)k_step_w_tps<B, void, true>;
     k.ring_pk = (ring_fn)k_ring_w_tps<B, void, true>;
 #endif

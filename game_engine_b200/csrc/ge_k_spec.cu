@@ -18,7 +18,7 @@ template <int BUCKET, class S> struct SpecKernelsOf<FAM_WEREWOLF, BUCKET, S> {
         e->tps = (step_fn)k_step_w_tps<BUCKET, S>;
         e->tiled = (step_fn)k_step_w_tps_tiled<BUCKET, S>;
         e->ring = (ring_fn)k_ring_w_tps<BUCKET, S>;
-        if constexpr (BUCKET == 8) {
+        if constexpr (BUCKET == 8 || BUCKET == 16) {
             e->tps_pk = (step_fn)k_step_w_tps<BUCKET, S, true>;
             e->ring_pk = (ring_fn)k_ring_w_tps<BUCKET, S, true>;
         }

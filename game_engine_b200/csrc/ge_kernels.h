@@ -21,7 +21,7 @@ struct KernelSet {
     step_fn tiled;      // tps with per-tile column needs (werewolf; batches with phase regrouping)
     step_fn human;      // tps with the human-seat path (SPEC D3h)
     ring_fn ring;       // one launch for a ring of batches
-    step_fn tps_pk;     // tps over the PACKED session store (werewolf, up to 8 players)
+    step_fn tps_pk;     // tps over the PACKED session store (werewolf, up to 16 players)
     ring_fn ring_pk;
 };
 // build-time specialised twins for one shipped table, matched at run time by a byte-identical blob

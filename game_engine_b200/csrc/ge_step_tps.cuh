@@ -13,7 +13,8 @@
 
 namespace ge {
 
-enum { DIRTY_C0 = 1, DIRTY_C1 = 2, DIRTY_C2 = 4, DIRTY_PL = 8 };
+enum { DIRTY_C0 = 1, DIRTY_C1 = 2, DIRTY_C2 = 4, DIRTY_PL = 8,
+       DIRTY_RV = 16 };     // role_revealed / investigated changed (they sit in their own column of the 16-player packed store)
 
 // =============================================================================== werewolf family
 template <int P8>
@@ -23,22 +24,38 @@ struct WState {
     uint32_t eligible, submitted, revealed, investigated;   // column 1
     uint32_t wolf, secret, role_lo, role_hi;           // column 2
     uint32_t tw[P8 / 4];                               // selected_target_id bytes
-    // Packed store (up to 8 players): the ten masks as they sit in HBM — pk0 = alive | can_vote << 8 | eligible << 16 |
-    // submitted << 24, pk1 = revealed | investigated << 8 | wolf << 16 | secret << 24, pk2 = role_lo | role_hi << 8.  A step
-    // unpacks them INSIDE its per-phase body and packs them again at its end, so that with a build-time table every phase
-    // extracts only the fields it reads and re-inserts only the ones it writes (pack(unpack(x)) folds to x).
-    uint32_t pk0, pk1, pk2;
+    // Packed store: the ten masks as they sit in HBM (the words of the dense wire record, SPEC 5b).
+    //   up to 8 players : pk0 = alive | can_vote << 8 | eligible << 16 | submitted << 24,
+    //                     pk1 = revealed | investigated << 8 | wolf << 16 | secret << 24, pk2 = role_lo | role_hi << 8
+    //   up to 16 players: pk0 = alive | can_vote << 16, pk1 = eligible | submitted << 16, pk2 = revealed | investigated << 16,
+    //                     pk3 = wolf | secret << 16, pk4 = role_lo | role_hi << 16
+    // A step unpacks them INSIDE its per-phase body and packs them again at its end, so that with a build-time table every
+    // phase extracts only the fields it reads and re-inserts only the ones it writes (pack(unpack(x)) folds to x).
+    uint32_t pk0, pk1, pk2, pk3, pk4;
     __device__ __forceinline__ void unpack() {
-        alive = pk0 & 0xFFu; can_vote = (pk0 >> 8) & 0xFFu; eligible = (pk0 >> 16) & 0xFFu; submitted = pk0 >> 24;
-        revealed = pk1 & 0xFFu; investigated = (pk1 >> 8) & 0xFFu; wolf = (pk1 >> 16) & 0xFFu; secret = pk1 >> 24;
-        role_lo = pk2 & 0xFFu; role_hi = (pk2 >> 8) & 0xFFu;
+        if constexpr (P8 == 8) {
+            alive = pk0 & 0xFFu; can_vote = (pk0 >> 8) & 0xFFu; eligible = (pk0 >> 16) & 0xFFu; submitted = pk0 >> 24;
+            revealed = pk1 & 0xFFu; investigated = (pk1 >> 8) & 0xFFu; wolf = (pk1 >> 16) & 0xFFu; secret = pk1 >> 24;
+            role_lo = pk2 & 0xFFu; role_hi = (pk2 >> 8) & 0xFFu;
+        } else {
+            alive = pk0 & 0xFFFFu; can_vote = pk0 >> 16; eligible = pk1 & 0xFFFFu; submitted = pk1 >> 16;
+            revealed = pk2 & 0xFFFFu; investigated = pk2 >> 16; wolf = pk3 & 0xFFFFu; secret = pk3 >> 16;
+            role_lo = pk4 & 0xFFFFu; role_hi = pk4 >> 16;
+        }
     }
     __device__ __forceinline__ void repack() {
-        pk0 = (alive & 0xFFu) | ((can_vote & 0xFFu) << 8) | ((eligible & 0xFFu) << 16) | (submitted << 24);
-        pk1 = (revealed & 0xFFu) | ((investigated & 0xFFu) << 8) | ((wolf & 0xFFu) << 16) | (secret << 24);
-        pk2 = (role_lo & 0xFFu) | ((role_hi & 0xFFu) << 8);
+        if constexpr (P8 == 8) {
+            pk0 = (alive & 0xFFu) | ((can_vote & 0xFFu) << 8) | ((eligible & 0xFFu) << 16) | (submitted << 24);
+            pk1 = (revealed & 0xFFu) | ((investigated & 0xFFu) << 8) | ((wolf & 0xFFu) << 16) | (secret << 24);
+            pk2 = (role_lo & 0xFFu) | ((role_hi & 0xFFu) << 8);
+        } else {
+            pk0 = (alive & 0xFFFFu) | (can_vote << 16); pk1 = (eligible & 0xFFFFu) | (submitted << 16);
+            pk2 = (revealed & 0xFFFFu) | (investigated << 16); pk3 = (wolf & 0xFFFFu) | (secret << 16);
+            pk4 = (role_lo & 0xFFFFu) | (role_hi << 16);
+        }
     }
 };
+
 
 constexpr int TPS_THREADS = 128;
 // resident CTAs per SM the werewolf kernels are compiled for (register budget = 65536 / (128 x this)); the 24/32-player
@@ -453,7 +470,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
             protect = first_choice;
             break;
         case EX_INVESTIGATE_RESOLVE:
-            s.submitted |= actors; s.investigated |= chosen; dirty |= DIRTY_C1;
+            s.submitted |= actors; s.investigated |= chosen; dirty |= DIRTY_C1 | DIRTY_RV;
             if (kill != 0 && kill != protect) w_die(s, (int)kill);
             kill = 0; protect = 0;
             break;
@@ -464,7 +481,7 @@ __device__ __forceinline__ int w_step_body(const V v, const int X, WState<P8>& s
                 revote = ((revote & 0x7Fu) + 1u) | 0x80u;
             } else {
                 revote &= 0x7Fu;
-                if (x) { w_die(s, (int)x); s.revealed |= 1u << (x - 1); dirty |= DIRTY_C1; }
+                if (x) { w_die(s, (int)x); s.revealed |= 1u << (x - 1); dirty |= DIRTY_C1 | DIRTY_RV; }
             }
         } break;
         default: break;
@@ -591,11 +608,12 @@ __device__ __forceinline__ int w_step_spec_chain(WState<P8>& s, const FieldTable
 
 // A step of a session whose phase needs nothing but column 0 (UI / timer phases with no effects; the host
 // proves this per phase in DevTable::need).  c = {h0, h1, is_alive, can_vote}.  Same SPEC as w_step.
-// PK: the packed store (below): c.z = is_alive | can_vote << 8 | ... as bytes instead of two 32-bit masks.
-template <bool PK = false>
+// PK: the packed store (below): c.z = is_alive | can_vote << 8 (or << 16) | ... instead of two 32-bit masks.
+template <int P8 = 32, bool PK = false>
 __device__ __forceinline__ int w_step_light(const DevTable& T, uint4& c) {
     const int X = c.x & 0xFF;
-    const uint32_t f_alive = PK ? (c.z & 0xFFu) : c.z, f_vote = PK ? ((c.z >> 8) & 0xFFu) : c.w;
+    const uint32_t f_alive = !PK ? c.z : P8 == 8 ? (c.z & 0xFFu) : (c.z & 0xFFFFu);
+    const uint32_t f_vote = !PK ? c.w : P8 == 8 ? ((c.z >> 8) & 0xFFu) : (c.z >> 16);
     const uint32_t step0 = c.x >> 16;
     const ge_phase_t& ph = T.phase[X];
     if (ph.kind == KIND_TERMINAL) return -1;
@@ -665,6 +683,10 @@ struct BlockCounters {
 template <class SlotFn>
 __device__ __forceinline__ void counters_init(BlockCounters* c, int n, SlotFn slot) {
     for (int i = threadIdx.x; i < n * (int)(sizeof(BlockCounters) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(c)[i] = 0;
+    // Programmatic dependent launch (GE_OPT_PDL): a step launch that was allowed to start before the previous kernel of
+    // its stream has drained waits HERE — after its block prologue, before it reads anything a predecessor wrote (launch
+    // inputs, records).  A no-op for ordinary launches.
+    grid_dependency_wait();
     __syncthreads();
     if ((int)threadIdx.x < n) {
         const SlotArgs& A = slot((int)threadIdx.x);
@@ -695,15 +717,16 @@ struct LightBulk {
 // the all-bot kernels are exactly what they were.
 // TILED: per-tile column needs (batches with phase regrouping); its own instantiations (k_step_w_tps_tiled), so the
 // lockstep kernels do not carry the extra words and branches (measured: -2.3 % on the headline when they did).
-// PK: the PACKED session store (werewolf tables up to 8 players; ge_capi.cu GE_OPT_STORE_PACKED): a record is the 32
-// bytes of the dense wire format (SPEC 5b) in two 16-byte columns — D0 = header + the eight masks is_alive ... has_secret_role
-// as bytes, D1 = role_lo, role_hi bytes + the eight target bytes — instead of 3.5 columns whose mask words are 3/4 zeros.
-// D0 moves on every step; D1 only when DevTable::need says so (bit 4).
+// PK: the PACKED session store (werewolf tables up to 16 players; ge_capi.cu GE_OPT_STORE_PACKED): a record is the dense
+// wire record (SPEC 5b) in 16-byte columns.  Up to 8 players, 32 bytes: D0 = header + the eight masks is_alive ...
+// has_secret_role as bytes, D1 = role_lo, role_hi bytes + the eight target bytes — instead of 3.5 columns whose mask words are
+// 3/4 zeros.  Up to 16 players, 48 bytes: D0 = header + is_alive, can_vote, eligible, submitted as u16, D1 = the other six
+// masks, D2 = the target bytes — instead of 4 columns.  D0 moves on every step; the others only when DevTable::need says so.
 template <int P8, class Spec, bool HUM = false, bool TILED = false, bool PK = false>
 __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C, const SlotArgs& A, BlockCounters& bc,
                                             uint32_t (*s_fields)[TPS_THREADS], uint8_t* s_lut_col, LightBulk* lb = nullptr) {
-    static_assert(!PK || P8 == 8, "the packed store covers tables up to 8 players");
-    constexpr int S = PK ? 32 : 48 + P8;
+    static_assert(!PK || P8 == 8 || P8 == 16, "the packed store covers tables up to 16 players");
+    constexpr int S = PK ? (P8 == 8 ? 32 : 48) : 48 + P8;
     constexpr int NT16 = P8 / 16;          // full 16-byte target columns
     constexpr bool THALF = (P8 % 16) != 0; // trailing 8-byte column
     uint32_t (&s_visits)[32] = bc.visits;
@@ -797,7 +820,7 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
                             if (tag0) c[j].y = (c[j].y & ~0xFFu) | tag0;
                             np = (int)y0;
                         } else if (in_range) {
-                            np = w_step_light<PK>(T, c[j]);
+                            np = w_step_light<P8, PK>(T, c[j]);
                         }
                         if (np >= 0) st128(base + j * tile_stride, c[j]);
                         mixed += visits.add(s_visits, np, lane) > 1;
@@ -839,16 +862,27 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             uint8_t* base8 = nullptr;
             // all loads are issued up front (no dependent second round trip)
             if constexpr (PK) {
+                // up to 8 players: D0 = header + 8 mask bytes, D1 = role bytes + target bytes (need bit 4);
+                // up to 16: D0 = header + alive, can_vote, eligible, submitted, D1 = the other six masks (need bit 4),
+                // D2 = the target bytes (need bit 2; night actions store theirs directly, PlSink)
                 const uint4 d0 = ld128(base);
-                uint4 d1 = make_uint4(0, 0, 0, 0);
+                uint4 d1 = make_uint4(0, 0, 0, 0), d2 = make_uint4(0, 0, 0, 0);
                 if (need & 16) d1 = ld128(base + 512);
+                if (P8 == 16 && (need & 4)) d2 = ld128(base + 1024);
                 if (tile + nwarps < n_tiles_act) {                       // next tile -> L1 (see below)
                     prefetch_l1(base + tile_stride);
                     if (need_next & 16) prefetch_l1(base + tile_stride + 512);
+                    if (P8 == 16 && (need_next & 4)) prefetch_l1(base + tile_stride + 1024);
                 }
                 s.h0 = d0.x; s.h1 = d0.y;
-                s.pk0 = d0.z; s.pk1 = d0.w; s.pk2 = d1.x;             // unpacked inside the step (WState::unpack)
-                s.tw[0] = d1.y; s.tw[1] = d1.z;
+                s.pk0 = d0.z;                                            // unpacked inside the step (WState::unpack)
+                if constexpr (P8 == 8) {
+                    s.pk1 = d0.w; s.pk2 = d1.x; s.pk3 = 0; s.pk4 = 0;
+                    s.tw[0] = d1.y; s.tw[1] = d1.z;
+                } else {
+                    s.pk1 = d0.w; s.pk2 = d1.x; s.pk3 = d1.y; s.pk4 = d1.z;
+                    s.tw[0] = d2.x; s.tw[1] = d2.y; s.tw[2] = d2.z; s.tw[3] = d2.w;
+                }
             } else {
             const uint4 c0 = ld128(base);
             uint4 c1 = make_uint4(0, 0, 0, 0), c2 = make_uint4(0, 0, 0, 0);
@@ -885,7 +919,7 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             s.wolf = c2.x; s.secret = c2.y; s.role_lo = c2.z; s.role_hi = c2.w;
             }
             // (packed store: the target bytes always travel through registers — D1 is loaded whenever a phase records them)
-            const PlSink K{base + 3 * 512, base8, !PK && (need & 4u) == 0};
+            const PlSink K{base + (PK ? 2 : 3) * 512, base8, !(PK && P8 == 8) && (need & 4u) == 0};
             bool live = in_range;
             const uint64_t sid = sid0 + org;
             uint32_t dirty = 0;
@@ -932,7 +966,12 @@ __device__ __forceinline__ void w_tps_tiles(const DevTable& T, const StepArgs& C
             live_cnt += __popc(lm);
             if constexpr (PK) {
                 if (dirty & (DIRTY_C0 | DIRTY_C1 | DIRTY_C2)) st128(base, make_uint4(s.h0, s.h1, s.pk0, s.pk1));
-                if (dirty & (DIRTY_C2 | DIRTY_PL)) st128(base + 512, make_uint4(s.pk2, s.tw[0], s.tw[1], 0u));
+                if constexpr (P8 == 8) {
+                    if (dirty & (DIRTY_C2 | DIRTY_PL)) st128(base + 512, make_uint4(s.pk2, s.tw[0], s.tw[1], 0u));
+                } else {
+                    if (dirty & (DIRTY_C2 | DIRTY_RV)) st128(base + 512, make_uint4(s.pk2, s.pk3, s.pk4, 0u));
+                    if (dirty & DIRTY_PL) st128(base + 1024, make_uint4(s.tw[0], s.tw[1], s.tw[2], s.tw[3]));
+                }
             } else {
             if (dirty & DIRTY_C0) st128(base, make_uint4(s.h0, s.h1, s.alive, s.can_vote));
             if (dirty & DIRTY_C1) st128(base + 512, make_uint4(s.eligible, s.submitted, s.revealed, s.investigated));
@@ -975,6 +1014,7 @@ k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
     w_tps_tiles<P8, Spec, false, false, PK>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0], lb);
+    grid_launch_dependents();      // this CTA's tiles are done: the stream's next launch may start filling the machine
     __syncthreads();
     w_tps_publish(A, sm.c[0]);
 }
@@ -987,6 +1027,7 @@ k_step_w_tps_tiled(const __grid_constant__ DevTable T, const __grid_constant__ S
     counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
     w_tps_tiles<P8, Spec, false, true>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
+    grid_launch_dependents();      // this CTA's tiles are done: the stream's next launch may start filling the machine
     __syncthreads();
     w_tps_publish(A, sm.c[0]);
 }
@@ -999,6 +1040,7 @@ k_step_w_tps_h(const __grid_constant__ DevTable T, const __grid_constant__ StepA
     counters_init(sm.c, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
     w_tps_tiles<P8, void, true>(T, A, A, sm.c[0], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
+    grid_launch_dependents();      // this CTA's tiles are done: the stream's next launch may start filling the machine
     __syncthreads();
     w_tps_publish(A, sm.c[0]);
 }
@@ -1021,6 +1063,7 @@ k_ring_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
         w_tps_tiles<P8, Spec, false, false, PK>(T, C, R.slot[i], sm.c[i], sm.fields, &sm.lut[0][P8 > 16 ? threadIdx.x : 0]);
         i = i + 1 == R.n ? 0 : i + 1;
     }
+    grid_launch_dependents();
     __syncthreads();
     for (int k = 0; k < R.n; ++k) w_tps_publish(R.slot[k], sm.c[k]);
 }
@@ -1449,6 +1492,7 @@ k_step_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
     counters_init(bc, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
     t_tps_tiles<PB, Spec>(T, A, A, bc[0]);
+    grid_launch_dependents();
     __syncthreads();
     t_tps_publish(A, bc[0]);
 }
@@ -1460,6 +1504,7 @@ k_step_t_tps_h(const __grid_constant__ DevTable T, const __grid_constant__ StepA
     counters_init(bc, 1, [&](int) -> const SlotArgs& { return A; });
     __syncthreads();
     t_tps_tiles<PB, void, true>(T, A, A, bc[0]);
+    grid_launch_dependents();
     __syncthreads();
     t_tps_publish(A, bc[0]);
 }
@@ -1476,6 +1521,7 @@ k_ring_t_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArg
         t_tps_tiles<PB, Spec>(T, C, R.slot[i], bc[i]);
         i = i + 1 == R.n ? 0 : i + 1;
     }
+    grid_launch_dependents();
     __syncthreads();
     for (int k = 0; k < R.n; ++k) t_tps_publish(R.slot[k], bc[k]);
 }

@@ -161,6 +161,11 @@ int ge_batch_get_kernel(const ge_batch *b);
  * GE_ERR_UNSUPPORTED when switched on for other tables. */
 #define GE_OPT_LIGHT_BULK 1
 #define GE_OPT_STORE_PACKED 2
+/* GE_OPT_PDL: step launches (ge_step, ge_step_many, ge_step_ring) are programmatic dependent launches: a launch may start
+ * filling the machine while the previous kernel of its stream drains and waits on the device (griddepcontrol.wait) before it
+ * reads that kernel's results.  On by default (measured: DESIGN section 6: +0.5 % with 8 streams, +16 % on one); 0 = plain
+ * stream-ordered launches. */
+#define GE_OPT_PDL 3
 int ge_batch_set_option(ge_batch *b, int option, int value);
 
 /* Record format of the host-buffer calls of this batch (ge_export_state, ge_import_state, ge_run_host[_async]):

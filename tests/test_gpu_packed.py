@@ -1,5 +1,5 @@
-"""The PACKED session store (GE_OPT_STORE_PACKED: werewolf tables up to 8 players keep a record as the 32 bytes of the dense
-wire format in two 16-byte columns) against Oracle B, through the C ABI: every byte of every canonical record after every
+"""The PACKED session store (GE_OPT_STORE_PACKED: werewolf tables up to 8 / 16 players keep a record as the 32 / 48 bytes of the
+dense wire format in two / three 16-byte columns) against Oracle B, through the C ABI: every byte of every canonical record after every
 step, on every path that touches the store — step kernels (specialised and interpreter), fused launches, the ring
 launch, compaction, auto-reset, both wire formats of import / export / the host-buffer call, the device-side record
 validator — and the transparent conversions for callers the packed layout does not serve (lane-per-player kernels,
@@ -31,18 +31,19 @@ def _diff(got, rec, first, k):
 
 
 @pytest.mark.parametrize("kernel", ["tps", "tps_generic"])
-@pytest.mark.parametrize("game,P", [(WEREWOLF, 8), (WEREWOLF, 4), (WEREWOLF, 5), (WEREWOLF, 7), (DRAFT, 8), (DRAFT, 6), (REVOTE, 8)])
+@pytest.mark.parametrize("game,P", [(WEREWOLF, 8), (WEREWOLF, 4), (WEREWOLF, 5), (WEREWOLF, 7), (DRAFT, 8), (DRAFT, 6), (REVOTE, 8),
+                                    (WEREWOLF, 16), (WEREWOLF, 9), (WEREWOLF, 13), (DRAFT, 12), (REVOTE, 16)])
 def test_every_step_bit_exact(games, oracle_for, game, P, kernel):
     cg = games(game, P)
     o = oracle_for(cg)
     n, first, seed = 1000, 12345, 0xC0FFEE
     t, b = _batch(cg, n, first, seed, kernel)
-    # 32 bytes per session in HBM — except the re-vote table, whose phase regrouping keeps the canonical columns
-    assert b.state_device_bytes() == ((n + 31) // 32) * 32 * (32 if game != REVOTE else cg.record_size)
+    # 32 / 48 bytes per session in HBM — except the re-vote table, whose phase regrouping keeps the canonical columns
+    assert b.state_device_bytes() == ((n + 31) // 32) * 32 * ((32 if P <= 8 else 48) if game != REVOTE else cg.record_size)
     rec = o.init(n)
     np.testing.assert_array_equal(b.export_state(), rec)
     ost = o.new_stats()
-    for k in range(90):
+    for k in range(90 if P <= 8 else 150):
         b.step(1)
         o.step(rec, first, seed, 1, ost)
         got = b.export_state()
@@ -52,16 +53,17 @@ def test_every_step_bit_exact(games, oracle_for, game, P, kernel):
     assert b.counted_steps() == int(ost[0])
 
 
+@pytest.mark.parametrize("P", [8, 16])
 @pytest.mark.parametrize("kernel", ["tps", "tps_generic"])
-def test_run_to_completion_with_compaction(games, oracle_for, kernel):
-    cg = games(WEREWOLF, 8)
+def test_run_to_completion_with_compaction(games, oracle_for, kernel, P):
+    cg = games(WEREWOLF, P)
     o = oracle_for(cg)
     n, first, seed = 1 << 16, 1 << 33, 7
     t, b = _batch(cg, n, first, seed, kernel)
     b.set_compaction(3, 3)
     rec = o.init(n)
     ost = o.new_stats()
-    for chunk in (10, 17, 29, 200):                       # exports of a compacted (permuted) packed store in between
+    for chunk in (10, 17, 29, 50, 200):                   # exports of a compacted (permuted) packed store in between
         b.step(chunk)
         o.step(rec, first, seed, chunk, ost)
         np.testing.assert_array_equal(b.export_state(), rec)
@@ -73,26 +75,28 @@ def test_run_to_completion_with_compaction(games, oracle_for, kernel):
     assert gst[1:4].sum() == n
 
 
-def test_fused_equals_single_steps_and_the_canonical_store(games):
-    cg = games(WEREWOLF, 8)
+@pytest.mark.parametrize("P", [8, 16])
+def test_fused_equals_single_steps_and_the_canonical_store(games, P):
+    cg = games(WEREWOLF, P)
     n = 4096
     _, a = _batch(cg, n, 0, 3)
     _, b = _batch(cg, n, 0, 3)
     _, c = _batch(cg, n, 0, 3, packed=False)
-    assert c.state_device_bytes() == n * cg.record_size and a.state_device_bytes() == n * 32
-    a.step(37)
-    b.run_fused(37)
-    c.step(37)
+    assert c.state_device_bytes() == n * cg.record_size and a.state_device_bytes() == n * (32 if P == 8 else 48)
+    a.step(67)
+    b.run_fused(67)
+    c.step(67)
     np.testing.assert_array_equal(a.export_state(), c.export_state())
     np.testing.assert_array_equal(b.export_state(), c.export_state())
     np.testing.assert_array_equal(a.stats(), c.stats())
     np.testing.assert_array_equal(b.stats(), c.stats())
 
 
+@pytest.mark.parametrize("P", [8, 14])
 @pytest.mark.parametrize("wire_fmt", ["canonical", "dense"])
-def test_import_export_windows_and_host_buffer_call(games, oracle_for, wire_fmt):
+def test_import_export_windows_and_host_buffer_call(games, oracle_for, wire_fmt, P):
     from game_engine_b200 import wire
-    cg = games(WEREWOLF, 8)
+    cg = games(WEREWOLF, P)
     o = oracle_for(cg)
     n, seed = 5000, 99
     conv = (lambda r: wire.to_dense(cg, r)) if wire_fmt == "dense" else (lambda r: r)
@@ -129,10 +133,11 @@ def test_import_export_windows_and_host_buffer_call(games, oracle_for, wire_fmt)
     np.testing.assert_array_equal(st, ost)
 
 
-def test_ring_launch(games, oracle_for):
+@pytest.mark.parametrize("P", [8, 16])
+def test_ring_launch(games, oracle_for, P):
     import torch
     from game_engine_b200.batch import step_ring
-    cg = games(WEREWOLF, 8)
+    cg = games(WEREWOLF, P)
     o = oracle_for(cg)
     stream = torch.cuda.Stream(device=0)
     firsts = (0, 7000, 1 << 35)
@@ -154,14 +159,15 @@ def test_ring_launch(games, oracle_for):
         step_ring(ring, 1)
 
 
-def test_auto_reset(games, oracle_for):
-    cg = games(WEREWOLF, 8)
+@pytest.mark.parametrize("P", [8, 11])
+def test_auto_reset(games, oracle_for, P):
+    cg = games(WEREWOLF, P)
     o = oracle_for(cg)
     n, first, seed = 2048, 50, 5
     t, b = _batch(cg, n, first, seed)
     b.set_autoreset(1 << 20)
     total = 0
-    for _ in range(30):
+    for _ in range(30 if P == 8 else 60):
         b.step(8)
         total += 8
     epochs = b.epochs()
@@ -176,10 +182,11 @@ def test_auto_reset(games, oracle_for):
     np.testing.assert_array_equal(b.stats(), c.stats())
 
 
-def test_switching_to_callers_the_packed_store_does_not_serve(games, oracle_for):
+@pytest.mark.parametrize("P", [8, 16])
+def test_switching_to_callers_the_packed_store_does_not_serve(games, oracle_for, P):
     """lane-per-player kernels, audience masks and human seats read the canonical columns: the store converts back and
     forth mid-game without a byte changing."""
-    cg = games(WEREWOLF, 8)
+    cg = games(WEREWOLF, P)
     o = oracle_for(cg)
     n, first, seed = 3000, 77, 21
     t, b = _batch(cg, n, first, seed)
@@ -212,9 +219,8 @@ def test_switching_to_callers_the_packed_store_does_not_serve(games, oracle_for)
     # a person sits down in seat 1 of every session and never answers: the action phases wait
     b.set_human_seats(np.full(n, 1, dtype=np.uint32))
     b.step(3)
-    o.step_humans(rec, first, seed, np.full(n, 1, dtype=np.uint32), np.full((n, 8), 0xFF, dtype=np.uint8))
-    o.step_humans(rec, first, seed, np.full(n, 1, dtype=np.uint32), np.full((n, 8), 0xFF, dtype=np.uint8))
-    o.step_humans(rec, first, seed, np.full(n, 1, dtype=np.uint32), np.full((n, 8), 0xFF, dtype=np.uint8))
+    for _ in range(3):
+        o.step_humans(rec, first, seed, np.full(n, 1, dtype=np.uint32), np.full((n, P), 0xFF, dtype=np.uint8))
     np.testing.assert_array_equal(b.export_state(), rec)
     assert b.state_device_bytes() > packed_bytes
     b.set_human_seats(None)
@@ -224,7 +230,7 @@ def test_switching_to_callers_the_packed_store_does_not_serve(games, oracle_for)
 
 def test_other_tables_are_refused(games):
     from game_engine_b200.capi import GameEngineError
-    for game, P in ((WEREWOLF, 9), (WEREWOLF, 16), (TTL, 4)):
+    for game, P in ((WEREWOLF, 17), (WEREWOLF, 32), (TTL, 4)):
         from game_engine_b200.batch import SessionBatch, Table
         b = SessionBatch(Table(games(game, P)), 100, first_session_id=0, seed=1)
         with pytest.raises(GameEngineError):
@@ -233,13 +239,13 @@ def test_other_tables_are_refused(games):
         b.step(3)
 
 
-def test_random_tables_up_to_eight_players(oracle_for):
+def test_random_tables_up_to_sixteen_players(oracle_for):
     from game_engine_b200.batch import SessionBatch, Table
     from oracle.oracle import Oracle
     ran = 0
     for seed in list(SEEDS) + [1000 + s for s in range(60)]:
         tab = random_table(seed, T.FAMILY_WEREWOLF)
-        if tab.n_players > 8:
+        if tab.n_players > 16:
             continue
         ran += 1
         cg = _Blob(tab)
@@ -260,14 +266,15 @@ def test_random_tables_up_to_eight_players(oracle_for):
         o.stats_final(rec, ost)
         np.testing.assert_array_equal(b.stats(), ost, err_msg="table seed %d" % seed)
         b.close()
-    assert ran >= 10
+    assert ran >= 20
 
 
+@pytest.mark.parametrize("P", [8, 12])
 @pytest.mark.parametrize("wire_fmt", ["canonical", "dense"])
-def test_device_validator_on_the_packed_store(games, oracle_for, wire_fmt):
+def test_device_validator_on_the_packed_store(games, oracle_for, wire_fmt, P):
     from game_engine_b200 import wire
     from game_engine_b200.capi import GameEngineError
-    cg = games(WEREWOLF, 8)
+    cg = games(WEREWOLF, P)
     o = oracle_for(cg)
     n, seed = 4000, 29
     good = _played(o, n, seed, 70)

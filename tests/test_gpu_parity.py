@@ -387,3 +387,39 @@ def test_ring_launch_equals_separate_launches(games, oracle_for, game, P, kernel
     other.set_stream(stream.cuda_stream)
     with pytest.raises(GameEngineError):
         step_ring([ring[0], other], 1)
+
+
+@pytest.mark.parametrize("game,P", [(WEREWOLF, 8), (WEREWOLF, 16), (REVOTE, 32), (TTL, 4)])
+def test_programmatic_dependent_launches_change_nothing(games, oracle_for, game, P):
+    """GE_OPT_PDL: back-to-back step launches of one stream may overlap the previous kernel's tail; they wait on the device
+    before reading its results.  Same records, same statistics — single-batch launches, compaction / regroup launches in
+    between, and the ring launch."""
+    import torch
+    from game_engine_b200.batch import SessionBatch, Table, step_ring
+    cg = games(game, P)
+    o = oracle_for(cg)
+    n, first, seed = 50000, 99, 4
+    t, b = _batch(cg, n, first, seed, "tps")
+    b.set_option("pdl", 1)
+    if game != TTL:
+        b.set_compaction(2, 4) if game != REVOTE else b.set_regroup(2, 4)
+    rec = o.init(n)
+    ost = o.new_stats()
+    for chunk in (1, 7, 30, 60):
+        b.step(chunk)
+        o.step(rec, first, seed, chunk, ost)
+        np.testing.assert_array_equal(b.export_state(), rec)
+    o.stats_final(rec, ost)
+    np.testing.assert_array_equal(b.stats(), ost)
+    if game == REVOTE:
+        return
+    stream = torch.cuda.Stream(device=0)
+    ring = [SessionBatch(t, 20000, first_session_id=f, seed=seed) for f in (0, 1 << 34)]
+    for r in ring:
+        r.set_stream(stream.cuda_stream)
+        r.set_option("pdl", 1)
+    step_ring(ring, 45)
+    for r, f in zip(ring, (0, 1 << 34)):
+        want = o.init(20000)
+        o.step(want, f, seed, 45)
+        np.testing.assert_array_equal(r.export_state(), want)

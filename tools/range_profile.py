@@ -58,7 +58,7 @@ def main():
     for i, b in enumerate(ring):
         b.set_stream(streams[i % NS].cuda_stream)
         b.set_grid(0 if merged else a.ctas_per_sm)
-        if cg.family == 1 and a.players <= 8:
+        if cg.family == 1 and a.players <= 16:
             b.set_option("store_packed", 1 if a.store == "packed" else 0)
     age, epoch = [0] * R, [0] * R
     for i, b in enumerate(ring):
