@@ -815,11 +815,24 @@ static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st) {
         b->since_compact = 0;
     }
     list[0]->launches += 2;                           // one launch pair for the whole list
-    k_compact_scan<<<dim3(max_scan, n), 1024, 0, st>>>(ca);
     uint64_t sg = (max_tiles * 16 + 127) / 128;
     const uint64_t cap = (uint64_t)list[0]->sm_count * 8 / (n > 4 ? 4 : n);       // the list shares the machine
     if (sg > cap) sg = cap;
-    k_compact_swap<<<dim3((unsigned)(sg < 1 ? 1 : sg), n), 128, 0, st>>>(ca);
+    if (list[0]->pdl) {                               // the check rides the same dependent-launch chain as the steps around it
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.gridDim = dim3((unsigned)max_scan, (unsigned)n); cfg.blockDim = dim3(1024);
+        CU(cudaLaunchKernelEx(&cfg, k_compact_scan, ca));
+        cfg.gridDim = dim3((unsigned)(sg < 1 ? 1 : sg), (unsigned)n); cfg.blockDim = dim3(128);
+        CU(cudaLaunchKernelEx(&cfg, k_compact_swap, ca));
+    } else {
+        k_compact_scan<<<dim3(max_scan, n), 1024, 0, st>>>(ca);
+        k_compact_swap<<<dim3((unsigned)(sg < 1 ? 1 : sg), n), 128, 0, st>>>(ca);
+    }
     CU(cudaGetLastError());
     return GE_OK;
 }
@@ -1344,9 +1357,7 @@ extern "C" int ge_eval_preds(ge_batch* b, const ge_pred_t* preds, int n_preds, u
     if (count == 0) return GE_OK;
     CU(cudaSetDevice(b->device));
     const size_t bytes = count * (size_t)n_preds * sizeof(uint32_t);
-    int rc = ensure_store(b, false, b->stream);       // the audience-mask kernel reads the canonical columns (the next step re-packs)
-    if (rc) return rc;
-    rc = ensure_stage(b, bytes);
+    int rc = ensure_stage(b, bytes);
     if (rc) return rc;
     PredList pl;
     memset(&pl, 0, sizeof pl);
@@ -1354,7 +1365,7 @@ extern "C" int ge_eval_preds(ge_batch* b, const ge_pred_t* preds, int n_preds, u
     pl.n = n_preds;
     k_eval_preds<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, pl, b->d_tiles, (uint32_t)b->rec_store,
                                                                b->compacted ? b->d_origin : nullptr, b->n, first, count,
-                                                               reinterpret_cast<uint32_t*>(b->d_stage));
+                                                               reinterpret_cast<uint32_t*>(b->d_stage), b->packed ? b->tab->bucket : 0);
     CU(cudaGetLastError());
     b->launches++;
     CU(cudaMemcpyAsync(host_masks, b->d_stage, bytes, cudaMemcpyDeviceToHost, b->stream));

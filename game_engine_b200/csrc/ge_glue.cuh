@@ -454,6 +454,9 @@ k_compact_scan(const __grid_constant__ CompactArgs CA) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_last;
+    // programmatic dependent launch (GE_OPT_PDL): wait for the counted step launch, then let the swap kernel start filling in
+    grid_dependency_wait();
+    grid_launch_dependents();
     const CompactSlot& Q = CA.s[blockIdx.y];
     const uint32_t* __restrict__ live_mask = Q.live_mask;
     uint32_t* loc = Q.loc;
@@ -504,6 +507,8 @@ k_compact_scan(const __grid_constant__ CompactArgs CA) {
 // back region [n_live, old prefix).  Both are located by binary search over the two-level prefix
 // P(t) = blk[t / 1024] + loc[t] (terminals before tile t = 32t - P(t)).  One thread per pair.
 __global__ void k_compact_swap(const __grid_constant__ CompactArgs CA) {
+    grid_dependency_wait();            // (GE_OPT_PDL) the scan's results; the batch's next step launch may start behind us
+    grid_launch_dependents();
     const CompactSlot& Q = CA.s[blockIdx.y];
     uint8_t* tiles = Q.tiles;
     const uint32_t S = CA.S;
@@ -704,9 +709,10 @@ __global__ void k_regroup_copyback(uint8_t* __restrict__ tiles, uint32_t S, uint
 // audience_ids, src/lib/canvas/types.ts:14-17).  Output row = session (original order), column = predicate.
 struct PredList { ge_pred_t p[32]; int n; };
 
+// packed_bucket: 0 = canonical columns, 8 / 16 = the packed store of that bucket (werewolf family)
 __global__ void k_eval_preds(const __grid_constant__ DevTable T, const __grid_constant__ PredList PL, const uint8_t* tiles,
                              uint32_t S_dev, const uint32_t* __restrict__ origin, uint64_t n, uint64_t first, uint64_t count,
-                             uint32_t* out) {
+                             uint32_t* out, int packed_bucket) {
     const uint32_t n16 = S_dev / 16;
     const int P = T.h.n_players;
     const uint32_t ALL = P >= 32 ? 0xFFFFFFFFu : ((1u << P) - 1u);
@@ -719,7 +725,26 @@ __global__ void k_eval_preds(const __grid_constant__ DevTable T, const __grid_co
 #pragma unroll
         for (int f = 0; f < 16; ++f) F[f] = 0;
         F[15] = ALL;
-        if (T.h.family == FAM_WEREWOLF) {
+        if (T.h.family == FAM_WEREWOLF && packed_bucket != 0) {
+            uint32_t w[16];
+            if (packed_bucket == 8) {
+                uint32_t w8[14];
+                tile_load_words<8, true>(tiles, slot, w8);
+#pragma unroll
+                for (int k = 0; k < 14; ++k) w[k] = w8[k];
+                w[14] = 0; w[15] = 0;
+            } else {
+                tile_load_words<16, true>(tiles, slot, w);
+            }
+#pragma unroll
+            for (int f = 0; f < 8; ++f) F[f] = w[2 + f];
+            const uint32_t lo = w[10], hi = w[11];
+            F[8] = F[7] ? ~(lo | hi) & ALL : 0u; F[9] = lo & ~hi; F[10] = ~lo & hi; F[11] = lo & hi;
+            F[12] = F[7] ? ALL : 0u;
+            for (int k = 0; k < T.h.n_cmp && k < 2; ++k)
+                for (int p = 0; p < P; ++p)
+                    if (cmp_holds(T.h.cmp[k].op, (w[12 + (p >> 2)] >> (8 * (p & 3))) & 0xFFu, T.h.cmp[k].constant)) F[13 + k] |= 1u << p;
+        } else if (T.h.family == FAM_WEREWOLF) {
             const uint4 c0 = *reinterpret_cast<const uint4*>(base + sl * 16);
             const uint4 c1 = *reinterpret_cast<const uint4*>(base + 512 + sl * 16);
             const uint4 c2 = *reinterpret_cast<const uint4*>(base + 1024 + sl * 16);

@@ -156,7 +156,7 @@ int ge_batch_get_kernel(const ge_batch *b);
  * the dense wire format (two 16-byte columns: header + eight mask bytes | role bytes + target bytes) instead of the
  * canonical 56 bytes in 3.5 columns whose mask words are three-quarters zeros; the all-bot thread-per-session kernels
  * run on it directly.  Records at the ABI are unchanged (canonical or dense wire, as ge_batch_set_wire says); callers
- * the packed layout does not serve (lane-per-player kernels, human seats, phase regrouping, ge_eval_preds) convert the
+ * the packed layout does not serve (lane-per-player kernels, human seats, phase regrouping) convert the
  * store back transparently.  ON by default for the tables it covers (value 0 = keep the canonical columns);
  * GE_ERR_UNSUPPORTED when switched on for other tables. */
 #define GE_OPT_LIGHT_BULK 1
