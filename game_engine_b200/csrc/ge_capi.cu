@@ -78,6 +78,7 @@ struct ge_batch {
     unsigned long long* d_hint;   // the same words as the device sees them
     unsigned long long epoch;     // bumped by every (re)initialisation; stale hints are ignored
     bool compacted;               // origin may differ from identity
+    bool origin_iota;             // !compacted, and d_origin already holds the identity (written by k_reinit): no k_iota needed
     // phase regrouping (see k_regroup_*): counting sort of the active prefix by phase, through a scratch store
     uint32_t* d_rg;               // RG_WORDS control words (histogram, trigger, bases, cursors)
     uint8_t* d_rg_tiles;          // scratch session store (same size as d_tiles)
@@ -487,6 +488,7 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
     k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch, 0);
     CU(cudaGetLastError());
     b->compacted = false;
+    b->origin_iota = false;
     b->since_compact = 0;
     b->tile_valid = false;
     return GE_OK;
@@ -498,10 +500,20 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
 extern "C" int ge_batch_reset(ge_batch* b, uint64_t first_session_id, uint64_t seed) {
     if (!b) return fail(GE_ERR_ARG, "batch is NULL");
     CU(cudaSetDevice(b->device));
-    k_stats<<<glue_grid(b, b->n, 256), 256, 0, b->stream>>>(b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->d_stats, alive_mask_of(b));
+    // harvest + initial records + identity slot order + bookkeeping in one launch (k_reinit)
+    b->first_sid = first_session_id;
+    b->seed = seed;
+    b->epoch++;
+    k_reinit<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, b->stream>>>(b->tab->dev, b->d_tiles, (uint32_t)b->rec_store, b->n, b->n_tiles, init_rec(b),
+                                                                         b->d_origin, b->d_stats, b->d_cstate, b->d_presence, b->epoch, alive_mask_of(b));
     CU(cudaGetLastError());
     b->launches++;
-    return init_sessions(b, first_session_id, seed);
+    b->next_override = 1u;        // every session is in phase index 0
+    b->compacted = false;
+    b->origin_iota = true;
+    b->since_compact = 0;
+    b->tile_valid = false;
+    return GE_OK;
 }
 
 extern "C" int ge_batch_clear_stats(ge_batch* b) {
@@ -805,9 +817,12 @@ static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st) {
     for (int i = 0; i < n; ++i) {
         ge_batch* b = list[i];
         if (!b->compacted) {
-            k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
+            if (!b->origin_iota) {
+                k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
+                b->launches++;
+            }
             b->compacted = true;
-            b->launches++;
+            b->origin_iota = false;
         }
         ca.s[i] = CompactSlot{b->d_tiles, b->d_origin, b->d_live_mask, b->d_prefix, b->d_blk, b->d_cstate, b->d_hint};
         if (b->scan_blocks > max_scan) max_scan = b->scan_blocks;
@@ -909,9 +924,12 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
     const bool regroup = b->regroup_every > 0 && b->kernel != GE_KERNEL_COOP && steps_per_launch == 1;
     for (int i = 0; i < n_launches; ++i) {
         if (regroup && !b->compacted) {              // the origin map must exist before the first regrouping
-            k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
+            if (!b->origin_iota) {
+                k_iota<<<glue_grid(b, b->n_tiles * 32, 256), 256, 0, st>>>(b->d_origin, b->n_tiles * 32);
+                b->launches++;
+            }
             b->compacted = true;
-            b->launches++;
+            b->origin_iota = false;
         }
         const bool regroup_after = regroup && b->since_compact + 1 >= b->regroup_every;
         const bool compact_after = !regroup && b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
@@ -1266,6 +1284,7 @@ static int restore_order(ge_batch* b, bool keep_records) {
         b->launches += 2;
     }
     b->compacted = false;
+    b->origin_iota = false;
     b->tile_valid = false;
     b->epoch++;
     k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch, 1);
@@ -1289,6 +1308,7 @@ static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void*
     b->tile_valid = false;
     if (whole) {
         b->compacted = false;
+        b->origin_iota = false;
         b->epoch++;
         b->since_compact = 0;
         R.cstate = b->d_cstate; R.epoch = b->epoch;

@@ -380,6 +380,33 @@ k_autoreset_apply(const __grid_constant__ DevTable T, uint8_t* tiles, uint32_t S
     stats_flush(sh, stats);
 }
 
+// ge_batch_reset in ONE launch: fold the resident sessions' final-state histograms into the accumulator (k_stats), rewrite
+// every slot with the initial record (k_init), put the slot order back to identity (k_iota) and reset the compaction state and
+// the phase-presence words (k_cstate_reset + a memset).  A batch of a steady-state ring starts over once per game cycle; as
+// five stream operations that was 3.4 % of the (serialised) GPU time of the headline workload.
+__global__ void __launch_bounds__(256)
+k_reinit(const __grid_constant__ DevTable T, uint8_t* tiles, uint32_t S_dev, uint64_t n, uint64_t n_tiles, const __grid_constant__ InitRec rec,
+         uint32_t* origin, unsigned long long* stats, unsigned long long* cstate, uint32_t* presence, unsigned long long epoch,
+         uint32_t alive_mask) {
+    __shared__ uint32_t sh[3 + 256 + 256];
+    for (int i = threadIdx.x; i < 515; i += blockDim.x) sh[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 16) cstate[threadIdx.x] = threadIdx.x == 0 ? n : threadIdx.x == 7 ? epoch : 0ull;
+    if (blockIdx.x == 0 && threadIdx.x < 3) presence[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n16 = S_dev / 16;
+    const uint64_t total = n_tiles * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (i < n) stats_one(T, tiles, S_dev, i, sh, alive_mask);  // read the finished game first ...
+        uint8_t* base = tiles + (i >> 5) * (uint64_t)(32 * S_dev);
+        const uint32_t sl = (uint32_t)(i & 31);
+        for (uint32_t k = 0; k < S_dev / 8; ++k)                   // ... then overwrite the same slot
+            *reinterpret_cast<uint2*>(base + rt_tile_off(8 * k, sl, n16)) = make_uint2(rec.w[2 * k], rec.w[2 * k + 1]);
+        origin[i] = (uint32_t)i;
+    }
+    __syncthreads();
+    stats_flush(sh, stats);
+}
+
 __global__ void k_autoreset_commit(unsigned long long* cstate, uint32_t* presence, uint32_t* rg, uint32_t next_launch_idx, unsigned long long n) {
     if (threadIdx.x != 0 || cstate[0] != 0) return;
     cstate[0] = n; cstate[5] = 0; cstate[8] += 1;
