@@ -581,6 +581,8 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)b->fn[k], 128, 0);
         if (e != cudaSuccess || per_sm < 1) per_sm = 4;
+        // (measured on the canonical-store kernel; its packed-store twin is launched with the same grids — the specialised
+        // 8-player one fits 10 CTAs per SM, which only matters when SMALL grids of several streams share the machine)
         b->occ[k] = per_sm;
         const uint64_t warps = k == GE_KERNEL_COOP ? b->n_tiles * (uint64_t)lanes_per_session(t) : b->n_tiles;
         uint64_t g = (warps + 3) / 4;

@@ -63,7 +63,21 @@ constexpr int TPS_THREADS = 128;
 #ifndef GE_P32_CTAS
 #define GE_P32_CTAS 5
 #endif
-#define GE_W_CTAS(P8) ((P8) <= 8 ? 8 : (P8) <= 16 ? 6 : GE_P32_CTAS)
+#ifndef GE_P8_CTAS
+#define GE_P8_CTAS 8
+#endif
+#ifndef GE_P16_CTAS
+#define GE_P16_CTAS 6
+#endif
+#define GE_W_CTAS(P8) ((P8) <= 8 ? GE_P8_CTAS : (P8) <= 16 ? GE_P16_CTAS : GE_P32_CTAS)
+// The specialised 8-player step kernel over the packed store needs 48 registers without a spill (the masks stay packed until a
+// phase body wants them), so it is compiled for 10 resident CTAs per SM: with the default 8 streams x 3 CTAs per SM more of the
+// ring's launches are co-resident (+2.9 %, tools/ab_occ.sh; 11 spills; the ring kernel and full-grid launches prefer 8).
+#ifndef GE_P8_PACKED_SPEC_CTAS
+#define GE_P8_PACKED_SPEC_CTAS 10
+#endif
+template <int P8, class Spec, bool PK>
+constexpr int w_step_ctas() { return (P8 == 8 && PK && !std::is_void<Spec>::value) ? GE_P8_PACKED_SPEC_CTAS : GE_W_CTAS(P8); }
 
 // Per-thread table of the 12 predicate field masks (SPEC.md section 2) in shared memory, laid out
 // [field][thread] (conflict-free).  Predicates index it dynamically; this replaced a switch over the field
@@ -1006,7 +1020,7 @@ __device__ __forceinline__ void w_tps_publish(const SlotArgs& A, const BlockCoun
 }
 
 template <int P8, class Spec = void, bool PK = false>
-__global__ void __launch_bounds__(TPS_THREADS, GE_W_CTAS(P8))
+__global__ void __launch_bounds__(TPS_THREADS, (w_step_ctas<P8, Spec, PK>()))
 k_step_w_tps(const __grid_constant__ DevTable T, const __grid_constant__ StepArgs A) {
     __shared__ WSmem<P8, 1> sm;
     extern __shared__ __align__(16) uint8_t dyn_smem[];       // sizeof(LightBulk) when the launch asked for STEP_LIGHT_BULK
