@@ -76,6 +76,14 @@ struct ge_batch {
     bool host_fused;              // ge_run_host[_async]: apply n_steps in one fused launch
     unsigned long long* h_hint;   // pinned, device-mapped {n_active, epoch}: stored by the compaction / regroup kernels
     unsigned long long* d_hint;   // the same words as the device sees them
+    // Learned check schedule: h_sched[c] = host epoch in which compaction check number c of an epoch last RAN,
+    // h_sched[64 + c] = in which it last FIRED (stored by k_compact_scan through the mapping).  Games of one table have the
+    // same length distribution in every epoch, so a check that did not fire the last time it was observed is not launched
+    // again until the periodic refresh epoch (want_check).  checks_seen = due checks since the last (re)initialisation.
+    uint32_t* h_sched;
+    uint32_t* d_sched;
+    uint32_t checks_seen;
+    bool sched_valid;             // the batch's sessions started their games together at the last (re)initialisation (not imported)
     unsigned long long epoch;     // bumped by every (re)initialisation; stale hints are ignored
     bool compacted;               // origin may differ from identity
     bool origin_iota;             // !compacted, and d_origin already holds the identity (written by k_reinit): no k_iota needed
@@ -490,6 +498,8 @@ static int init_sessions(ge_batch* b, uint64_t first_session_id, uint64_t seed) 
     b->compacted = false;
     b->origin_iota = false;
     b->since_compact = 0;
+    b->checks_seen = 0;
+    b->sched_valid = true;
     b->tile_valid = false;
     return GE_OK;
 }
@@ -512,6 +522,8 @@ extern "C" int ge_batch_reset(ge_batch* b, uint64_t first_session_id, uint64_t s
     b->compacted = false;
     b->origin_iota = true;
     b->since_compact = 0;
+    b->checks_seen = 0;
+    b->sched_valid = true;
     b->tile_valid = false;
     return GE_OK;
 }
@@ -551,7 +563,13 @@ extern "C" int ge_batch_create(ge_table* t, int device, uint64_t n_sessions, uin
     if (e == cudaSuccess) e = cudaMemset(b->d_live_mask, 0, mask_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_prefix, mask_words * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&b->d_cstate, 16 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaHostAlloc(&b->h_hint, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&b->h_hint, 2 * sizeof(unsigned long long) + 128 * sizeof(uint32_t), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&b->d_hint, b->h_hint, 0);
+    if (e == cudaSuccess) {
+        b->h_sched = reinterpret_cast<uint32_t*>(b->h_hint + 2);
+        b->d_sched = reinterpret_cast<uint32_t*>(b->d_hint + 2);
+        memset(b->h_sched, 0, 128 * sizeof(uint32_t));
+    }
     if (e == cudaSuccess) e = cudaHostAlloc(&b->h_err, 2 * sizeof(uint32_t), cudaHostAllocMapped);
     if (e == cudaSuccess) { b->h_err[0] = 0; b->h_err[1] = 0; }
     if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&b->d_err, b->h_err, 0);
@@ -719,6 +737,11 @@ extern "C" int ge_batch_set_compaction(ge_batch* b, int every_n_steps, int min_d
     if (every_n_steps > 0 && b->scan_blocks > 1024) return fail(GE_ERR_UNSUPPORTED, "compaction supports batches up to 2^25 sessions");
     b->compact_every = every_n_steps;
     b->dead_shift = min_dead_shift;
+    // the learned schedule belongs to a cadence and a threshold: start over (a check still in flight may log a stale entry,
+    // which the periodic refresh corrects)
+    memset(b->h_sched, 0, 128 * sizeof(uint32_t));
+    b->checks_seen = 0;
+    b->since_compact = 0;
     return GE_OK;
 }
 
@@ -808,7 +831,8 @@ extern "C" int ge_batch_get_kernel(const ge_batch* b) { return b ? b->kernel : G
 
 // scan -> rank -> swap -> commit on the live masks of the step that just ran, for a list of batches of one table in
 // ONE launch pair (all asynchronous, no host sync, no copies: the kernels store the host's progress hint themselves)
-static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st) {
+// (check_idx >= 0: the check's number inside the batch's epoch, logged for the learned schedule; -1 = not logged)
+static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st, int check_idx = -1) {
     CompactArgs ca;
     memset(&ca, 0, sizeof ca);
     ca.n = n;
@@ -826,7 +850,8 @@ static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st) {
             b->compacted = true;
             b->origin_iota = false;
         }
-        ca.s[i] = CompactSlot{b->d_tiles, b->d_origin, b->d_live_mask, b->d_prefix, b->d_blk, b->d_cstate, b->d_hint};
+        ca.s[i] = CompactSlot{b->d_tiles, b->d_origin, b->d_live_mask, b->d_prefix, b->d_blk, b->d_cstate, b->d_hint,
+                              check_idx >= 0 ? b->d_sched : nullptr, (uint32_t)(check_idx < 0 ? 0 : check_idx)};
         if (b->scan_blocks > max_scan) max_scan = b->scan_blocks;
         if (b->n_tiles > max_tiles) max_tiles = b->n_tiles;
         b->since_compact = 0;
@@ -852,6 +877,16 @@ static int enqueue_compaction(ge_batch** list, int n, cudaStream_t st) {
     }
     CU(cudaGetLastError());
     return GE_OK;
+}
+
+// Should compaction check number c of the batch's current epoch be launched?  Yes while nothing is known about it, on every
+// 8th epoch (refresh: the distribution may drift, a threshold may be crossed one check later), and when it FIRED the last
+// time it ran.  A check that would not fire changes nothing, so skipping it does not move the checks that do.
+static bool want_check(const ge_batch* b, int c) {
+    if (c < 0 || c >= 64) return true;
+    const uint32_t seen = ((volatile uint32_t*)b->h_sched)[c], fired = ((volatile uint32_t*)b->h_sched)[64 + c];
+    if (seen == 0 || (b->epoch & 7ull) == 0) return true;
+    return fired == seen;
 }
 
 // plan -> scatter -> copy back on the histogram of the counted step that just ran (all asynchronous, no host sync)
@@ -934,7 +969,13 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
             b->origin_iota = false;
         }
         const bool regroup_after = regroup && b->since_compact + 1 >= b->regroup_every;
-        const bool compact_after = !regroup && b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
+        const bool check_due = !regroup && b->compact_every > 0 && b->kernel != GE_KERNEL_COOP && b->since_compact + 1 >= b->compact_every;
+        // learned schedule: checks that did not fire the last time they ran are skipped (want_check); only batches whose
+        // epochs the host starts itself (no device-side auto-reset) and that are stepped one step per launch are scheduled
+        const bool scheduled = check_due && b->sched_valid && b->sid_stride == 0 && !b->d_hmask && steps_per_launch == 1;
+        const int check_idx = scheduled ? (int)b->checks_seen++ : -1;
+        const bool compact_after = check_due && (!scheduled || want_check(b, check_idx));
+        if (check_due && !compact_after) b->since_compact = -1;       // skipped: the cadence restarts with this launch
         fill_slot(b, a, compact_after || regroup_after, regroup);
         if (!tiled) { a.tile_present = nullptr; a.tile_present_out = nullptr; b->tile_valid = false; }
         // the bulk-copy variant of the light path stages its tiles in dynamic shared memory (werewolf single-batch kernels)
@@ -962,7 +1003,7 @@ static int launch_steps(ge_batch* b, int n_launches, int steps_per_launch, cudaS
             const int rc = enqueue_regroup(b, st);
             if (rc != GE_OK) return rc;
         } else if (compact_after) {
-            const int rc = enqueue_compaction(&b, 1, st);
+            const int rc = enqueue_compaction(&b, 1, st, check_idx);
             if (rc != GE_OK) return rc;
         }
         if ((regroup_after || compact_after) && b->sid_stride != 0) {      // every game over? start the next epoch on the device
@@ -1287,6 +1328,7 @@ static int restore_order(ge_batch* b, bool keep_records) {
     }
     b->compacted = false;
     b->origin_iota = false;
+    b->sched_valid = false;
     b->tile_valid = false;
     b->epoch++;
     k_cstate_reset<<<1, 32, 0, b->stream>>>(b->d_cstate, b->n, b->epoch, 1);
@@ -1311,6 +1353,7 @@ static int import_async(ge_batch* b, uint64_t first, uint64_t count, const void*
     if (whole) {
         b->compacted = false;
         b->origin_iota = false;
+        b->sched_valid = false;
         b->epoch++;
         b->since_compact = 0;
         R.cstate = b->d_cstate; R.epoch = b->epoch;

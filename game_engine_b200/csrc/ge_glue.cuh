@@ -467,6 +467,11 @@ struct CompactSlot {
     uint32_t* blk;
     unsigned long long* cstate;
     unsigned long long* hint;
+    // Check log (mapped host memory, NULL = not kept): the scan kernel stores the host epoch tag in sched[check_idx] whenever
+    // check number check_idx of an epoch RAN and in sched[64 + check_idx] when it also FIRED, so that the host can stop
+    // launching the checks that never fire (ge_capi.cu: want_check).
+    uint32_t* sched;
+    uint32_t check_idx;
 };
 struct CompactArgs {
     int n;
@@ -496,7 +501,10 @@ k_compact_scan(const __grid_constant__ CompactArgs CA) {
     const uint32_t nblk = (uint32_t)((nt + CS_TILES - 1) / CS_TILES);
     // every block takes the same decision from the same two words (nobody writes them in this kernel)
     if (live_now > n_act || ((n_act - live_now) << dead_shift) < n_act) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { cstate[1] = n_act; cstate[2] = 0; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            cstate[1] = n_act; cstate[2] = 0;
+            if (Q.sched && Q.check_idx < 64) ((volatile uint32_t*)Q.sched)[Q.check_idx] = (uint32_t)cstate[7];
+        }
         return;
     }
     if (blockIdx.x >= nblk) return;
@@ -527,6 +535,10 @@ k_compact_scan(const __grid_constant__ CompactArgs CA) {
             pairs = n_live - in_front;
         }
         cstate[0] = n_live; cstate[1] = n_live; cstate[2] = pairs; cstate[3] = in_front; cstate[4] = nt; cstate[6] = 0;
+        if (Q.sched && Q.check_idx < 64) {
+            ((volatile uint32_t*)Q.sched)[64 + Q.check_idx] = (uint32_t)cstate[7];
+            ((volatile uint32_t*)Q.sched)[Q.check_idx] = (uint32_t)cstate[7];
+        }
     }
 }
 

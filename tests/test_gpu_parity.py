@@ -423,3 +423,33 @@ def test_programmatic_dependent_launches_change_nothing(games, oracle_for, game,
         want = o.init(20000)
         o.step(want, f, seed, 45)
         np.testing.assert_array_equal(r.export_state(), want)
+
+
+def test_learned_compaction_schedule_and_progress_hint(games, oracle_for):
+    """Compaction checks that did not fire in an earlier epoch are not launched again (the host learns the schedule from a
+    log the scan kernel keeps in mapped memory); results never depend on when compaction happens.  The same mapping
+    carries the progress hint: an upper bound of the live prefix that only decreases, 0 once every game is over."""
+    cg = games(WEREWOLF, 8)
+    o = oracle_for(cg)
+    n, seed, cap = 1 << 15, 17, 56
+    t, b = _batch(cg, n, 0, seed, "tps")
+    b.set_compaction(5, 2)
+    launches = []
+    for epoch in range(1, 8):
+        first = epoch * n
+        b.reset(first_session_id=first)
+        l0 = b.launch_count()
+        hints = []
+        for _ in range(cap // 4):
+            b.step(4)
+            b.sync()
+            hints.append(b.active_hint())
+        launches.append(b.launch_count() - l0)
+        rec = o.init(n)
+        o.step(rec, first, seed, 4 * (cap // 4))
+        np.testing.assert_array_equal(b.export_state(), rec)
+        assert all(x >= y for x, y in zip(hints, hints[1:])) and hints[0] <= n and hints[-1] < n // 4, hints
+    # the first epoch runs all 11 checks (two launches each), later ones only those that fired; every 8th epoch of the
+    # batch observes all of them again (refresh)
+    assert launches[0] >= 56 + 2 * 11 and max(launches[1:-1]) <= 56 + 2 * 6 + 2 and launches[-1] == launches[0], launches
+    assert b.active() < n // 4
