@@ -656,9 +656,14 @@ def run_ours(a):
         e2e_stream(2, cap, rin)                               # warm-up
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        e_counted = e2e_stream(a.e2e_calls, cap, rin)
-        dt = time.perf_counter() - t0
+        # three repeats of the timed stream of calls, the MEDIAN is reported (host-side jitter moves a 20 ms measurement by
+        # +-7 % from one repeat to the next on the pool's boxes); all three are listed in e2e.repeats
+        reps = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            e_counted = e2e_stream(a.e2e_calls, cap, rin)
+            reps.append((time.perf_counter() - t0, e_counted))
+        dt, e_counted = sorted(reps)[1]
         tl = time.perf_counter()
         e2e_stream(1, cap, rin)                               # one isolated call: latency, pipeline fill and drain exposed
         lat_ms = (time.perf_counter() - tl) * 1e3
@@ -688,6 +693,7 @@ def run_ours(a):
                     "%d steps -> records + stats out for %d sessions in %d pipelined sub-batches; one sync at the end; bytes "
                     "are per call" % (a.e2e_calls, NSUB, cap, NE, NSUB),
             "calls": a.e2e_calls, "ms_per_call": dt / a.e2e_calls * 1e3, "single_call_latency_ms": lat_ms,
+            "repeats": {"values": [c / t for t, c in reps], "reported": "median of 3 (this rank)"},
             "statistics_only_output": {"value": so_counted / dts, "unit": UNIT, "ms_per_call": dts / a.e2e_calls * 1e3,
                                        "d2h_bytes_per_step": NSUB * 560 * 8,
                                        "note": "the same call with records_out = NULL: records in, the statistics (win rates, histograms) out"},
