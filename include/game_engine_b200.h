@@ -118,7 +118,11 @@ int ge_batch_set_kernel(ge_batch *b, int kernel);
  * are swapped in front of them (on the device, no host sync) so later launches walk only the live prefix.
  * Session ids, export order and statistics are unaffected.  every_n_steps = 0 turns it off; default (5, 2) for the
  * werewolf family and off for the TTL family (fixed-length games: nothing to compact).
- * ge_batch_active returns the current prefix length (synchronises). */
+ * A batch that is re-initialised epoch after epoch (ge_batch_reset) learns which of an epoch's checks fire — the check kernel
+ * logs it through mapped host memory — and stops launching the ones that do not (every 8th epoch observes all of them again);
+ * results never depend on when compaction happens.  Calling this function forgets the learned schedule.
+ * ge_batch_active returns the current prefix length (synchronises); ge_batch_active_hint the value of the most recent
+ * completed check without synchronising. */
 int ge_batch_set_compaction(ge_batch *b, int every_n_steps, int min_dead_shift);
 int ge_batch_active(ge_batch *b, uint64_t *out);
 /* Launch geometry: the step kernels run a persistent grid of (SM count x ctas_per_sm) CTAs of 128 threads, by
