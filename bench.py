@@ -42,10 +42,10 @@ def game_cap(family: int, players: int, max_revotes: int = 0) -> int:
 # BASELINE.json configs[1..4] ("config 2..5" in BASELINE.md section 4).  `total` sessions are sharded over the ranks; each
 # rank keeps a ring of R independent replicas of its shard (different session ids) so that its inputs come from HBM.
 CONFIGS = {
-    # (ring of 16 batches on 8 streams: stream j steps batches j and j + 8, which are half a game cycle apart, so every stream
-    # carries about the same work in any window of passes — a short timed run (K = 20) is then 320 launches / 2.2 ms and
-    # reads 7.2e10 instead of 6.8e10 with a ring of 8; the long-run value is the same within 1 %)
-    2: dict(game="werewolf-(mafia)", players=8, total=None, sessions=1 << 20, ring=16, streams=8, ctas_per_sm=3),
+    # (ring of 16 batches, one stream each: a short timed run (K = 20) is then 320 launches / 2.2 ms and the streams that run
+    # out of work early in such a window are a smaller share of the machine — 7.3e10 instead of 6.8e10 with a ring of 8 on 8
+    # streams; the long-run value is the same within 1 %: 7.53e10 against 7.56e10.  16 batches on 8 streams: 7.17 / 7.48e10)
+    2: dict(game="werewolf-(mafia)", players=8, total=None, sessions=1 << 20, ring=16, streams=16, ctas_per_sm=3),
     3: dict(game="werewolf-(mafia)", players=16, total=1 << 24, ring=4, streams=4, ctas_per_sm=3),
     4: dict(game="werewolf-revote", players=32, total=1 << 26, ring=1, streams=1, ctas_per_sm=0),
     5: dict(game="two-truths-and-a-lie", players=4, total=1 << 28, ring=2, streams=2, ctas_per_sm=0),
