@@ -568,24 +568,43 @@ __global__ void k_compact_swap(const __grid_constant__ CompactArgs CA) {
     if (pairs == 0) return;
     const uint32_t n16 = S / 16;
     const bool half = (S % 16) != 0;
-    const uint64_t tb = n_live >> 5;
-    const uint32_t lb = (uint32_t)(n_live & 31);
-    auto P = [&](uint64_t t) -> uint64_t { return (uint64_t)blk[t / CS_TILES] + loc[t]; };
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t lo = 0, hi = tb;                                // front: largest t in [0, tb] with 32t - P(t) <= i
+    // Compaction covers batches up to 2^25 sessions (ge_batch_set_compaction), so slots, tiles and counts fit 32 bits.  Both
+    // searches are two-level like the prefix itself: first the scan block (blk[], at most a few dozen entries that stay in
+    // L1), then the tile inside it with the block's base hoisted — one load and 32-bit arithmetic per probe instead of two
+    // loads and 64-bit arithmetic (the swap was 38 % of a step launch's warp-instructions per firing check, ncu).
+    const uint32_t n_live32 = (uint32_t)n_live, pairs32 = (uint32_t)pairs, in_front32 = (uint32_t)in_front, nt32 = (uint32_t)nt;
+    const uint32_t tb = n_live32 >> 5, lb = n_live32 & 31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < pairs32; i += gridDim.x * blockDim.x) {
+        // front: largest tile t in [0, tb] with D(t) = 32 t - P(t) <= i  (terminal sessions before tile t)
+        uint32_t lo = 0, hi = tb / CS_TILES;
         while (lo < hi) {
-            const uint64_t mid = (lo + hi + 1) >> 1;
-            if (32 * mid - P(mid) <= i) lo = mid; else hi = mid - 1;
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (mid * (32u * CS_TILES) - blk[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        uint32_t base = blk[lo];
+        hi = min(tb, lo * CS_TILES + (CS_TILES - 1));
+        lo = lo * CS_TILES;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (32u * mid - base - loc[mid] <= i) lo = mid; else hi = mid - 1;
         }
         const uint32_t valid_a = lo == tb ? ((1u << lb) - 1u) : 0xFFFFFFFFu;
-        const uint32_t a = (uint32_t)(32 * lo) + (uint32_t)kth_set_bit<32>(~live_mask[lo] & valid_a, (uint32_t)(i - (32 * lo - P(lo))));
-        const uint64_t r = in_front + i;                          // back: largest t in [tb, nt-1] with P(t) <= r
-        lo = tb; hi = nt - 1;
+        const uint32_t a = 32u * lo + (uint32_t)kth_set_bit<32>(~live_mask[lo] & valid_a, i - (32u * lo - base - loc[lo]));
+        // back: largest tile t in [tb, nt - 1] with P(t) <= r  (live sessions before tile t)
+        const uint32_t r = in_front32 + i;
+        lo = tb / CS_TILES; hi = (nt32 - 1) / CS_TILES;
         while (lo < hi) {
-            const uint64_t mid = (lo + hi + 1) >> 1;
-            if (P(mid) <= r) lo = mid; else hi = mid - 1;
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (blk[mid] <= r) lo = mid; else hi = mid - 1;
         }
-        const uint32_t b = (uint32_t)(32 * lo) + (uint32_t)kth_set_bit<32>(live_mask[lo], (uint32_t)(r - P(lo)));
+        base = blk[lo];
+        hi = min(nt32 - 1, lo * CS_TILES + (CS_TILES - 1));
+        lo = max(tb, lo * CS_TILES);
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (base + loc[mid] <= r) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t b = 32u * lo + (uint32_t)kth_set_bit<32>(live_mask[lo], r - (base + loc[lo]));
         uint8_t* ba = tiles + (uint64_t)(a >> 5) * (32ull * S);
         uint8_t* bb = tiles + (uint64_t)(b >> 5) * (32ull * S);
         for (uint32_t c = 0; c < n16; ++c) {
