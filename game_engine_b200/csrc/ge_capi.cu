@@ -2,8 +2,9 @@
 //
 // Host-side runtime in C++: table validation, session-store allocation, launch geometry and the
 // glue kernels (init / import / export / statistics).  The step kernels live in ge_step_tps.cuh
-// (thread per session) and ge_step_coop.cuh (lane per player).  No CPU fallback exists: every
-// compute entry point needs a CUDA device.
+// (thread per session) and ge_step_coop.cuh (lane per player) and are instantiated in their own translation
+// units (ge_k_generic.cu, ge_k_spec.cu; registry: ge_kernels.h).  No CPU fallback exists: every compute entry
+// point needs a CUDA device.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

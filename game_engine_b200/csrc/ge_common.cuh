@@ -6,6 +6,8 @@
 // sessions of the tile:   tile_base + c*512 + lane*16   (trailing column: tile_base + N16*512 + lane*8).
 // A warp that owns one tile therefore reads/writes every column with one fully coalesced 128-bit
 // (or 64-bit) access per lane: 512 contiguous bytes per instruction, no padding bytes moved.
+// Werewolf tables up to 8 / 16 players keep the PACKED record instead (the 32 / 48 bytes of the dense wire format, two /
+// three 16-byte columns, same tile addressing; ge_step_tps.cuh, ge_capi.cu ensure_store).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
